@@ -1,0 +1,451 @@
+// api.cu -- the C-ABI of libedgpu (include/edgpu.h): context, Hamiltonian, sectors, vectors, H*v entry points.
+#include "edgpu_internal.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+uint64_t edgpu_binom(int n, int k);
+int sector_map_kernel(edgpu_sector *s, int64_t first, int64_t count, uint64_t *d_out);
+int sector_map_check_kernel(edgpu_sector *s, unsigned long long *d_sum, unsigned long long *d_viol);
+int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst);
+int vec_fill_normal(edgpu_sector *s, uint64_t seed, double *dst);
+int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
+int csr_build(edgpu_sector *s);
+int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
+
+static thread_local std::string g_null_err;
+
+int edgpu_fail(edgpu_ctx *ctx, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_null_err = buf;
+    return 1;
+}
+
+CsrMatrix::~CsrMatrix() { cudaFree(rowptr); cudaFree(cols); cudaFree(rowlen); cudaFree(vals); }
+
+extern "C" const char *edgpu_last_error(const edgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_null_err.c_str(); }
+extern "C" int edgpu_version(void) { return EDGPU_VERSION; }
+extern "C" int edgpu_ns(const edgpu_ctx *ctx) { return ctx ? ctx->ham.ns : -1; }
+
+extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu_ctx **out)
+{
+    if (!p || !out) return edgpu_fail(nullptr, "edgpu_init: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return edgpu_fail(nullptr, "edgpu_init: no CUDA device available (%s); this library has no CPU fallback",
+                          e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (p->norb < 1 || p->norb > EDGPU_MAXORB || p->nbath < 1 || p->nspin < 1 || p->nspin > 2)
+        return edgpu_fail(nullptr, "edgpu_init: bad shape norb=%d nbath=%d nspin=%d", p->norb, p->nbath, p->nspin);
+    edgpu_ctx *ctx = new edgpu_ctx();
+    ctx->par = *p;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: cudaSetDevice(%d) failed", device); }
+    ctx->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: cudaGetDeviceProperties failed"); }
+    if (prop.major < 10) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: device sm_%d%d is not Blackwell (sm_100a build)", prop.major, prop.minor); }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = prop.l2CacheSize;
+    ctx->mem_bytes = (int64_t)prop.totalGlobalMem;
+    HamParams &h = ctx->ham;
+    h.norb = p->norb; h.nbath = p->nbath; h.nspin = p->nspin; h.hfmode = p->hfmode;
+    h.ns = (p->nbath + 1) * p->norb;                                    // ED_SETUP.f90:99-101
+    if (h.ns > 24) { const int nsbad = h.ns; delete ctx; return edgpu_fail(nullptr, "edgpu_init: Ns=%d > 24 unsupported", nsbad); }
+    h.e.assign((size_t)h.nspin * h.norb * h.nbath, 0.0);
+    h.v.assign((size_t)h.nspin * h.norb * h.nbath, 0.0);
+    h.hloc.assign((size_t)h.nspin * h.norb * h.norb, 0.0);
+    const size_t nscal = 8 + 2 * 4096;
+    if (cudaMalloc(&ctx->d_partials, sizeof(double) * kRedBlocks * 4) != cudaSuccess ||
+        cudaMalloc(&ctx->d_scal, sizeof(double) * nscal) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_scal, sizeof(double) * 64) != cudaSuccess) {
+        delete ctx;
+        return edgpu_fail(nullptr, "edgpu_init: scratch allocation failed");
+    }
+    cudaMemset(ctx->d_scal, 0, sizeof(double) * nscal);
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int edgpu_finalize(edgpu_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->bases.clear();
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int edgpu_device_info(edgpu_ctx *ctx, int32_t *sm_count, int64_t *l2_bytes, int64_t *mem_bytes)
+{
+    if (!ctx) return 1;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return 0;
+}
+
+extern "C" int edgpu_sync(edgpu_ctx *ctx)
+{
+    if (!ctx) return 1;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int edgpu_set_hamiltonian(edgpu_ctx *ctx, const double *bath, int32_t bath_len, const double *hloc_cplx,
+                                     const double *uloc, double ust, double jh, double jx, double jp, double xmu)
+{
+    if (!ctx || !bath || !uloc) return ctx ? edgpu_fail(ctx, "edgpu_set_hamiltonian: null argument") : 1;
+    HamParams &h = ctx->ham;
+    const int nb = h.nspin * h.norb * h.nbath;
+    // check_bath_dimension (ED_MAIN.f90:257-258): normal bath, normal mode = 2*Nspin*Norb*Nbath
+    if (bath_len != 2 * nb) return edgpu_fail(ctx, "ED_SOLVE_SINGLE Error: wrong bath dimensions (%d, expected %d)", bath_len, 2 * nb);
+    for (int i = 0; i < nb; i++) { h.e[i] = bath[i]; h.v[i] = bath[nb + i]; }    // dmft_aux.f90:494-511
+    std::fill(h.hloc.begin(), h.hloc.end(), 0.0);
+    if (hloc_cplx) {
+        for (int is = 0; is < h.nspin; is++)
+            for (int js = 0; js < h.nspin; js++)
+                for (int a = 0; a < h.norb; a++)
+                    for (int b = 0; b < h.norb; b++) {
+                        const size_t idx = (size_t)is + h.nspin * ((size_t)js + h.nspin * ((size_t)a + h.norb * (size_t)b));
+                        const double re = hloc_cplx[2 * idx], im = hloc_cplx[2 * idx + 1];
+                        if (im != 0.0) return edgpu_fail(ctx, "edgpu_set_hamiltonian: complex impHloc is not supported on the GPU path");
+                        if (is != js && re != 0.0) return edgpu_fail(ctx, "edgpu_set_hamiltonian: spin-mixing impHloc needs ed_mode=nonsu2 (unsupported)");
+                        if (is == js) h.hloc[(size_t)(is * h.norb + a) * h.norb + b] = re;
+                    }
+    }
+    for (int a = 0; a < EDGPU_MAXORB; a++) h.uloc[a] = a < h.norb ? uloc[a] : 0.0;
+    h.ust = ust; h.jh = jh; h.jx = jx; h.jp = jp; h.xmu = xmu;
+    h.jhflag = (h.norb > 1) && (jx != 0.0 || jp != 0.0);                     // ED_SETUP.f90:289-290
+    h.version++;
+    ctx->bases.clear();                                                        // tables depend on the parameters
+    return upload_xtab(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int edgpu_sector_build(edgpu_ctx *ctx, int32_t nup, int32_t ndw, edgpu_sector **out)
+{
+    if (!ctx || !out) return ctx ? edgpu_fail(ctx, "edgpu_sector_build: null argument") : 1;
+    *out = nullptr;
+    const HamParams &h = ctx->ham;
+    if (h.version == 0) return edgpu_fail(ctx, "edgpu_sector_build: Hamiltonian not set");
+    if (nup < 0 || nup > h.ns || ndw < 0 || ndw > h.ns) return edgpu_fail(ctx, "edgpu_sector_build: (nup,ndw)=(%d,%d) outside 0..%d", nup, ndw, h.ns);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    auto s = new edgpu_sector();
+    s->ctx = ctx; s->nup = nup; s->ndw = ndw;
+    if (int rc = build_spin_basis(ctx, 0, nup, s->up)) { delete s; return rc; }
+    if (int rc = build_spin_basis(ctx, h.nspin - 1, ndw, s->dw)) { delete s; return rc; }    // DW uses index Nspin (HxVbath.f90:8-9)
+    s->dim_up = s->up->dim; s->dim_dw = s->dw->dim;
+    s->dim = s->dim_up * s->dim_dw;                                           // ED_SETUP.f90:818-830
+    s->ld = s->dim_up;
+    if (s->up->layout == 2) s->ld = (s->dim_up + 3) / 4 * 4;                  // 32-byte aligned rows for the tiled kernels
+    s->nalloc = s->dim_dw * s->ld;
+    *out = s;
+    return 0;
+}
+
+extern "C" int edgpu_sector_free(edgpu_sector *s)
+{
+    if (!s) return 0;
+    cudaStreamSynchronize(s->ctx->stream);
+    for (int i = 0; i < 3; i++) cudaFree(s->work[i]);
+    delete s;
+    return 0;
+}
+
+extern "C" int edgpu_sector_dim(const edgpu_sector *s, int64_t *dim, int64_t *dim_up, int64_t *dim_dw)
+{
+    if (!s) return 1;
+    if (dim) *dim = s->dim;
+    if (dim_up) *dim_up = s->dim_up;
+    if (dim_dw) *dim_dw = s->dim_dw;
+    return 0;
+}
+
+extern "C" int edgpu_sector_map(const edgpu_sector *s, int64_t first, int64_t count, uint64_t *host_out)
+{
+    if (!s || !host_out) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (first < 0 || count < 0 || first + count > s->dim) return edgpu_fail(ctx, "edgpu_sector_map: range outside the sector");
+    const int64_t chunk = 1 << 24;
+    uint64_t *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(uint64_t) * (size_t)(count < chunk ? (count > 0 ? count : 1) : chunk)));
+    for (int64_t off = 0; off < count; off += chunk) {
+        const int64_t c = (count - off) < chunk ? (count - off) : chunk;
+        if (int rc = sector_map_kernel(const_cast<edgpu_sector *>(s), first + off, c, d)) { cudaFree(d); return rc; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(host_out + off, d, sizeof(uint64_t) * (size_t)c, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int edgpu_sector_map_check(const edgpu_sector *s, uint64_t *checksum, int64_t *violations)
+{
+    if (!s) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (int rc = sector_map_check_kernel(const_cast<edgpu_sector *>(s), d, d + 1)) { cudaFree(d); return rc; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    if (checksum) *checksum = h[0];
+    if (violations) *violations = (int64_t)h[1];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int edgpu_vec_alloc(edgpu_sector *s, edgpu_vec **out)
+{
+    if (!s || !out) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    auto v = new edgpu_vec();
+    v->s = s;
+    cudaError_t e = cudaMalloc(&v->d, sizeof(double) * (size_t)s->nalloc);
+    if (e != cudaSuccess) { delete v; return edgpu_fail(ctx, "edgpu_vec_alloc: cudaMalloc of %lld doubles failed: %s", (long long)s->nalloc, cudaGetErrorString(e)); }
+    CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)s->nalloc, ctx->stream));
+    *out = v;
+    return 0;
+}
+
+extern "C" int edgpu_vec_free(edgpu_vec *v)
+{
+    if (!v) return 0;
+    cudaStreamSynchronize(v->s->ctx->stream);
+    cudaFree(v->d);
+    delete v;
+    return 0;
+}
+
+// Staging buffer in the reference order (real or interleaved complex), then a conversion kernel.
+static int stage_alloc(edgpu_ctx *ctx, size_t bytes, double **p)
+{
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return edgpu_fail(ctx, "staging cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cplx)
+{
+    if (!v || !host) return 1;
+    edgpu_sector *s = v->s;
+    edgpu_ctx *ctx = s->ctx;
+    const size_t bytes = sizeof(double) * (size_t)s->dim * (is_cplx ? 2 : 1);
+    if (!is_cplx && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {     // reference layout: direct copy
+        CUDA_TRY(ctx, cudaMemcpyAsync(v->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    double *stage = nullptr;
+    if (int rc = stage_alloc(ctx, bytes, &stage)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = vec_convert(s, is_cplx ? 1 : 0, stage, v->d);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_cplx)
+{
+    if (!v || !host) return 1;
+    edgpu_sector *s = v->s;
+    edgpu_ctx *ctx = s->ctx;
+    const size_t bytes = sizeof(double) * (size_t)s->dim * (is_cplx ? 2 : 1);
+    if (!is_cplx && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, v->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    double *stage = nullptr;
+    if (int rc = stage_alloc(ctx, bytes, &stage)) return rc;
+    int rc = vec_convert(s, is_cplx ? 3 : 2, v->d, stage);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_vec_download: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+extern "C" int edgpu_vec_fill_normal(edgpu_vec *v, uint64_t seed)
+{
+    if (!v) return 1;
+    return vec_fill_normal(v->s, seed, v->d);
+}
+
+extern "C" int edgpu_vec_copy(edgpu_vec *dst, const edgpu_vec *src)
+{
+    if (!dst || !src || dst->s->nalloc != src->s->nalloc) return 1;
+    CUDA_TRY(dst->s->ctx, cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (size_t)dst->s->nalloc, cudaMemcpyDeviceToDevice, dst->s->ctx->stream));
+    return 0;
+}
+
+extern "C" int edgpu_vec_dot(const edgpu_vec *a, const edgpu_vec *b, double *out)
+{
+    if (!a || !b || !out || a->s->nalloc != b->s->nalloc) return 1;
+    edgpu_ctx *ctx = a->s->ctx;
+    if (int rc = vec_dot(ctx, a->d, b->d, a->s->nalloc, ctx->d_scal)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_scal[0];
+    return 0;
+}
+
+extern "C" int edgpu_vec_scale(edgpu_vec *a, double alpha)
+{
+    if (!a) return 1;
+    return vec_scale(a->s->ctx, a->d, alpha, a->s->nalloc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int hxv_dispatch(edgpu_sector *s, const double *x, double *y)
+{
+    if (s->csr) return hxv_csr(s, x, y);
+    if (s->up->layout == 2 && s->ctx->par.hxv_kernel != 1 && !s->ctx->ham.jhflag) return hxv_star(s, x, y);
+    return hxv_generic(s, x, y);
+}
+
+extern "C" int edgpu_hxv_dev(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y)
+{
+    if (!s || !x || !y || x->s != s || y->s != s) return s ? edgpu_fail(s->ctx, "edgpu_hxv_dev: vectors do not belong to the sector") : 1;
+    if (x->d == y->d) return edgpu_fail(s->ctx, "edgpu_hxv_dev: in-place product is not allowed");
+    return hxv_dispatch(s, x->d, y->d);
+}
+
+extern "C" int edgpu_hxv(edgpu_sector *s, int64_t nloc, const double *v_cplx, double *hv_cplx)
+{
+    if (!s || !v_cplx || !hv_cplx) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (nloc != s->dim) return edgpu_fail(ctx, "directMatVec_cc ERROR: Nloc != dim(isector)");     // DIRECT_HxV.f90:50
+    double *stage = nullptr, *xr, *xi, *yr;
+    const size_t cb = sizeof(double) * 2 * (size_t)s->dim;
+    if (int rc = stage_alloc(ctx, cb, &stage)) return rc;
+    if (int rc = sector_work(s, 0, &xr)) return rc;
+    if (int rc = sector_work(s, 1, &xi)) return rc;
+    if (int rc = sector_work(s, 2, &yr)) return rc;
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(stage, v_cplx, cb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = edgpu_fail(ctx, "edgpu_hxv: H2D failed"); break; }
+        if ((rc = vec_convert(s, 1, stage, xr))) break;
+        if ((rc = vec_convert(s, 4, stage, xi))) break;
+        if ((rc = hxv_dispatch(s, xr, yr))) break;                 // H is real: act on Re and Im separately
+        if ((rc = vec_convert(s, 3, yr, stage))) break;
+        if ((rc = hxv_dispatch(s, xi, yr))) break;
+        if ((rc = vec_convert(s, 5, yr, stage))) break;
+        if (cudaMemcpyAsync(hv_cplx, stage, cb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = edgpu_fail(ctx, "edgpu_hxv: D2H failed"); break; }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (!rc && e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_hxv: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int edgpu_sector_dense(edgpu_sector *s, double *hmat)
+{
+    if (!s || !hmat) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (s->dim > 4096) return edgpu_fail(ctx, "edgpu_sector_dense: dim=%lld too large", (long long)s->dim);
+    const int64_t n = s->dim;
+    double *x, *y, *yr;
+    if (int rc = sector_work(s, 0, &x)) return rc;
+    if (int rc = sector_work(s, 1, &y)) return rc;
+    if (int rc = sector_work(s, 2, &yr)) return rc;
+    std::vector<double> col(n, 0.0);
+    for (int64_t j = 0; j < n; j++) {
+        // unit vector e_j in the reference order -> internal layout
+        std::fill(col.begin(), col.end(), 0.0);
+        col[j] = 1.0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(yr, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(x, 0, sizeof(double) * (size_t)s->nalloc, ctx->stream));
+        if (int rc = vec_convert(s, 0, yr, x)) return rc;
+        if (int rc = hxv_dispatch(s, x, y)) return rc;
+        if (int rc = vec_convert(s, 2, y, yr)) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(hmat + j * n, yr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_flush(double *p, int64_t n, double v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+extern "C" int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y, int32_t iters, int32_t flush_l2,
+                               double *ms_avg, int64_t *launches)
+{
+    if (!s || !x || !y || iters < 1) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (flush_l2 && !ctx->d_flush) {
+        ctx->flush_bytes = (size_t)(ctx->l2_bytes > 0 ? ctx->l2_bytes : (128ll << 20)) * 2;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    }
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    double total = 0.0;
+    int rc = 0;
+    if (flush_l2) {
+        for (int i = 0; i < iters && !rc; i++) {
+            k_flush<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((double *)ctx->d_flush, (int64_t)(ctx->flush_bytes / 8), (double)i);
+            cudaEventRecord(e0, ctx->stream);
+            rc = hxv_dispatch(s, x->d, y->d);
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            total += ms;
+        }
+    } else {
+        cudaEventRecord(e0, ctx->stream);
+        for (int i = 0; i < iters && !rc; i++) rc = hxv_dispatch(s, x->d, y->d);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (ms_avg) *ms_avg = total / iters;
+    if (launches) {
+        int per = 1;
+        if (s->csr) per = 1;
+        else if (s->up->layout == 2 && ctx->par.hxv_kernel != 1 && !ctx->ham.jhflag) per = 2;
+        else per = 1 + (ctx->ham.jhflag ? 1 : 0);
+        *launches = (int64_t)per * iters;
+    }
+    return 0;
+}
+
+// ---- CSR entry points (csr.cu) ----------------------------------------------------------------------------
+extern "C" int edgpu_sector_build_csr(edgpu_sector *s) { return s ? csr_build(s) : 1; }
+extern "C" int edgpu_sector_drop_csr(edgpu_sector *s) { if (!s) return 1; cudaStreamSynchronize(s->ctx->stream); s->csr.reset(); return 0; }
+extern "C" int edgpu_sector_csr_nnz(const edgpu_sector *s, int64_t *nnz)
+{
+    if (!s || !s->csr || !nnz) return s ? edgpu_fail(s->ctx, "edgpu_sector_csr_nnz: CSR not built") : 1;
+    *nnz = s->csr->nnz_true;
+    return 0;
+}
+extern "C" int edgpu_sector_csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals)
+{
+    if (!s || !s->csr) return s ? edgpu_fail(s->ctx, "edgpu_sector_csr_download: CSR not built") : 1;
+    return csr_download(s, rowptr, cols, vals);
+}

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Builds libedgpu.so (sm_100a) in-tree: dmft-ed_b200/libedgpu.so
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall"
+SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
+mkdir -p ../build
+OBJS=""
+for f in $SRCS; do
+  [ -f "$f" ] || continue
+  o=../build/$(basename ${f%.*}).o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ edgpu_internal.h -nt "$o" ] || [ ../../include/edgpu.h -nt "$o" ] || [ -f host/ed_host.h -a host/ed_host.h -nt "$o" ] || [ ../../include/ed_b200.h -nt "$o" ]; then
+    echo "nvcc $f"
+    $NVCC $FLAGS ${EXTRA_FLAGS} -x cu -c "$f" -o "$o" &
+  fi
+  OBJS="$OBJS $o"
+done
+wait
+$NVCC -shared -o ../libedgpu.so $OBJS -lcudart
+echo "built $(cd ..; pwd)/libedgpu.so"

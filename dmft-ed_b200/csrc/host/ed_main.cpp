@@ -1,0 +1,643 @@
+// ed_main.cpp -- host-side mirror of the reference solver phases that drive the Lanczos hot path.
+//
+// Mirrors (file:line relative to the reference root):
+//   ed_init_solver / ed_solve            ED_MAIN.f90:61-101, 253-282
+//   ed_diag_c / ed_post_diag             ED_DIAG.f90:49-251, 383-416
+//   build_gf_normal / lanc_build_gf_normal_c / add_to_lanczos_gf_normal / build_sigma_normal
+//                                        ED_GF_NORMAL.f90:18-31, 116-260, 580-632, 656-694
+//   observables_impurity (normal core)   ED_OBSERVABLES.f90:105-162
+//   delta_bath / invg0_bath              ED_BATH_FUNCTIONS.f90:221-258, 1784-1807
+//   init_dmft_bath                       ED_BATH/dmft_aux.f90:105-127
+//   allocate_grids                       ED_AUX_FUNX.f90:449-461
+// Everything heavy goes through the C-ABI of include/edgpu.h (device kernels); only O(nlanc*L) pole sums, the
+// tiny dense/tridiagonal eigenproblems and bookkeeping run on the host, as in the reference.
+#include "../../../include/ed_b200.h"
+#include "../../../include/edgpu.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+int host_tql2(int n, double *d, double *e, double *z);
+
+typedef std::complex<double> cplx;
+
+struct EdState {
+    double e = 0;
+    int nup = 0, ndw = 0;
+    edgpu_sector *sec = nullptr;
+    edgpu_vec *vec = nullptr;
+};
+
+struct EdChain {
+    int iorb, ispin, isign, istate, nlanc, nused;
+    double norm2;
+    std::vector<double> alfa, beta;
+};
+
+struct ed_solver {
+    ed_input in;
+    edgpu_ctx *ctx = nullptr;
+    std::string err;
+    int Ns = 0;
+    std::vector<double> hloc;                 // complex interleaved (Nspin,Nspin,Norb,Norb)
+    std::vector<double> bath;
+    std::vector<EdState> states;
+    double zeta = 0, egs = 0;
+    std::map<std::pair<int, int>, double> sector_e;
+    std::vector<std::pair<int, int>> mask;
+    std::vector<EdChain> chains;
+    std::vector<double> wm, wr;
+    std::vector<cplx> Gmats, Greal, Smats, Sreal, G0mats, G0real;
+    std::vector<double> dens, dens_up, dens_dw, docc, magz, sz2, n2;
+    double s2tot = 0;
+    double timings[4] = {0, 0, 0, 0};
+};
+
+static int fail(ed_solver *s, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (s) s->err = buf;
+    return 1;
+}
+#define GPU_TRY(s, call)                                                               \
+    do {                                                                               \
+        if ((call) != 0) return fail((s), "%s", edgpu_last_error((s)->ctx));           \
+    } while (0)
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" void ed_input_defaults(ed_input *in)
+{
+    memset(in, 0, sizeof(*in));                 // ED_INPUT_VARS.f90:121-196
+    in->Norb = 1; in->Nbath = 6; in->Nspin = 1;
+    in->uloc[0] = 2.0;
+    in->beta = 1000.0; in->xmu = 0.0; in->hfmode = 1;
+    in->Lmats = 5000; in->Lreal = 5000;
+    in->wini = -5.0; in->wfin = 5.0; in->eps = 0.01;
+    in->gs_threshold = 1e-9; in->hwband = 2.0;
+    in->lanc_method = 0; in->lanc_nstates_sector = 6; in->lanc_nstates_total = 1;
+    in->lanc_niter = 512; in->lanc_ngfiter = 200; in->lanc_tolerance = 1e-12; in->lanc_dim_threshold = 256;
+    in->ed_twin = 0; in->ed_sparse_H = 1; in->ed_verbose = 3;
+}
+
+extern "C" int32_t ed_get_bath_dimension(const ed_input *in)
+{
+    return 2 * in->Nspin * in->Norb * in->Nbath;            // user_aux.f90:11-30 (normal/normal: e and v)
+}
+
+static void init_dmft_bath(const ed_input &in, double *bath)
+{
+    // ED_BATH/dmft_aux.f90:105-127 with ed_bath_noise_thr = 0
+    const int N = in.Nbath;
+    std::vector<double> e(N + 2, 0.0), v(N + 2, 0.0);
+    e[1] = -in.hwband;
+    e[N] = in.hwband;
+    const int Nh = N / 2;
+    if (N % 2 == 0 && N >= 4) {
+        const double de = in.hwband / std::max(Nh - 1, 1);
+        e[Nh] = -1e-3;
+        e[Nh + 1] = 1e-3;
+        for (int i = 2; i <= Nh - 1; i++) { e[i] = -in.hwband + (i - 1) * de; e[N - i + 1] = in.hwband - (i - 1) * de; }
+    } else if (N % 2 != 0 && N >= 3) {
+        const double de = in.hwband / Nh;
+        e[Nh + 1] = 0.0;
+        for (int i = 2; i <= Nh; i++) { e[i] = -in.hwband + (i - 1) * de; e[N - i + 1] = in.hwband - (i - 1) * de; }
+    }
+    for (int i = 1; i <= N; i++) v[i] = std::max(0.1, 1.0 / std::sqrt((double)N));
+    const int nb = in.Nspin * in.Norb * N;
+    for (int is = 0; is < in.Nspin; is++)
+        for (int io = 0; io < in.Norb; io++)
+            for (int k = 1; k <= N; k++) {
+                bath[(is * in.Norb + io) * N + (k - 1)] = e[k];
+                bath[nb + (is * in.Norb + io) * N + (k - 1)] = v[k];
+            }
+}
+
+extern "C" int ed_init_solver(const ed_input *in, int device, void *stream, double *bath, int32_t bath_len,
+                              const double *hloc_cplx, ed_solver **out)
+{
+    if (!in || !out) return 1;
+    *out = nullptr;
+    ed_solver *s = new ed_solver();
+    s->in = *in;
+    // ed_checks_global (ED_SETUP.f90:36-83), the subset relevant to ed_mode=normal
+    if (in->Nspin > 2) { delete s; return 1; }
+    if (in->lanc_method == 1 && (in->lanc_nstates_total > 1 || in->lanc_nstates_sector > 1)) {
+        fprintf(stderr, "ED ERROR: lanc_method==lanczos available only for lanc_nstates_total==1 and lanc_nstates_sector==1, T=0\n");
+        delete s;
+        return 1;
+    }
+    if (in->lanc_nstates_total > 1) { fprintf(stderr, "ED ERROR (GPU path): finite temperature (lanc_nstates_total>1) is not supported yet\n"); delete s; return 1; }
+    if (in->ed_twin) { fprintf(stderr, "ED ERROR (GPU path): ed_twin=T is not supported yet\n"); delete s; return 1; }
+    if (bath_len != ed_get_bath_dimension(in)) { fprintf(stderr, "ED ERROR: wrong bath dimensions\n"); delete s; return 1; }
+    s->Ns = (in->Nbath + 1) * in->Norb;
+    edgpu_params p;
+    memset(&p, 0, sizeof(p));
+    p.norb = in->Norb; p.nbath = in->Nbath; p.nspin = in->Nspin; p.hfmode = in->hfmode;
+    p.layout = in->gpu_layout; p.hxv_kernel = in->gpu_hxv_kernel;
+    if (edgpu_init(&p, device, stream, &s->ctx) != 0) {
+        fprintf(stderr, "ed_init_solver: %s\n", edgpu_last_error(nullptr));
+        delete s;
+        return 1;
+    }
+    const size_t nh = (size_t)in->Nspin * in->Nspin * in->Norb * in->Norb;
+    s->hloc.assign(2 * nh, 0.0);
+    if (hloc_cplx) memcpy(s->hloc.data(), hloc_cplx, sizeof(double) * 2 * nh);
+    if (bath) init_dmft_bath(*in, bath);
+    *out = s;
+    return 0;
+}
+
+static void free_states(ed_solver *s)
+{
+    std::vector<edgpu_sector *> secs;
+    for (auto &st : s->states) {
+        if (st.vec) edgpu_vec_free(st.vec);
+        if (st.sec && std::find(secs.begin(), secs.end(), st.sec) == secs.end()) secs.push_back(st.sec);
+    }
+    for (auto *q : secs) edgpu_sector_free(q);
+    s->states.clear();
+}
+
+extern "C" int ed_finalize_solver(ed_solver *s)
+{
+    if (!s) return 0;
+    free_states(s);
+    edgpu_finalize(s->ctx);
+    delete s;
+    return 0;
+}
+
+extern "C" const char *ed_last_error(const ed_solver *s) { return s ? s->err.c_str() : "null solver"; }
+
+extern "C" int ed_set_sectors_mask(ed_solver *s, const int32_t *pairs, int32_t n)
+{
+    if (!s) return 1;
+    s->mask.clear();
+    for (int i = 0; i < n; i++) s->mask.push_back({pairs[2 * i], pairs[2 * i + 1]});
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dense symmetric eigensolver: Householder tridiagonalisation + tql2 (LAPACK eigh in the reference)
+// ---------------------------------------------------------------------------------------------------------
+static void tred2(int n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e)
+{
+    // a: row-major n x n symmetric; on return a holds the orthogonal transformation Q (a[k*n+i] = Q_ki)
+    auto A = [&](int i, int j) -> double & { return a[(size_t)i * n + j]; };
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; k++) scale += std::fabs(A(i, k));
+            if (scale == 0.0) e[i] = A(i, l);
+            else {
+                for (int k = 0; k <= l; k++) { A(i, k) /= scale; h += A(i, k) * A(i, k); }
+                double f = A(i, l);
+                double g = (f >= 0.0) ? -std::sqrt(h) : std::sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                A(i, l) = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; j++) {
+                    A(j, i) = A(i, j) / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; k++) g += A(j, k) * A(i, k);
+                    for (int k = j + 1; k <= l; k++) g += A(k, j) * A(i, k);
+                    e[j] = g / h;
+                    f += e[j] * A(i, j);
+                }
+                const double hh = f / (h + h);
+                for (int j = 0; j <= l; j++) {
+                    f = A(i, j);
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; k++) A(j, k) -= (f * e[k] + g * A(i, k));
+                }
+            }
+        } else e[i] = A(i, l);
+        d[i] = h;
+    }
+    d[0] = 0.0;
+    e[0] = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= l; k++) g += A(i, k) * A(k, j);
+                for (int k = 0; k <= l; k++) A(k, j) -= g * A(k, i);
+            }
+        }
+        d[i] = A(i, i);
+        A(i, i) = 1.0;
+        for (int j = 0; j <= l; j++) A(j, i) = A(i, j) = 0.0;
+    }
+}
+
+extern "C" int ed_host_eigh(int32_t n, double *a_colmajor, double *w)
+{
+    if (n < 1) return 1;
+    if (n == 1) { w[0] = a_colmajor[0]; a_colmajor[0] = 1.0; return 0; }
+    std::vector<double> a((size_t)n * n), d(n), e(n), z((size_t)n * n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) a[(size_t)i * n + j] = 0.5 * (a_colmajor[i + (size_t)n * j] + a_colmajor[j + (size_t)n * i]);
+    tred2(n, a, d, e);
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < n; i++) z[k + (size_t)n * i] = a[(size_t)k * n + i];
+    int ierr = host_tql2(n, d.data(), e.data(), z.data());
+    if (ierr) return ierr;
+    memcpy(w, d.data(), sizeof(double) * n);
+    memcpy(a_colmajor, z.data(), sizeof(double) * (size_t)n * n);
+    return 0;
+}
+
+extern "C" int ed_host_eigh_tridiag(int32_t n, const double *diag, const double *sub, double *w, double *z)
+{
+    std::vector<double> e(n, 0.0);
+    for (int i = 0; i < n; i++) w[i] = diag[i];
+    for (int i = 1; i < n; i++) e[i] = sub[i];
+    for (size_t q = 0; q < (size_t)n * n; q++) z[q] = 0.0;
+    for (int i = 0; i < n; i++) z[i + (size_t)n * i] = 1.0;
+    return host_tql2(n, w, e.data(), z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ed_diag_c (ED_DIAG.f90:49-251), T=0
+// ---------------------------------------------------------------------------------------------------------
+static void insert_state(std::vector<EdState> &list, const EdState &st)
+{
+    // es_insert_state_c (ED_EIGENSPACE.f90:169-218): ordered list, new entry goes before the first c with e <= c%e
+    size_t pos = 0;
+    while (pos < list.size() && !(st.e <= list[pos].e)) pos++;
+    list.insert(list.begin() + pos, st);
+}
+
+static int ed_diag(ed_solver *s)
+{
+    const ed_input &in = s->in;
+    const int Ns = s->Ns;
+    free_states(s);
+    s->sector_e.clear();
+    double oldzero = 1000.0;
+    for (int nup = 0; nup <= Ns; nup++)
+        for (int ndw = 0; ndw <= Ns; ndw++) {                                  // isector order, ED_SETUP.f90:382-393
+            if (!s->mask.empty() && std::find(s->mask.begin(), s->mask.end(), std::make_pair(nup, ndw)) == s->mask.end()) continue;
+            edgpu_sector *sec = nullptr;
+            GPU_TRY(s, edgpu_sector_build(s->ctx, nup, ndw, &sec));
+            int64_t dim = 0;
+            edgpu_sector_dim(sec, &dim, nullptr, nullptr);
+            int64_t neigen, nitermax;
+            if (in.lanc_method == 1) { neigen = 1; nitermax = std::min<int64_t>(dim, in.lanc_niter); }      // :93-97
+            else { neigen = std::min<int64_t>(dim, std::min<int64_t>(dim, in.lanc_nstates_sector)); nitermax = std::min<int64_t>(dim, in.lanc_niter); }
+            bool lanc_solve = true;
+            if (neigen == dim) lanc_solve = false;                                                        // :100
+            if (dim <= std::max(in.lanc_dim_threshold, 1)) lanc_solve = false;                             // :101
+            std::vector<double> evals, H;
+            std::vector<edgpu_vec *> evecs;
+            int rc = 0;
+            auto need_vec = [&](size_t i) -> int {       // eigenvector i of a dense sector -> device handle
+                if (evecs[i]) return 0;
+                if (H.empty()) return 1;
+                if (edgpu_vec_alloc(sec, &evecs[i])) return 1;
+                return edgpu_vec_upload(evecs[i], H.data() + i * (size_t)dim, 0);
+            };
+            if (lanc_solve) {
+                if (in.ed_sparse_H) rc = edgpu_sector_build_csr(sec);                                      // ED_HAMILTONIAN.f90:85-92
+                edgpu_vec *v = nullptr;
+                if (!rc) rc = edgpu_vec_alloc(sec, &v);
+                if (!rc) rc = edgpu_vec_fill_normal(v, 1234567ull);       // start vector (reference: random_number)
+                double e0 = 0;
+                int nl = 0;
+                if (!rc) rc = edgpu_lanczos_gs(sec, v, (int)nitermax, in.lanc_tolerance, 10, &e0, &nl, nullptr, nullptr);
+                if (rc) { if (v) edgpu_vec_free(v); edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
+                // lanc_method=arpack asks for Neigen pairs; at T=0 only states within gs_threshold of the minimum are
+                // kept (:224-235), so the device solver returns the lowest pair (finite-T spectra: out of scope).
+                evals.push_back(e0);
+                evecs.push_back(v);
+                if (in.ed_sparse_H) edgpu_sector_drop_csr(sec);
+            } else {
+                H.assign((size_t)dim * dim, 0.0);
+                std::vector<double> w(dim);
+                rc = edgpu_sector_dense(sec, H.data());                                                   // :188-193
+                if (rc) { edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
+                if (ed_host_eigh((int)dim, H.data(), w.data())) { edgpu_sector_free(sec); return fail(s, "ed_diag: dense eigh failed"); }
+                for (int64_t i = 0; i < neigen; i++) { evals.push_back(w[i]); evecs.push_back(nullptr); }   // uploaded on demand
+            }
+            s->sector_e[{nup, ndw}] = evals.empty() ? 0.0 : evals[0];
+            bool used = false;
+            for (size_t i = 0; i < evals.size(); i++) {                                                   // :224-235
+                const double enemin = evals[i];
+                EdState st;
+                st.e = enemin; st.nup = nup; st.ndw = ndw; st.sec = sec;
+                const bool lower = enemin < oldzero - 10.0 * in.gs_threshold;
+                const bool degen = !lower && std::fabs(enemin - oldzero) <= in.gs_threshold;
+                if ((lower || degen) && need_vec(i)) return fail(s, "ed_diag: %s", edgpu_last_error(s->ctx));
+                st.vec = evecs[i];
+                if (lower) {
+                    oldzero = enemin;
+                    // es_free_espace: drop every stored state
+                    std::vector<edgpu_sector *> secs;
+                    for (auto &o : s->states) {
+                        if (o.vec) edgpu_vec_free(o.vec);
+                        if (o.sec != sec && std::find(secs.begin(), secs.end(), o.sec) == secs.end()) secs.push_back(o.sec);
+                    }
+                    for (auto *q : secs) edgpu_sector_free(q);
+                    s->states.clear();
+                    if (!st.vec) return fail(s, "ed_diag: internal error (missing eigenvector)");
+                    insert_state(s->states, st);
+                    used = true;
+                } else if (degen) {
+                    oldzero = std::min(oldzero, enemin);
+                    if (!st.vec) return fail(s, "ed_diag: internal error (missing eigenvector)");
+                    insert_state(s->states, st);
+                    used = true;
+                } else if (st.vec) {
+                    edgpu_vec_free(st.vec);
+                }
+            }
+            if (!used) edgpu_sector_free(sec);
+        }
+    if (s->states.empty()) return fail(s, "ed_diag: no state found");
+    // ed_post_diag (ED_DIAG.f90:403-416), T=0
+    s->egs = s->states[0].e;
+    for (auto &st : s->states) s->egs = std::min(s->egs, st.e);
+    s->zeta = (double)s->states.size();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Green's functions
+// ---------------------------------------------------------------------------------------------------------
+static inline size_t gidx(const ed_input &in, int ispin, int jspin, int iorb, int jorb, int i)
+{
+    // (Nspin,Nspin,Norb,Norb,L) column-major
+    return (size_t)ispin + in.Nspin * ((size_t)jspin + in.Nspin * ((size_t)iorb + in.Norb * ((size_t)jorb + (size_t)in.Norb * i)));
+}
+
+static void add_to_lanczos_gf(ed_solver *s, double vnorm2, double Ei, const std::vector<double> &alanc,
+                              const std::vector<double> &blanc, int isign, int iorb, int jorb, int ispin)
+{
+    // add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:580-632), T=0: pesoBZ = vnorm2/zeta_function
+    const ed_input &in = s->in;
+    const int nlanc = (int)alanc.size();
+    const double pesoBZ = vnorm2 / s->zeta;
+    std::vector<double> w(nlanc), Z((size_t)nlanc * nlanc);
+    ed_host_eigh_tridiag(nlanc, alanc.data(), blanc.data(), w.data(), Z.data());
+    for (int j = 0; j < nlanc; j++) {
+        const double de = w[j] - Ei;
+        const double peso = pesoBZ * Z[(size_t)nlanc * j] * Z[(size_t)nlanc * j];      // Z(1,j)^2
+        if (peso == 0.0) continue;
+        for (int i = 0; i < in.Lmats; i++)
+            s->Gmats[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(0.0, s->wm[i]) - (double)isign * de);
+        for (int i = 0; i < in.Lreal; i++)
+            s->Greal[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(s->wr[i], in.eps) - (double)isign * de);
+    }
+}
+
+static int build_gf(ed_solver *s)
+{
+    const ed_input &in = s->in;
+    const int Ns = s->Ns;
+    const size_t nblk = (size_t)in.Nspin * in.Nspin * in.Norb * in.Norb;
+    // allocate_grids (ED_AUX_FUNX.f90:449-461)
+    s->wm.resize(in.Lmats);
+    s->wr.resize(in.Lreal);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < in.Lmats; i++) s->wm[i] = pi / in.beta * (2.0 * (i + 1) - 1.0);
+    for (int i = 0; i < in.Lreal; i++) s->wr[i] = in.Lreal > 1 ? in.wini + (in.wfin - in.wini) * (double)i / (double)(in.Lreal - 1) : in.wini;
+    s->Gmats.assign(nblk * in.Lmats, cplx(0, 0));
+    s->Greal.assign(nblk * in.Lreal, cplx(0, 0));
+    s->chains.clear();
+    for (int ispin = 0; ispin < in.Nspin; ispin++)
+        for (int iorb = 0; iorb < in.Norb; iorb++) {                                   // build_gf_normal :24-31
+            const int isite = (ispin == 0) ? iorb + 1 : iorb + 1 + Ns;                // impIndex, ED_SETUP.f90:443-446
+            for (size_t istate = 0; istate < s->states.size(); istate++) {             // :132
+                EdState &st = s->states[istate];
+                for (int pass = 0; pass < 2; pass++) {
+                    const int dagger = pass == 0 ? 1 : 0, isign = pass == 0 ? 1 : -1;  // :150 cdg first, :203 c
+                    const int jup = st.nup + (ispin == 0 ? (dagger ? 1 : -1) : 0);
+                    const int jdw = st.ndw + (ispin == 1 ? (dagger ? 1 : -1) : 0);
+                    if (jup < 0 || jup > Ns || jdw < 0 || jdw > Ns) continue;          // getCDGsector/getCsector == 0
+                    edgpu_sector *sj = nullptr;
+                    edgpu_vec *vv = nullptr;
+                    GPU_TRY(s, edgpu_sector_build(s->ctx, jup, jdw, &sj));
+                    int64_t jdim = 0;
+                    edgpu_sector_dim(sj, &jdim, nullptr, nullptr);
+                    int rc = edgpu_vec_alloc(sj, &vv);
+                    double norm2 = 0;
+                    if (!rc) rc = edgpu_apply_c(st.sec, sj, isite, dagger, st.vec, vv, 1, &norm2);     // :159-174
+                    EdChain ch;
+                    ch.iorb = iorb; ch.ispin = ispin; ch.isign = isign; ch.istate = (int)istate; ch.norm2 = norm2;
+                    ch.nlanc = (int)std::min<int64_t>(jdim, in.lanc_ngfiter);                           // :177
+                    ch.alfa.assign(ch.nlanc, 0.0);
+                    ch.beta.assign(ch.nlanc, 0.0);
+                    ch.nused = 0;
+                    if (!rc && in.ed_sparse_H && jdim > 1) rc = edgpu_sector_build_csr(sj);              // build_Hv_sector :180
+                    if (!rc && norm2 > 0.0)
+                        rc = edgpu_lanczos_tridiag(sj, vv, ch.nlanc, 1e-13, ch.alfa.data(), ch.beta.data(), &ch.nused);
+                    if (vv) edgpu_vec_free(vv);
+                    edgpu_sector_free(sj);
+                    if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
+                    if (norm2 > 0.0) add_to_lanczos_gf(s, norm2, st.e, ch.alfa, ch.beta, isign, iorb, iorb, ispin);  // :194
+                    s->chains.push_back(std::move(ch));
+                }
+            }
+        }
+    return 0;
+}
+
+static cplx delta_bath(const ed_solver *s, cplx x, int ispin, int iorb)
+{
+    // delta_bath_mats_main, normal/normal (ED_BATH_FUNCTIONS.f90:245-256)
+    const ed_input &in = s->in;
+    const int nb = in.Nspin * in.Norb * in.Nbath;
+    cplx d(0, 0);
+    for (int k = 0; k < in.Nbath; k++) {
+        const double e = s->bath[(size_t)(ispin * in.Norb + iorb) * in.Nbath + k];
+        const double v = s->bath[(size_t)nb + (size_t)(ispin * in.Norb + iorb) * in.Nbath + k];
+        d += v * v / (x - e);
+    }
+    return d;
+}
+
+static void build_sigma(ed_solver *s)
+{
+    // build_sigma_normal (ED_GF_NORMAL.f90:656-694, 725-726) + invg0_bath (ED_BATH_FUNCTIONS.f90:1784-1807)
+    const ed_input &in = s->in;
+    const size_t nblk = (size_t)in.Nspin * in.Nspin * in.Norb * in.Norb;
+    s->Smats.assign(nblk * in.Lmats, cplx(0, 0));
+    s->Sreal.assign(nblk * in.Lreal, cplx(0, 0));
+    s->G0mats.assign(nblk * in.Lmats, cplx(0, 0));
+    s->G0real.assign(nblk * in.Lreal, cplx(0, 0));
+    for (int ispin = 0; ispin < in.Nspin; ispin++)
+        for (int iorb = 0; iorb < in.Norb; iorb++) {
+            const size_t hidx = (size_t)ispin + in.Nspin * ((size_t)ispin + in.Nspin * ((size_t)iorb + in.Norb * (size_t)iorb));
+            const cplx hl(s->hloc[2 * hidx], s->hloc[2 * hidx + 1]);
+            for (int i = 0; i < in.Lmats; i++) {
+                const cplx z(0.0, s->wm[i]);
+                const cplx invg0 = z + in.xmu - hl - delta_bath(s, z, ispin, iorb);
+                const size_t q = gidx(in, ispin, ispin, iorb, iorb, i);
+                s->Smats[q] = invg0 - 1.0 / s->Gmats[q];
+                s->G0mats[q] = 1.0 / invg0;
+            }
+            for (int i = 0; i < in.Lreal; i++) {
+                const cplx z(s->wr[i], in.eps);
+                const cplx invg0 = z + in.xmu - hl - delta_bath(s, z, ispin, iorb);
+                const size_t q = gidx(in, ispin, ispin, iorb, iorb, i);
+                s->Sreal[q] = invg0 - 1.0 / s->Greal[q];
+                s->G0real[q] = 1.0 / invg0;
+            }
+        }
+}
+
+static int observables(ed_solver *s)
+{
+    // observables_impurity (ED_OBSERVABLES.f90:105-162), T=0: peso = 1/zeta_function
+    const int n = s->in.Norb;
+    s->dens.assign(n, 0.0); s->dens_up.assign(n, 0.0); s->dens_dw.assign(n, 0.0); s->docc.assign(n, 0.0); s->magz.assign(n, 0.0);
+    s->sz2.assign((size_t)n * n, 0.0); s->n2.assign((size_t)n * n, 0.0);
+    s->s2tot = 0.0;
+    for (auto &st : s->states)
+        GPU_TRY(s, edgpu_observables(st.sec, st.vec, 1.0 / s->zeta, s->dens.data(), s->dens_up.data(), s->dens_dw.data(),
+                                     s->docc.data(), s->magz.data(), s->sz2.data(), s->n2.data(), &s->s2tot));
+    return 0;
+}
+
+extern "C" int ed_solve(ed_solver *s, const double *bath, int32_t bath_len, const double *hloc_cplx)
+{
+    if (!s || !bath) return 1;
+    const ed_input &in = s->in;
+    if (bath_len != ed_get_bath_dimension(&in)) return fail(s, "ED_SOLVE_SINGLE Error: wrong bath dimensions");   // ED_MAIN.f90:258
+    if (hloc_cplx) memcpy(s->hloc.data(), hloc_cplx, sizeof(double) * s->hloc.size());                           // set_Hloc :256
+    s->bath.assign(bath, bath + bath_len);
+    GPU_TRY(s, edgpu_set_hamiltonian(s->ctx, bath, bath_len, s->hloc.data(), in.uloc, in.ust, in.jh, in.jx, in.jp, in.xmu));
+    double t0 = now_s();
+    if (int rc = ed_diag(s)) return rc;                     // diagonalize_impurity
+    double t1 = now_s();
+    if (int rc = build_gf(s)) return rc;                    // buildgf_impurity
+    double t2 = now_s();
+    build_sigma(s);
+    double t3 = now_s();
+    if (int rc = observables(s)) return rc;                 // observables_impurity
+    double t4 = now_s();
+    s->timings[0] = t1 - t0; s->timings[1] = t2 - t1; s->timings[2] = t3 - t2; s->timings[3] = t4 - t3;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// getters (ED_IO)
+// ---------------------------------------------------------------------------------------------------------
+static int copy_c(const std::vector<cplx> &src, double *dst)
+{
+    if (!dst || src.empty()) return 1;
+    memcpy(dst, src.data(), sizeof(cplx) * src.size());
+    return 0;
+}
+static int copy_d(const std::vector<double> &src, double *dst)
+{
+    if (!dst || src.empty()) return 1;
+    memcpy(dst, src.data(), sizeof(double) * src.size());
+    return 0;
+}
+extern "C" int ed_get_sigma_matsubara(const ed_solver *s, double *o) { return s ? copy_c(s->Smats, o) : 1; }
+extern "C" int ed_get_sigma_real(const ed_solver *s, double *o) { return s ? copy_c(s->Sreal, o) : 1; }
+extern "C" int ed_get_gimp_matsubara(const ed_solver *s, double *o) { return s ? copy_c(s->Gmats, o) : 1; }
+extern "C" int ed_get_gimp_real(const ed_solver *s, double *o) { return s ? copy_c(s->Greal, o) : 1; }
+extern "C" int ed_get_g0imp_matsubara(const ed_solver *s, double *o) { return s ? copy_c(s->G0mats, o) : 1; }
+extern "C" int ed_get_g0imp_real(const ed_solver *s, double *o) { return s ? copy_c(s->G0real, o) : 1; }
+extern "C" int ed_get_dens(const ed_solver *s, double *o) { return s ? copy_d(s->dens, o) : 1; }
+extern "C" int ed_get_dens_up(const ed_solver *s, double *o) { return s ? copy_d(s->dens_up, o) : 1; }
+extern "C" int ed_get_dens_dw(const ed_solver *s, double *o) { return s ? copy_d(s->dens_dw, o) : 1; }
+extern "C" int ed_get_docc(const ed_solver *s, double *o) { return s ? copy_d(s->docc, o) : 1; }
+extern "C" int ed_get_mag(const ed_solver *s, double *o) { return s ? copy_d(s->magz, o) : 1; }
+extern "C" int ed_get_sz2_n2(const ed_solver *s, double *sz2, double *n2, double *s2tot)
+{
+    if (!s) return 1;
+    if (sz2) copy_d(s->sz2, sz2);
+    if (n2) copy_d(s->n2, n2);
+    if (s2tot) *s2tot = s->s2tot;
+    return 0;
+}
+extern "C" int ed_get_grids(const ed_solver *s, double *wm, double *wr)
+{
+    if (!s) return 1;
+    if (wm) copy_d(s->wm, wm);
+    if (wr) copy_d(s->wr, wr);
+    return 0;
+}
+extern "C" int ed_get_state_count(const ed_solver *s, int32_t *n, double *zeta, double *egs)
+{
+    if (!s) return 1;
+    if (n) *n = (int32_t)s->states.size();
+    if (zeta) *zeta = s->zeta;
+    if (egs) *egs = s->egs;
+    return 0;
+}
+extern "C" int ed_get_state(const ed_solver *s, int32_t i, double *e, int32_t *nup, int32_t *ndw)
+{
+    if (!s || i < 0 || i >= (int)s->states.size()) return 1;
+    if (e) *e = s->states[i].e;
+    if (nup) *nup = s->states[i].nup;
+    if (ndw) *ndw = s->states[i].ndw;
+    return 0;
+}
+extern "C" int ed_get_state_vector(const ed_solver *s, int32_t i, double *vec, int64_t len)
+{
+    if (!s || i < 0 || i >= (int)s->states.size() || !vec) return 1;
+    int64_t dim = 0;
+    edgpu_sector_dim(s->states[i].sec, &dim, nullptr, nullptr);
+    if (len != dim) return 1;
+    return edgpu_vec_download(s->states[i].vec, vec, 0);
+}
+extern "C" int ed_get_sector_energy(const ed_solver *s, int32_t nup, int32_t ndw, double *e)
+{
+    if (!s || !e) return 1;
+    auto it = s->sector_e.find({nup, ndw});
+    if (it == s->sector_e.end()) return 1;
+    *e = it->second;
+    return 0;
+}
+extern "C" int ed_get_chain_count(const ed_solver *s, int32_t *n)
+{
+    if (!s || !n) return 1;
+    *n = (int32_t)s->chains.size();
+    return 0;
+}
+extern "C" int ed_get_chain(const ed_solver *s, int32_t i, int32_t *iorb, int32_t *ispin, int32_t *isign, int32_t *istate,
+                            int32_t *nlanc, int32_t *nused, double *norm2, double *alfa, double *beta, int32_t cap)
+{
+    if (!s || i < 0 || i >= (int)s->chains.size()) return 1;
+    const EdChain &c = s->chains[i];
+    if (iorb) *iorb = c.iorb;
+    if (ispin) *ispin = c.ispin;
+    if (isign) *isign = c.isign;
+    if (istate) *istate = c.istate;
+    if (nlanc) *nlanc = c.nlanc;
+    if (nused) *nused = c.nused;
+    if (norm2) *norm2 = c.norm2;
+    for (int k = 0; k < c.nlanc && k < cap; k++) {
+        if (alfa) alfa[k] = c.alfa[k];
+        if (beta) beta[k] = c.beta[k];
+    }
+    return 0;
+}
+extern "C" int ed_get_timings(const ed_solver *s, double *t4)
+{
+    if (!s || !t4) return 1;
+    for (int i = 0; i < 4; i++) t4[i] = s->timings[i];
+    return 0;
+}

@@ -1,0 +1,386 @@
+// lanczos.cu -- device Lanczos: fused vector kernels, deterministic reductions, ground-state and
+// tridiagonalisation drivers.
+//
+// Replaces SciFortran sp_lanc_eigh / sp_lanc_tridiag as used at ED_DIAG.f90:173-181 and
+// ED_GF_NORMAL.f90:187-192,240-245 (in-tree ancestor .repo/PLAIN_LANCZOS.f90:87-118,154-180,286-385).
+// Recurrence (no re-orthogonalisation, like the reference):
+//   tmp = H vin - b vout ; a = <vin,tmp> ; tmp -= a vin ; b = |tmp| ; vout = vin ; vin = tmp/b
+// All Lanczos scalars live in device memory so that the GF tridiagonalisation runs without host round trips;
+// dot products use a fixed launch shape + fixed-order second stage => bit-reproducible run to run.
+#include "edgpu_internal.h"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void block_store_partial(double v, double *out)
+{
+    __shared__ double sh[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) *out = v;
+    }
+}
+
+// second stage: one block, fixed order.  mode 0: out = sum ; mode 1: out = sqrt(sum)
+__global__ void k_reduce_final(const double *__restrict__ partials, int n, double *__restrict__ out, int mode)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    __shared__ double sh[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) *out = mode ? sqrt(v) : v;
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_dot(const double *__restrict__ a, const double *__restrict__ b,
+                                                     int64_t n, double *__restrict__ partials)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i] * b[i];
+    block_store_partial(acc, partials + blockIdx.x);
+}
+
+// tmp -= b*vout ; partial <vin,tmp>          (b read from device memory)
+__global__ void __launch_bounds__(kRedThreads) k_lanc_a(double *__restrict__ tmp, const double *__restrict__ vout,
+                                                        const double *__restrict__ vin, const double *__restrict__ bptr,
+                                                        int64_t n, double *__restrict__ partials)
+{
+    const double b = *bptr;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double t = tmp[i] - b * vout[i];
+        tmp[i] = t;
+        acc += vin[i] * t;
+    }
+    block_store_partial(acc, partials + blockIdx.x);
+}
+
+// tmp -= a*vin ; partial <tmp,tmp>
+__global__ void __launch_bounds__(kRedThreads) k_lanc_b(double *__restrict__ tmp, const double *__restrict__ vin,
+                                                        const double *__restrict__ aptr, int64_t n,
+                                                        double *__restrict__ partials)
+{
+    const double a = *aptr;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double t = tmp[i] - a * vin[i];
+        tmp[i] = t;
+        acc += t * t;
+    }
+    block_store_partial(acc, partials + blockIdx.x);
+}
+
+// v = v / (*den)      (vin = tmp/b, also the initial normalisation)
+__global__ void __launch_bounds__(kRedThreads) k_div(double *__restrict__ v, const double *__restrict__ den, int64_t n)
+{
+    const double d = *den;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = v[i] / d;
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_scale(double *__restrict__ v, double alpha, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] *= alpha;
+}
+
+// acc += z * v
+__global__ void __launch_bounds__(kRedThreads) k_axpy(double *__restrict__ acc, const double *__restrict__ v, double z, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc[i] += z * v[i];
+}
+
+static inline int red_blocks(int64_t n)
+{
+    int64_t b = (n + kRedThreads - 1) / kRedThreads;
+    return (int)(b < kRedBlocks ? (b > 0 ? b : 1) : kRedBlocks);
+}
+
+int vec_dot(edgpu_ctx *ctx, const double *a, const double *b, int64_t n, double *d_out)
+{
+    int nb = red_blocks(n);
+    k_dot<<<nb, kRedThreads, 0, ctx->stream>>>(a, b, n, ctx->d_partials);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, d_out, 0);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n)
+{
+    k_scale<<<red_blocks(n), kRedThreads, 0, ctx->stream>>>(v, alpha, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int vec_axpy(edgpu_ctx *ctx, double *acc, const double *v, double z, int64_t n)
+{
+    k_axpy<<<red_blocks(n), kRedThreads, 0, ctx->stream>>>(acc, v, z, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int sector_work(edgpu_sector *s, int i, double **p)
+{
+    if (!s->work[i]) {
+        CUDA_TRY(s->ctx, cudaMalloc(&s->work[i], sizeof(double) * (size_t)s->nalloc));
+        CUDA_TRY(s->ctx, cudaMemsetAsync(s->work[i], 0, sizeof(double) * (size_t)s->nalloc, s->ctx->stream));
+    }
+    *p = s->work[i];
+    return 0;
+}
+
+// Device scalar slots (ctx->d_scal): [0] norm / b , [1] a , [2] zero constant, [8 + k] alanc[k], [8 + NMAX + k] blanc[k]
+static constexpr int kScalB = 0, kScalArr = 8, kLancMax = 4096;
+
+// One Lanczos step on device pointers. b_in: device pointer to the b of the previous step; a_out/b_out: where
+// to leave this step's a and b.  On return the roles rotate: (vin, vout, tmp) -> (tmp, vin, vout).
+static int lanczos_step(edgpu_sector *s, double *vin, double *vout, double *tmp,
+                        const double *b_in, double *a_out, double *b_out)
+{
+    edgpu_ctx *ctx = s->ctx;
+    const int64_t n = s->nalloc;
+    const int nb = red_blocks(n);
+    if (int rc = hxv_dispatch(s, vin, tmp)) return rc;
+    k_lanc_a<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, vout, vin, b_in, n, ctx->d_partials);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, a_out, 0);
+    k_lanc_b<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, vin, a_out, n, ctx->d_partials);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, b_out, 1);
+    k_div<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, b_out, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int normalise(edgpu_sector *s, double *v)
+{
+    edgpu_ctx *ctx = s->ctx;
+    const int64_t n = s->nalloc;
+    const int nb = red_blocks(n);
+    k_dot<<<nb, kRedThreads, 0, ctx->stream>>>(v, v, n, ctx->d_partials);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, ctx->d_scal + kScalB, 1);
+    k_div<<<nb, kRedThreads, 0, ctx->stream>>>(v, ctx->d_scal + kScalB, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// tql2 (EISPACK, as carried in .repo/PLAIN_LANCZOS.f90:427-565): host, tiny.
+int host_tql2(int n, double *d, double *e, double *z);
+
+extern "C" int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlanc, double threshold,
+                                     double *alfa, double *beta, int32_t *nused)
+{
+    if (!s || !v || v->s != s) return s ? edgpu_fail(s->ctx, "edgpu_lanczos_tridiag: bad vector/sector") : 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (nlanc < 1 || nlanc > kLancMax) return edgpu_fail(ctx, "edgpu_lanczos_tridiag: nlanc=%d out of range", nlanc);
+    double *vin = v->d, *vout, *tmp;
+    if (int rc = sector_work(s, 0, &vout)) return rc;
+    if (int rc = sector_work(s, 1, &tmp)) return rc;
+    const int64_t n = s->nalloc;
+    CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    if (int rc = normalise(s, vin)) return rc;                 // iter==1: vin=vin/norm ; b=0   (:94-99)
+    double *d_a = ctx->d_scal + kScalArr, *d_b = ctx->d_scal + kScalArr + kLancMax;
+    // d_b[k] holds Fortran blanc(k+1): d_b[0] = 0 (b entering iteration 1)
+    for (int iter = 1; iter <= nlanc; iter++) {
+        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
+        double *t = vout; vout = vin; vin = tmp; tmp = t;       // vout = vin ; vin = tmp/b
+    }
+    std::vector<double> ha(nlanc), hb(nlanc + 1);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ha.data(), d_a, sizeof(double) * nlanc, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hb.data(), d_b, sizeof(double) * (nlanc + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the vector handle must keep pointing at memory it owns: the buffers rotated, data is destroyed anyway
+    // reproduce the reference's exit: alanc(iter)=a ; if(iter<n) blanc(iter+1)=b ; if(|b|<thr) exit   (:172-174)
+    int used = 0;
+    for (int i = 0; i < nlanc; i++) { alfa[i] = 0.0; beta[i] = 0.0; }
+    for (int iter = 1; iter <= nlanc; iter++) {
+        alfa[iter - 1] = ha[iter - 1];
+        if (iter < nlanc) beta[iter] = hb[iter];
+        used = iter;
+        if (std::fabs(hb[iter]) < threshold || !std::isfinite(hb[iter])) break;
+    }
+    if (nused) *nused = used;
+    return 0;
+}
+
+extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax, double threshold, int32_t ncheck,
+                                double *e0, int32_t *nlanc_out, double *alanc_out, double *blanc_out)
+{
+    if (!s || !v0 || v0->s != s) return s ? edgpu_fail(s->ctx, "edgpu_lanczos_gs: bad vector/sector") : 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (nitermax < 1 || nitermax > kLancMax - 1) return edgpu_fail(ctx, "edgpu_lanczos_gs: nitermax=%d out of range", nitermax);
+    if (ncheck < 1) ncheck = 10;
+    const int64_t n = s->nalloc;
+    double *w0, *w1, *w2;
+    if (int rc = sector_work(s, 0, &w0)) return rc;
+    if (int rc = sector_work(s, 1, &w1)) return rc;
+    if (int rc = sector_work(s, 2, &w2)) return rc;
+    double *d_a = ctx->d_scal + kScalArr, *d_b = ctx->d_scal + kScalArr + kLancMax;
+    std::vector<double> alanc(nitermax + 1, 0.0), blanc(nitermax + 2, 0.0), diag(nitermax + 1), sub(nitermax + 1),
+        esave(nitermax + 2, 0.0), Z;
+    int nlanc = 0;
+
+    // ---- pass 1: tridiagonalise until the lowest Ritz value stops moving (:328-360) ----
+    double *vin = w0, *vout = w1, *tmp = w2;
+    CUDA_TRY(ctx, cudaMemcpyAsync(vin, v0->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    if (int rc = normalise(s, vin)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal + kScalB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scal[0] == 0.0) return edgpu_fail(ctx, "lanczos_plain_iteration: norm =0!!");
+    for (int iter = 1; iter <= nitermax; iter++) {
+        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
+        { double *t = vout; vout = vin; vin = tmp; tmp = t; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, d_a + (iter - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + 1, d_b + iter, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const double a = ctx->h_scal[0], b = ctx->h_scal[1];
+        if (std::fabs(b) < threshold) break;                                    // :333
+        nlanc++;
+        alanc[iter - 1] = a;
+        blanc[iter] = b;
+        for (int i = 0; i < nlanc; i++) { diag[i] = alanc[i]; sub[i] = i > 0 ? blanc[i] : 0.0; }
+        Z.assign((size_t)nlanc * nlanc, 0.0);
+        for (int i = 0; i < nlanc; i++) Z[i + (size_t)nlanc * i] = 1.0;
+        host_tql2(nlanc, diag.data(), sub.data(), Z.data());
+        if (nlanc >= ncheck) {                                                  // :352-359
+            esave[nlanc - (ncheck - 1)] = diag[0];
+            if (nlanc >= ncheck + 1) {
+                double diff = esave[nlanc - (ncheck - 1)] - esave[nlanc - (ncheck - 1) - 1];
+                if (std::fabs(diff) <= threshold) break;
+            }
+        }
+    }
+    if (nlanc == 0) return edgpu_fail(ctx, "edgpu_lanczos_gs: Lanczos broke down at the first step");
+    for (int i = 0; i < nlanc; i++) { diag[i] = alanc[i]; sub[i] = i > 0 ? blanc[i] : 0.0; }
+    Z.assign((size_t)nlanc * nlanc, 0.0);
+    for (int i = 0; i < nlanc; i++) Z[i + (size_t)nlanc * i] = 1.0;
+    host_tql2(nlanc, diag.data(), sub.data(), Z.data());
+    if (e0) *e0 = diag[0];
+
+    // ---- pass 2: regenerate the Lanczos vectors and accumulate the Ritz vector sum_k Z(k,1) v_k (:375-384,
+    //      with Z(k,1) paired with the k-th basis vector) ----
+    vin = w0; vout = w1; tmp = w2;
+    CUDA_TRY(ctx, cudaMemcpyAsync(vin, v0->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(v0->d, 0, sizeof(double) * (size_t)n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    if (int rc = normalise(s, vin)) return rc;
+    for (int iter = 1; iter <= nlanc; iter++) {
+        if (int rc = vec_axpy(ctx, v0->d, vin, Z[iter - 1], n)) return rc;      // Z(iter,1)
+        if (iter == nlanc) break;
+        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
+        { double *t = vout; vout = vin; vin = tmp; tmp = t; }
+    }
+    if (int rc = normalise(s, v0->d)) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nlanc_out) *nlanc_out = nlanc;
+    if (alanc_out) for (int i = 0; i < nlanc; i++) alanc_out[i] = alanc[i];
+    if (blanc_out) for (int i = 0; i < nlanc; i++) blanc_out[i] = i > 0 ? blanc[i] : 0.0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// EISPACK tql2 (host).  d(1:n) diagonal, e(2:n) sub-diagonal in e[1..n-1], z column-major n x n.
+// ---------------------------------------------------------------------------------------------------------
+static double h_pythag(double a, double b)
+{
+    double p = std::fmax(std::fabs(a), std::fabs(b));
+    if (p == 0.0) return 0.0;
+    double r = std::fmin(std::fabs(a), std::fabs(b)) / p;
+    r *= r;
+    for (;;) {
+        double t = 4.0 + r;
+        if (t == 4.0) break;
+        double s = r / t, u = 1.0 + 2.0 * s;
+        p *= u;
+        r *= (s / u) * (s / u);
+    }
+    return p;
+}
+
+int host_tql2(int n, double *d, double *e, double *z)
+{
+    if (n == 1) return 0;
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    for (int l = 0; l < n; l++) {
+        int iters = 0;
+        double h = std::fabs(d[l]) + std::fabs(e[l]);
+        if (tst1 < h) tst1 = h;
+        int m = l;
+        while (m < n && !(tst1 + std::fabs(e[m]) == tst1)) m++;
+        if (m != l) {
+            double tst2;
+            do {
+                if (iters++ == 30) return l + 1;
+                const int l1 = l + 1;
+                double g = d[l];
+                double p = (d[l1] - g) / (2.0 * e[l]);
+                double r = h_pythag(p, 1.0);
+                const double sr = std::copysign(r, p);
+                d[l] = e[l] / (p + sr);
+                d[l1] = e[l] * (p + sr);
+                const double dl1 = d[l1];
+                h = g - d[l];
+                for (int i = l1 + 1; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+                const double el1 = e[l1];
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    r = h_pythag(p, e[i]);
+                    e[i + 1] = s * r;
+                    s = e[i] / r;
+                    c = p / r;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    double *zi = z + (size_t)n * i, *zi1 = z + (size_t)n * (i + 1);
+                    for (int k = 0; k < n; k++) {
+                        const double hh = zi1[k];
+                        zi1[k] = s * zi[k] + c * hh;
+                        zi[k] = c * zi[k] - s * hh;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+                tst2 = tst1 + std::fabs(e[l]);
+            } while (tst2 > tst1);
+        }
+        d[l] += f;
+    }
+    for (int ii = 1; ii < n; ii++) {
+        int i = ii - 1, k = i;
+        double p = d[i];
+        for (int j = ii; j < n; j++) if (d[j] < p) { k = j; p = d[j]; }
+        if (k != i) {
+            d[k] = d[i]; d[i] = p;
+            for (int j = 0; j < n; j++) std::swap(z[j + (size_t)n * i], z[j + (size_t)n * k]);
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,124 @@
+/*
+ * edgpu.h -- C-ABI of the B200-native Lanczos hot path of dmft-ed (libedgpu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch/C++ types.  Every entry point names the
+ * reference interface it replaces (file:line relative to the reference root).  The Fortran ISO_C_BINDING shim
+ * that binds these symbols at the ED_DIAG / ED_GF_NORMAL / ED_OBSERVABLES call sites is in
+ * fortran/ed_gpu_binding.f90 and described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; edgpu_last_error() gives the message (the
+ *    reference's `stop "..."`, e.g. ED_HAMILTONIAN_DIRECT_HxV.f90:45,50).
+ *  - "cplx" host arrays are interleaved (re,im) doubles = Fortran complex(8) = C double _Complex.
+ *  - levels are 1-based like the reference (level l <-> bit l-1; up levels 1..Ns, down levels Ns+1..2Ns).
+ *  - sector vectors live on the device behind edgpu_vec handles as REAL fp64 (H is real symmetric for
+ *    ed_mode=normal, bath_type=normal, real Hloc); host import/export uses the reference ordering
+ *    i = r_up + r_dw*DimUp (0-based; ED_SETUP.f90:905-916).
+ *  - there is no CPU fallback: every compute entry point needs a CUDA device.
+ *  - one host thread drives a context (the reference's global-state, single-thread model).
+ */
+#ifndef EDGPU_H
+#define EDGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct edgpu_ctx edgpu_ctx;
+typedef struct edgpu_sector edgpu_sector;
+typedef struct edgpu_vec edgpu_vec;
+
+#define EDGPU_MAXORB 5
+
+/* Problem shape (ED_INPUT_VARS.f90:121-196; only ed_mode=normal, bath_type=normal are on this path). */
+typedef struct {
+    int32_t norb, nbath, nspin;
+    int32_t hfmode;          /* HFMODE */
+    int32_t layout;          /* 0 = auto, 1 = reference (colex) order on device, 2 = star-product order */
+    int32_t hxv_kernel;      /* 0 = auto, 1 = generic table kernel, 2 = star-product tile kernels */
+    int32_t reserved[8];
+} edgpu_params;
+
+/* init_ed_structure + setup_pointers_normal (ED_MAIN.f90:73,91; ED_SETUP.f90:150-360,372-496).
+ * device < 0: use the current CUDA device.  stream: a cudaStream_t (may be NULL = default stream). */
+int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu_ctx **ctx);
+int edgpu_finalize(edgpu_ctx *ctx);
+const char *edgpu_last_error(const edgpu_ctx *ctx);
+int edgpu_version(void);
+int edgpu_ns(const edgpu_ctx *ctx);                         /* Ns = (Nbath+1)*Norb, ED_SETUP.f90:99-101 */
+
+/* set_dmft_bath + set_Hloc (ED_MAIN.f90:260-267; dmft_aux.f90:494-511; ED_AUX_FUNX.f90:139-158).
+ * bath: [e(ispin,iorb,k) ..., v(ispin,iorb,k) ...], k fastest; hloc_cplx: impHloc(Nspin,Nspin,Norb,Norb)
+ * column-major, may be NULL (= 0).  Complex Hloc entries are rejected (error) on this path. */
+int edgpu_set_hamiltonian(edgpu_ctx *ctx, const double *bath, int32_t bath_len, const double *hloc_cplx,
+                          const double *uloc, double ust, double jh, double jx, double jp, double xmu);
+
+/* build_sector / build_Hv_sector / delete_Hv_sector / vecDim_Hv_sector (ED_SETUP.f90:886-916;
+ * ED_HAMILTONIAN.f90:42-149).  Device-resident per-spin tables; the full map is never needed by H*v. */
+int edgpu_sector_build(edgpu_ctx *ctx, int32_t nup, int32_t ndw, edgpu_sector **s);
+int edgpu_sector_free(edgpu_sector *s);
+int edgpu_sector_dim(const edgpu_sector *s, int64_t *dim, int64_t *dim_up, int64_t *dim_dw);
+/* type(sector_map)%map (ED_VARS_GLOBAL.f90:28-31), 64-bit, entries [first, first+count): built by a device
+ * kernel and copied to host_out. */
+int edgpu_sector_map(const edgpu_sector *s, int64_t first, int64_t count, uint64_t *host_out);
+/* order-sensitive checksum of the whole map computed on the device (for full-size sectors):
+ * sum_i map[i]*(2i+1) mod 2^64, plus sortedness / popcount violations count. */
+int edgpu_sector_map_check(const edgpu_sector *s, uint64_t *checksum, int64_t *violations);
+
+/* vectors */
+int edgpu_vec_alloc(edgpu_sector *s, edgpu_vec **v);
+int edgpu_vec_free(edgpu_vec *v);
+int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cplx);    /* complex: real part is taken */
+int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_cplx); /* complex: imag = 0 */
+int edgpu_vec_fill_normal(edgpu_vec *v, uint64_t seed);   /* Philox4x32-10 N(0,1), element index = counter */
+int edgpu_vec_copy(edgpu_vec *dst, const edgpu_vec *src);
+int edgpu_vec_dot(const edgpu_vec *a, const edgpu_vec *b, double *out);
+int edgpu_vec_scale(edgpu_vec *a, double alpha);
+
+/* spHtimesV_cc (ED_VARS_GLOBAL.f90:48-54,105) = directMatVec_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:21-92) or
+ * spMatVec_cc (ED_HAMILTONIAN_STORED_HxV.f90:132-143).  Host complex in/out: parity hook / fine seam. */
+int edgpu_hxv(edgpu_sector *s, int64_t nloc, const double *v_cplx, double *hv_cplx);
+/* device-resident real vectors: the product path */
+int edgpu_hxv_dev(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y);
+/* ed_sparse_H=T: ed_buildH_c (ED_HAMILTONIAN_STORED_HxV.f90:28-113) on the device; afterwards edgpu_hxv*
+ * use the stored CSR.  edgpu_sector_csr_download mirrors the spH0 rows (insertion order, 0-based cols). */
+int edgpu_sector_build_csr(edgpu_sector *s);
+int edgpu_sector_drop_csr(edgpu_sector *s);
+int edgpu_sector_csr_nnz(const edgpu_sector *s, int64_t *nnz);
+int edgpu_sector_csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
+/* dense Hmat (build_Hv_sector(isector,Hmat), ED_HAMILTONIAN.f90:75-79) for small sectors: column-major
+ * real dim x dim, computed as H applied to the identity on the device. */
+int edgpu_sector_dense(edgpu_sector *s, double *hmat);
+
+/* sp_lanc_eigh (ED_DIAG.f90:173-181; ancestor .repo/PLAIN_LANCZOS.f90:286-385): two-pass plain Lanczos.
+ * v0: start vector handle (overwritten by the normalised ground state).  alanc/blanc: host arrays of
+ * nitermax+1 (blanc[0] unused, Fortran blanc(1)); may be NULL. */
+int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax, double threshold, int32_t ncheck,
+                     double *e0, int32_t *nlanc, double *alanc, double *blanc);
+/* sp_lanc_tridiag (ED_GF_NORMAL.f90:187-192,240-245; ancestor .repo/PLAIN_LANCZOS.f90:154-180).
+ * v is normalised and destroyed.  alfa[nlanc], beta[nlanc] (beta[0] unused) are zero-filled first. */
+int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlanc, double threshold,
+                          double *alfa, double *beta, int32_t *nused);
+
+/* GF seed loops (ED_GF_NORMAL.f90:159-174 cdg, :212-227 c): out(j) = sgn*in(m); returns <out|out> in
+ * *norm2; normalise != 0 divides by sqrt(norm2) like :174.  isite is the 1-based level. */
+int edgpu_apply_c(edgpu_sector *s_in, edgpu_sector *s_out, int32_t isite, int32_t dagger,
+                  const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm2);
+
+/* observables_impurity core (ED_OBSERVABLES.f90:127-158): accumulates (+=) like the reference.
+ * dens,dens_up,dens_dw,docc,magz: [Norb]; sz2,n2: [Norb*Norb] column-major; s2tot scalar. */
+int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double peso,
+                      double *dens, double *dens_up, double *dens_dw, double *docc, double *magz,
+                      double *sz2, double *n2, double *s2tot);
+
+/* measurement helpers (bench.py): average device time of `iters` H*v launches between CUDA events on the
+ * context stream; flush_l2 != 0 writes a >L2 scratch buffer between launches (outside the events). */
+int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y, int32_t iters, int32_t flush_l2,
+                    double *ms_avg, int64_t *launches);
+int edgpu_device_info(edgpu_ctx *ctx, int32_t *sm_count, int64_t *l2_bytes, int64_t *mem_bytes);
+int edgpu_sync(edgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,189 @@
+"""CPU: pins the oracle (oracle/ed_oracle.{c,py}) by independent invariants, since the reference has no golden
+vectors for this path ("parity unpinned") and cannot be built here."""
+import itertools
+
+import numpy as np
+import pytest
+
+
+def params(O, **kw):
+    base = dict(lanc_method="lanczos", lanc_nstates_sector=1, Lmats=64, Lreal=64)
+    base.update(kw)
+    return O.Params(**base)
+
+
+def test_binomial_and_dims(oracle):
+    import math
+    for n in range(0, 21):
+        for k in range(0, n + 1):
+            assert oracle.binomial(n, k) == math.comb(n, k)
+    assert oracle.sector_dim(16, 8, 8) == 165636900
+    assert oracle.sector_dim(18, 9, 9) == 2363904400          # overflows the reference's int32
+
+
+@pytest.mark.parametrize("Ns,nup,ndw", [(5, 2, 3), (5, 0, 5), (6, 3, 3), (7, 1, 6)])
+def test_build_sector_literal_scan_equals_fast_enumeration(oracle, Ns, nup, ndw):
+    lit = oracle.build_sector(Ns, nup, ndw, literal=True)
+    fast = oracle.build_sector(Ns, nup, ndw)
+    assert np.array_equal(lit, fast)
+    assert np.all(np.diff(lit.astype(np.int64)) > 0)
+    up = lit & np.uint64((1 << Ns) - 1)
+    dw = lit >> np.uint64(Ns)
+    assert all(bin(int(u)).count("1") == nup for u in up) and all(bin(int(d)).count("1") == ndw for d in dw)
+    # position = colex_rank(up) + colex_rank(dw)*DimUp  
+    import math
+    def colex(w):
+        r, i = 0, 1
+        for b in range(Ns):
+            if (w >> b) & 1:
+                r += math.comb(b, i); i += 1
+        return r
+    dup = oracle.binomial(Ns, nup)
+    for pos in range(0, lit.size, max(1, lit.size // 50)):
+        assert colex(int(up[pos])) + colex(int(dw[pos])) * dup == pos
+
+
+def test_binary_search_literal(oracle):
+    import ctypes as C
+    m = oracle.build_sector(6, 3, 2)
+    L = oracle.lib()
+    for pos in range(m.size):
+        assert L.ora_binary_search(m.ctypes.data_as(C.POINTER(C.c_uint64)), m.size, int(m[pos])) == pos + 1
+    assert L.ora_binary_search(m.ctypes.data_as(C.POINTER(C.c_uint64)), m.size, int(m[-1]) + 1) == 0
+
+
+CASES = [
+    dict(Norb=1, Nbath=4),
+    dict(Norb=1, Nbath=3, xmu=0.3, hfmode=False),
+    dict(Norb=2, Nbath=2, uloc=(2.0, 1.5), ust=1.2, jh=0.3),
+    dict(Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, jx=0.25, jp=0.25),
+    dict(Norb=1, Nbath=3, Nspin=2),
+    dict(Norb=3, Nbath=1, uloc=(2.0, 2.0, 2.0), ust=1.0, jh=0.2, jx=0.2, jp=0.2),
+]
+
+
+def make_model(O, rng, **kw):
+    p = params(O, **kw)
+    bath = O.init_bath(p)
+    bath = bath + 0.05 * rng.normal(size=bath.size)            # generic (spin/orbital dependent) bath
+    hloc = np.zeros((p.Nspin, p.Nspin, p.Norb, p.Norb), dtype=complex)
+    for s in range(p.Nspin):
+        for a in range(p.Norb):
+            hloc[s, s, a, a] = 0.1 * (a + 1) * (1 if s == 0 else -1)
+    if p.Norb > 1:
+        for s in range(p.Nspin):
+            hloc[s, s, 0, 1] = hloc[s, s, 1, 0] = 0.15
+    return p, O.Model(p, bath, hloc)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_scatter_gather_stored_forms_agree_and_h_is_hermitian(oracle, case):
+    rng = np.random.default_rng(7)
+    p, m = make_model(oracle, rng, **case)
+    Ns = p.Ns
+    for nup, ndw in [(Ns // 2, Ns // 2), (Ns // 2 + 1, Ns // 2), (1, Ns - 1), (0, 0), (Ns, Ns // 2)]:
+        smap = oracle.build_sector(Ns, nup, ndw)
+        H = oracle.dense_h(m, smap)
+        assert np.abs(H - H.conj().T).max() < 1e-14
+        v = rng.normal(size=smap.size) + 1j * rng.normal(size=smap.size)
+        a = oracle.direct_hxv(m, smap, v)
+        b = oracle.gather_hxv(m, smap, v)
+        rp, c, vals = oracle.stored_build(m, smap)
+        s = oracle.stored_hxv(rp, c, vals, v)
+        ref = H @ v
+        for x in (a, b, s):
+            assert np.abs(x - ref).max() < 1e-12
+
+
+def test_anchor_energies(oracle):
+    """BASELINE.md section 5 probe anchors."""
+    p = params(oracle, Norb=1, Nbath=4)
+    m = oracle.Model(p, oracle.init_bath(p))
+    for sec in [(2, 3), (3, 2)]:
+        e = np.linalg.eigvalsh(oracle.dense_h(m, oracle.build_sector(5, *sec)))[0]
+        assert abs(e - (-5.671950916933)) < 1e-11
+    p0 = params(oracle, Norb=1, Nbath=4, uloc=(0.0,))
+    m0 = oracle.Model(p0, oracle.init_bath(p0))
+    e = np.linalg.eigvalsh(oracle.dense_h(m0, oracle.build_sector(5, 2, 3)))[0]
+    assert abs(e - (-5.595866798531)) < 1e-11
+
+
+def test_u0_ground_energy_is_sum_of_single_particle_levels(oracle):
+    p = params(oracle, Norb=1, Nbath=4, uloc=(0.0,), hfmode=False)
+    bath = oracle.init_bath(p)
+    m = oracle.Model(p, bath)
+    e, v = bath[:4], bath[4:]
+    h1 = np.zeros((5, 5))
+    h1[0, 1:] = h1[1:, 0] = v
+    h1[1:, 1:] = np.diag(e)
+    lev = np.sort(np.linalg.eigvalsh(h1))
+    for nup, ndw in [(2, 3), (1, 1), (5, 0), (3, 3)]:
+        e0 = np.linalg.eigvalsh(oracle.dense_h(m, oracle.build_sector(5, nup, ndw)))[0]
+        assert abs(e0 - (lev[:nup].sum() + lev[:ndw].sum())) < 1e-12
+
+
+def test_lanczos_gs_against_dense(oracle):
+    rng = np.random.default_rng(3)
+    p, m = make_model(oracle, rng, Norb=2, Nbath=2, uloc=(2.0, 1.0), ust=0.8, jh=0.1)
+    smap = oracle.build_sector(6, 3, 3)
+    w, Z = np.linalg.eigh(oracle.dense_h(m, smap))
+    e0, vec, nlanc, al, bl = oracle.lanc_gs(m, smap, oracle.start_vector(smap.size), min(smap.size, 512), 1e-12)
+    assert abs(e0 - w[0]) < 1e-10
+    assert abs(abs(np.vdot(Z[:, 0], vec)) - 1.0) < 1e-8
+    r = oracle.direct_hxv(m, smap, vec) - e0 * vec
+    assert np.abs(r).max() < 1e-5
+
+
+def test_tridiag_reproduces_moments(oracle):
+    """Lanczos coefficients reproduce the moments <v|H^j|v>, j < 2*nlanc (what add_to_lanczos_gf's pole sum uses)."""
+    rng = np.random.default_rng(5)
+    p, m = make_model(oracle, rng, Norb=1, Nbath=4)
+    smap = oracle.build_sector(5, 3, 3)
+    H = oracle.dense_h(m, smap)
+    v = rng.normal(size=smap.size).astype(complex)
+    v /= np.linalg.norm(v)
+    a, b, nused = oracle.lanc_tridiag(m, smap, v, 12)
+    assert nused == 12
+    lam, Z = oracle.eigh_tridiag(a, b)
+    w = v.copy()
+    for j in range(0, 10):
+        mu_d = (v.conj() @ w).real
+        mu_l = (Z[0] ** 2 * lam ** j).sum()
+        assert abs(mu_d - mu_l) < 1e-9 * max(1.0, abs(mu_d))
+        w = H @ w
+
+
+def test_ed_solve_cfg1_invariants(oracle):
+    """Config 1 (Norb=1, Nbath=4): particle-hole symmetry, sum rules, U=0 => Sigma=0."""
+    p = params(oracle, Norb=1, Nbath=4, Lmats=256, Lreal=64, beta=50.0)
+    r = oracle.ed_solve(p, oracle.init_bath(p))
+    assert abs(r.egs - (-5.671950916933)) < 1e-10
+    assert abs(r.dens[0] - 1.0) < 1e-10                                # half filling
+    assert np.abs(r.impGmats.real).max() < 1e-9                        # particle-hole symmetric
+    for c in r.chains:                                                 # spectral sum rule sum_j Z(1,j)^2 = 1
+        lam, Z = oracle.eigh_tridiag(c["alfa"], c["beta"])
+        assert abs((Z[0] ** 2).sum() - 1.0) < 1e-10
+    tot = sum(c["norm2"] for c in r.chains) / r.zeta                    # <{c,c+}> = 1
+    assert abs(tot - 1.0) < 1e-10
+    p0 = params(oracle, Norb=1, Nbath=4, uloc=(0.0,), Lmats=64, Lreal=64)
+    r0 = oracle.ed_solve(p0, oracle.init_bath(p0))
+    assert np.abs(r0.impSmats).max() < 1e-8 and np.abs(r0.impSreal).max() < 1e-8
+    g0 = 1.0 / (1j * r0.wm - oracle.delta_bath(r0.model, 1j * r0.wm, 0, 0))
+    assert np.abs(r0.impGmats[0, 0, 0, 0] - g0).max() < 1e-9
+
+
+def test_ed_solve_arpack_and_lanczos_methods_agree(oracle):
+    pa = oracle.Params(Norb=1, Nbath=4, Lmats=32, Lreal=32)          # reference defaults: arpack, 6 states/sector
+    pl = params(oracle, Norb=1, Nbath=4, Lmats=32, Lreal=32)
+    bath = oracle.init_bath(pa)
+    ra, rl = oracle.ed_solve(pa, bath), oracle.ed_solve(pl, bath)
+    assert abs(ra.egs - rl.egs) < 1e-11
+    assert np.abs(ra.impGmats - rl.impGmats).max() < 1e-9
+    assert np.abs(ra.docc - rl.docc).max() < 1e-10
+
+
+def test_philox_normal_statistics(oracle):
+    x = oracle.philox_normal(20240607, 200000)
+    assert abs(x.mean()) < 0.01 and abs(x.std() - 1.0) < 0.01
+    y = oracle.philox_normal(20240607, 1000, i0=5000)
+    assert np.array_equal(y, x[5000:6000])                            # counter-based: any partition reproduces
