@@ -51,7 +51,7 @@ class ed_input(C.Structure):
 EDGPU_SYMBOLS = [
     "edgpu_init", "edgpu_finalize", "edgpu_last_error", "edgpu_version", "edgpu_ns", "edgpu_set_hamiltonian",
     "edgpu_sector_build", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
-    "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal",
+    "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
     "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_observables",
@@ -104,6 +104,7 @@ def lib():
     L.edgpu_vec_upload.argtypes = [vp, vp, C.c_int32]
     L.edgpu_vec_download.argtypes = [vp, vp, C.c_int32]
     L.edgpu_vec_fill_normal.argtypes = [vp, C.c_uint64]
+    L.edgpu_vec_fill_uniform.argtypes = [vp, C.c_uint64]
     L.edgpu_vec_copy.argtypes = [vp, vp]
     L.edgpu_vec_dot.argtypes = [vp, vp, dp]
     L.edgpu_vec_scale.argtypes = [vp, C.c_double]
@@ -318,6 +319,10 @@ class Vec:
 
     def fill_normal(self, seed):
         self.s.ctx.check(lib().edgpu_vec_fill_normal(self.h, seed))
+        return self
+
+    def fill_uniform(self, seed):
+        self.s.ctx.check(lib().edgpu_vec_fill_uniform(self.h, seed))
         return self
 
     def dot(self, other):

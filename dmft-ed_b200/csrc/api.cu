@@ -10,7 +10,7 @@ uint64_t edgpu_binom(int n, int k);
 int sector_map_kernel(edgpu_sector *s, int64_t first, int64_t count, uint64_t *d_out);
 int sector_map_check_kernel(edgpu_sector *s, unsigned long long *d_sum, unsigned long long *d_viol);
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst);
-int vec_fill_normal(edgpu_sector *s, uint64_t seed, double *dst);
+int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst);
 int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 int csr_build(edgpu_sector *s);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
@@ -284,7 +284,13 @@ extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_c
 extern "C" int edgpu_vec_fill_normal(edgpu_vec *v, uint64_t seed)
 {
     if (!v) return 1;
-    return vec_fill_normal(v->s, seed, v->d);
+    return vec_fill_random(v->s, 0, seed, v->d);
+}
+
+extern "C" int edgpu_vec_fill_uniform(edgpu_vec *v, uint64_t seed)
+{
+    if (!v) return 1;
+    return vec_fill_random(v->s, 1, seed, v->d);
 }
 
 extern "C" int edgpu_vec_copy(edgpu_vec *dst, const edgpu_vec *src)

@@ -319,7 +319,7 @@ static int ed_diag(ed_solver *s)
                 if (in.ed_sparse_H) rc = edgpu_sector_build_csr(sec);                                      // ED_HAMILTONIAN.f90:85-92
                 edgpu_vec *v = nullptr;
                 if (!rc) rc = edgpu_vec_alloc(sec, &v);
-                if (!rc) rc = edgpu_vec_fill_normal(v, 1234567ull);       // start vector (reference: random_number)
+                if (!rc) rc = edgpu_vec_fill_uniform(v, 1234567ull);      // start vector (reference: random_number)
                 double e0 = 0;
                 int nl = 0;
                 if (!rc) rc = edgpu_lanczos_gs(sec, v, (int)nitermax, in.lanc_tolerance, 10, &e0, &nl, nullptr, nullptr);

@@ -61,7 +61,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 }
 
 __global__ void __launch_bounds__(256)
-k_fill_normal(uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_t ld,
+k_fill_random(int uniform, uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_t ld,
               const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw, double *__restrict__ dst)
 {
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,13 +76,19 @@ k_fill_normal(uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_t ld,
         const uint64_t b = ((uint64_t)c[2] << 21) ^ (uint64_t)(c[3] >> 11);
         const double u1 = ((double)a + 0.5) * (1.0 / 9007199254740992.0);
         const double u2 = ((double)b + 0.5) * (1.0 / 9007199254740992.0);
-        dst[id * ld + iu] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+        if (uniform) {
+            // (a52 + 0.5)/2^51 - 1 in (-1,1): every step is exact in fp64 => bit-identical to the host generator
+            const uint64_t a52 = ((uint64_t)c[0] << 20) ^ (uint64_t)(c[1] >> 12);
+            dst[id * ld + iu] = ((double)a52 + 0.5) * (1.0 / 2251799813685248.0) - 1.0;
+        } else {
+            dst[id * ld + iu] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+        }
     }
 }
 
-int vec_fill_normal(edgpu_sector *s, uint64_t seed, double *dst)
+int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst)
 {
-    k_fill_normal<<<grid2d(s), 256, 0, s->ctx->stream>>>(seed, s->dim_up, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, dst);
+    k_fill_random<<<grid2d(s), 256, 0, s->ctx->stream>>>(uniform, seed, s->dim_up, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, dst);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }

@@ -71,6 +71,9 @@ int edgpu_vec_free(edgpu_vec *v);
 int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cplx);    /* complex: real part is taken */
 int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_cplx); /* complex: imag = 0 */
 int edgpu_vec_fill_normal(edgpu_vec *v, uint64_t seed);   /* Philox4x32-10 N(0,1), element index = counter */
+/* Philox uniforms in (-1,1), exact arithmetic (bit-identical to the oracle's generator): Lanczos start vector,
+ * standing in for the random_number() start of sp_lanc_eigh (.repo/PLAIN_LANCZOS.f90:310-318) */
+int edgpu_vec_fill_uniform(edgpu_vec *v, uint64_t seed);
 int edgpu_vec_copy(edgpu_vec *dst, const edgpu_vec *src);
 int edgpu_vec_dot(const edgpu_vec *a, const edgpu_vec *b, double *out);
 int edgpu_vec_scale(edgpu_vec *a, double alpha);

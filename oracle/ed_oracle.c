@@ -728,6 +728,19 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
     }
 }
 
+void ora_philox_uniform(uint64_t seed, int64_t i0, int64_t n, double *out)
+{
+    /* uniform in (-1,1), exactly representable arithmetic => bit-identical to the CUDA generator.
+     * (The reference seeds Lanczos with random_number() uniforms, .repo/PLAIN_LANCZOS.f90:310-318.) */
+    for (int64_t q = 0; q < n; q++) {
+        uint64_t idx = (uint64_t)(i0 + q);
+        uint32_t c[4] = { (uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u };
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint64_t a = ((uint64_t)c[0] << 20) ^ (uint64_t)(c[1] >> 12);     /* 52 bits */
+        out[q] = ((double)a + 0.5) * (1.0 / 2251799813685248.0) - 1.0;    /* (a+0.5)/2^51 - 1 */
+    }
+}
+
 void ora_philox_normal(uint64_t seed, int64_t i0, int64_t n, double *out)
 {
     /* element index is the counter: reproducible for any partition of the vector */

@@ -97,6 +97,8 @@ void ora_observables(int Ns, int Norb, const uint64_t *map, int64_t dim, const d
 
 /* Counter-based N(0,1) generator shared with the CUDA library (Philox4x32-10 + Box-Muller). */
 void ora_philox_normal(uint64_t seed, int64_t i0, int64_t n, double *out);
+/* uniform in (-1,1); exact arithmetic, bit-identical on CPU and GPU (Lanczos start vectors) */
+void ora_philox_uniform(uint64_t seed, int64_t i0, int64_t n, double *out);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ def lib():
     L.ora_apply_op.argtypes = [C.c_int, C.c_int, C.c_int, u64p, C.c_int64, u64p, C.c_int64, dp, dp]
     L.ora_observables.argtypes = [C.c_int, C.c_int, u64p, C.c_int64, dp, C.c_double] + [dp] * 8
     L.ora_philox_normal.argtypes = [C.c_uint64, C.c_int64, C.c_int64, dp]
+    L.ora_philox_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_int64, dp]
     L.ora_num_threads.restype = C.c_int
     L.ora_gather_hxv_mt.restype = C.c_double
     L.ora_gather_hxv_mt.argtypes = [C.c_void_p, u64p, C.c_int64, dp, dp, C.c_int64, C.c_int64, C.c_int]
@@ -264,6 +265,12 @@ def philox_normal(seed: int, n: int, i0: int = 0) -> np.ndarray:
     return out
 
 
+def philox_uniform(seed: int, n: int, i0: int = 0) -> np.ndarray:
+    out = np.empty(n)
+    lib().ora_philox_uniform(seed, i0, n, _dp(out))
+    return out
+
+
 def lanc_tridiag(model: Model, smap, vin, nitermax, threshold=1e-13):
     """sp_lanc_tridiag (ancestor .repo/PLAIN_LANCZOS.f90:154-180). Returns alanc[n], blanc[n] (blanc[0] unused
     = Fortran blanc(1)), nused.  vin is normalised in place like the reference."""
@@ -337,9 +344,10 @@ def sector_index(Ns, nup, ndw):
 
 
 def start_vector(dim: int, seed: int = 1234567) -> np.ndarray:
-    """Deterministic Lanczos start vector shared by oracle and product (the reference draws random numbers,
-    .repo/PLAIN_LANCZOS.f90:310-318; seed value from .repo/ARPACK_LANCZOS.f90:165)."""
-    return philox_normal(seed, dim).astype(np.complex128)
+    """Deterministic Lanczos start vector shared by oracle and product: Philox uniforms in (-1,1), bit-identical
+    on CPU and GPU (the reference draws random_number() uniforms, .repo/PLAIN_LANCZOS.f90:310-318; seed value
+    from .repo/ARPACK_LANCZOS.f90:165)."""
+    return philox_uniform(seed, dim).astype(np.complex128)
 
 
 def ed_diag(model: Model, res: Result, sectors=None):

@@ -20,7 +20,7 @@ CASES = {
 }
 
 
-def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, layout=0, hxv_kernel=0):
+def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, hloc_diag=True, layout=0, hxv_kernel=0):
     kw = dict(lanc_method="lanczos", lanc_nstates_sector=1, Lmats=64, Lreal=64)
     kw.update(case)
     p = oracle.Params(**kw)
@@ -31,7 +31,7 @@ def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, layo
     hloc = np.zeros((p.Nspin, p.Nspin, p.Norb, p.Norb), dtype=complex)
     for s in range(p.Nspin):
         for a in range(p.Norb):
-            hloc[s, s, a, a] = 0.1 * (a + 1) * (1 if s == 0 else -1)
+            hloc[s, s, a, a] = 0.1 * (a + 1) * (1 if s == 0 else -1) if hloc_diag else 0.0
         if hloc_offdiag and p.Norb > 1:
             hloc[s, s, 0, 1] = hloc[s, s, 1, 0] = 0.15
     model = oracle.Model(p, bath, hloc)
@@ -84,10 +84,11 @@ def test_sector_map_full_size_properties(oracle, edb):
         Ns = p.Ns
         ups = np.array([w for w in range(1 << Ns) if bin(w).count("1") == n], dtype=np.uint64)
         assert ups.size == s.dim_up
-        head = s.map(0, 4096)
-        assert np.array_equal(head, (ups[:4096] + (ups[0] << np.uint64(Ns))))
-        tail = s.map(s.dim - 4096, 4096)
-        assert np.array_equal(tail, ups[-4096:] + (ups[-1] << np.uint64(Ns)))
+        k = min(4096, int(s.dim_up))
+        head = s.map(0, k)
+        assert np.array_equal(head, (ups[:k] + (ups[0] << np.uint64(Ns))))
+        tail = s.map(s.dim - k, k)
+        assert np.array_equal(tail, ups[-k:] + (ups[-1] << np.uint64(Ns)))
         # checksum of checksums: sum_i map[i]*(2i+1) factorises over the two spin lists
         du = s.dim_up
         iu = np.arange(du, dtype=np.uint64)
@@ -138,6 +139,8 @@ def test_hxv_cfg2_half_filling_and_linearity(oracle, edb):
     # device Philox fill agrees with the host generator (libm differences only)
     z.fill_normal(20240607)
     assert np.abs(z.download() - v).max() < 1e-12
+    z.fill_uniform(1234567)
+    assert np.array_equal(z.download(), oracle.philox_uniform(1234567, smap.size))      # bit-identical
     # symmetry <a|H b> = <H a|b>
     w = rng.normal(size=smap.size)
     a, ha = s.vec(w), s.vec()
@@ -198,7 +201,7 @@ def test_dense_matrix_small_sector(oracle, edb):
 
 # ---------------------------------------------------------------------------------------------- Lanczos
 def test_lanczos_gs_cfg2(oracle, edb):
-    p, model, ctx, rng = make(oracle, edb, dict(Norb=1, Nbath=9), generic_bath=False)
+    p, model, ctx, rng = make(oracle, edb, dict(Norb=1, Nbath=9), generic_bath=False, hloc_diag=False)
     smap = oracle.build_sector(10, 5, 5)
     v0 = oracle.start_vector(smap.size)
     e_ref, vec_ref, nl_ref, a_ref, b_ref = oracle.lanc_gs(model, smap, v0, 512, 1e-12)
@@ -214,7 +217,13 @@ def test_lanczos_gs_cfg2(oracle, edb):
     k = 20
     assert np.abs(a[:k] - a_ref[:k]).max() < 1e-9 and np.abs(b[1:k] - b_ref[1:k]).max() < 1e-9
     obs = s.observables(v)
-    assert abs(obs["dens"][0] - 1.0) < 1e-9 and abs(obs["docc"][0] - 0.162122572520) < 1e-8
+    # a plain-Lanczos Ritz vector is only ~sqrt(1e-12) accurate, so analytic values hold to ~1e-7 ...
+    assert abs(obs["dens"][0] - 1.0) < 1e-6 and abs(obs["docc"][0] - 0.162122572520) < 1e-6
+    # ... while oracle and device, which run the same recurrence from the same start vector, agree to 1e-9
+    up = (smap & np.uint64(1)).astype(float)
+    dw = ((smap >> np.uint64(10)) & np.uint64(1)).astype(float)
+    w = np.abs(vec_ref) ** 2
+    assert abs(obs["dens"][0] - ((up + dw) * w).sum()) < 1e-9 and abs(obs["docc"][0] - (up * dw * w).sum()) < 1e-9
     v.free(); s.free(); ctx.close()
 
 
@@ -243,7 +252,15 @@ def test_apply_c_and_tridiag_chain(oracle, edb, name, sec, isite, dagger):
     vout.scale(1.0 / np.sqrt(n2))
     a, b, nu = sj.lanczos_tridiag(vout, nlanc)
     assert nu == nu_ref
-    assert np.abs(a - a_ref).max() < 1e-9 and np.abs(b - b_ref).max() < 1e-9
+    # alpha/beta to 1e-9 over the leading part; without re-orthogonalisation the trailing coefficients of a chain
+    # that exhausts a small sector amplify rounding noise, so the tail is compared through the
+    # quantity it feeds: the pole sum of add_to_lanczos_gf_normal
+    k = nlanc if mapJ.size >= 200 else min(nlanc, 12)
+    assert np.abs(a[:k] - a_ref[:k]).max() < 1e-9 and np.abs(b[:k] - b_ref[:k]).max() < 1e-9
+    lam, Z = oracle.eigh_tridiag(a, b)
+    lam0, Z0 = oracle.eigh_tridiag(a_ref, b_ref)
+    for zz in (1.0j, 3.0j, 0.5 + 1.0j):
+        assert abs((Z[0] ** 2 / (zz - lam)).sum() - (Z0[0] ** 2 / (zz - lam0)).sum()) < 1e-8
     with pytest.raises(edb.EdgpuError):
         edb.apply_c(si, si, isite, dagger, vin, vin)
     for t in (vin, vout):
