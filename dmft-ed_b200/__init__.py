@@ -62,7 +62,7 @@ ED_SYMBOLS = [
     "ed_get_sigma_matsubara", "ed_get_sigma_real", "ed_get_gimp_matsubara", "ed_get_gimp_real",
     "ed_get_g0imp_matsubara", "ed_get_g0imp_real", "ed_get_dens", "ed_get_dens_up", "ed_get_dens_dw", "ed_get_docc",
     "ed_get_mag", "ed_get_sz2_n2", "ed_get_grids", "ed_get_state_count", "ed_get_state", "ed_get_state_vector",
-    "ed_get_sector_energy", "ed_get_chain_count", "ed_get_chain", "ed_set_sectors_mask", "ed_get_timings",
+    "ed_get_sector_energy", "ed_get_sector_nlanc", "ed_get_chain_count", "ed_get_chain", "ed_set_sectors_mask", "ed_get_timings",
     "ed_host_eigh", "ed_host_eigh_tridiag",
 ]
 
@@ -142,6 +142,7 @@ def lib():
     L.ed_get_state.argtypes = [vp, C.c_int32, dp, i32p, i32p]
     L.ed_get_state_vector.argtypes = [vp, C.c_int32, dp, C.c_int64]
     L.ed_get_sector_energy.argtypes = [vp, C.c_int32, C.c_int32, dp]
+    L.ed_get_sector_nlanc.argtypes = [vp, C.c_int32, C.c_int32, i32p]
     L.ed_get_chain_count.argtypes = [vp, i32p]
     L.ed_get_chain.argtypes = [vp, C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p, dp, dp, dp, C.c_int32]
     L.ed_set_sectors_mask.argtypes = [vp, i32p, C.c_int32]
@@ -448,6 +449,11 @@ class Solver:
         e = C.c_double()
         self.check(lib().ed_get_sector_energy(self.h, nup, ndw, C.byref(e)))
         return e.value
+
+    def sector_nlanc(self, nup, ndw):
+        n = C.c_int32()
+        self.check(lib().ed_get_sector_nlanc(self.h, nup, ndw, C.byref(n)))
+        return n.value
 
     def chains(self):
         n = C.c_int32()

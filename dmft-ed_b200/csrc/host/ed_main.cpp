@@ -51,6 +51,7 @@ struct ed_solver {
     std::vector<EdState> states;
     double zeta = 0, egs = 0;
     std::map<std::pair<int, int>, double> sector_e;
+    std::map<std::pair<int, int>, int> sector_nlanc;      // Lanczos steps used per sector (0 = LAPACK sector)
     std::vector<std::pair<int, int>> mask;
     std::vector<EdChain> chains;
     std::vector<double> wm, wr;
@@ -292,6 +293,7 @@ static int ed_diag(ed_solver *s)
     const int Ns = s->Ns;
     free_states(s);
     s->sector_e.clear();
+    s->sector_nlanc.clear();
     double oldzero = 1000.0;
     for (int nup = 0; nup <= Ns; nup++)
         for (int ndw = 0; ndw <= Ns; ndw++) {                                  // isector order, ED_SETUP.f90:382-393
@@ -328,6 +330,7 @@ static int ed_diag(ed_solver *s)
                 // kept (:224-235), so the device solver returns the lowest pair (finite-T spectra: out of scope).
                 evals.push_back(e0);
                 evecs.push_back(v);
+                s->sector_nlanc[{nup, ndw}] = nl;
                 if (in.ed_sparse_H) edgpu_sector_drop_csr(sec);
             } else {
                 H.assign((size_t)dim * dim, 0.0);
@@ -609,6 +612,13 @@ extern "C" int ed_get_sector_energy(const ed_solver *s, int32_t nup, int32_t ndw
     auto it = s->sector_e.find({nup, ndw});
     if (it == s->sector_e.end()) return 1;
     *e = it->second;
+    return 0;
+}
+extern "C" int ed_get_sector_nlanc(const ed_solver *s, int32_t nup, int32_t ndw, int32_t *nlanc)
+{
+    if (!s || !nlanc) return 1;
+    auto it = s->sector_nlanc.find({nup, ndw});
+    *nlanc = it == s->sector_nlanc.end() ? 0 : it->second;
     return 0;
 }
 extern "C" int ed_get_chain_count(const ed_solver *s, int32_t *n)

@@ -88,6 +88,8 @@ int ed_get_state(const ed_solver *s, int32_t istate, double *e, int32_t *nup, in
 int ed_get_state_vector(const ed_solver *s, int32_t istate, double *vec, int64_t len);
 /* lowest eigenvalue found in sector (nup,ndw) during the last ed_solve (eigenvalues_list.ed, ED_DIAG.f90:240) */
 int ed_get_sector_energy(const ed_solver *s, int32_t nup, int32_t ndw, double *e);
+/* number of plain-Lanczos steps sp_lanc_eigh took in that sector (0: LAPACK sector, ED_DIAG.f90:99-101) */
+int ed_get_sector_nlanc(const ed_solver *s, int32_t nup, int32_t ndw, int32_t *nlanc);
 /* GF Lanczos chains of the last ed_solve (ED_GF_NORMAL.f90:187-194): count, then per chain the meta data and
  * alfa/beta (length nlanc, beta[0] unused). */
 int ed_get_chain_count(const ed_solver *s, int32_t *nchains);

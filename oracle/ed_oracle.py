@@ -320,6 +320,7 @@ class Result:
     egs: float = 0.0
     zeta: float = 0.0
     eig_by_sector: dict = field(default_factory=dict)
+    nlanc_by_sector: dict = field(default_factory=dict)
     chains: list = field(default_factory=list)     # (iorb, ispin, isign, istate, norm2, alfa, beta, nused)
     wm: np.ndarray | None = None
     wr: np.ndarray | None = None
@@ -375,7 +376,8 @@ def ed_diag(model: Model, res: Result, sectors=None):
             smap = build_sector(Ns, nup, ndw)
             if lanc_solve:
                 if p.lanc_method == "lanczos":
-                    e0, vec, _, _, _ = lanc_gs(model, smap, start_vector(dim), nitermax, p.lanc_tolerance)
+                    e0, vec, nl, _, _ = lanc_gs(model, smap, start_vector(dim), nitermax, p.lanc_tolerance)
+                    res.nlanc_by_sector[(nup, ndw)] = nl
                     evals = np.array([e0])
                     evecs = vec[:, None]
                 else:

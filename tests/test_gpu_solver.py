@@ -82,8 +82,12 @@ def test_ed_solve_cfg2_half_filling_window(oracle, edb):
     # alpha/beta of the GF chains: 1e-9 over the leading coefficients.  Plain Lanczos amplifies the 1e-14
     # differences of the seed (different summation order of CPU and GPU dot products) by about a decade per
     # step once Ritz values start converging; G and Sigma above are the stable comparison.
+    # The seeds are c/c+ applied to the Ritz vector, which depends on WHERE sp_lanc_eigh's stop test |dE|<=1e-12
+    # trips; when rounding makes CPU and GPU stop one step apart the seeds differ by ~1e-7 and only G agrees.
+    same_stop = sol.sector_nlanc(5, 5) == ref.nlanc_by_sector[(5, 5)]
     for c, r in zip(sol.chains(), ref.chains):
-        k = 10
+        k = 10 if same_stop else 3
+        assert abs(c["norm2"] - r["norm2"]) < (1e-9 if same_stop else 1e-6)
         assert np.abs(c["alfa"][:k] - r["alfa"][:k]).max() < 1e-9
         assert np.abs(c["beta"][:k] - r["beta"][:k]).max() < 1e-9
     sol.close()
