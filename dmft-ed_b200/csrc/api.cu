@@ -13,6 +13,7 @@ int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst);
 int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst);
 int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 int csr_build(edgpu_sector *s);
+int hxv_star_launches(const edgpu_sector *s);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
 
 static thread_local std::string g_null_err;
@@ -434,7 +435,7 @@ extern "C" int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y
     if (launches) {
         int per = 1;
         if (s->csr) per = 1;
-        else if (s->up->layout == 2 && ctx->par.hxv_kernel != 1 && !ctx->ham.jhflag) per = 2;
+        else if (s->up->layout == 2 && ctx->par.hxv_kernel != 1 && !ctx->ham.jhflag) per = hxv_star_launches(s);
         else per = 1 + (ctx->ham.jhflag ? 1 : 0);
         *launches = (int64_t)per * iters;
     }

@@ -1,0 +1,96 @@
+"""GPU (B200): the star-product layout + tiled kernels (layout=2, hxv_kernel=2) against the oracle and against
+the generic table kernel.  Same tolerances as test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import CASES as BASE_CASES, HXV_TOL, all_sectors, make
+
+pytestmark = pytest.mark.gpu
+
+STAR_CASES = ["cfg1", "nohf_mu", "2orb_hund", "nspin2", "3orb"]
+CASES = dict(BASE_CASES)
+CASES["3orb"] = dict(Norb=3, Nbath=1, uloc=(2.0, 1.0, 3.0), ust=1.0, jh=0.2)
+
+
+@pytest.mark.parametrize("name", STAR_CASES)
+def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name):
+    p, model, ctx, rng = make(oracle, edb, CASES[name], layout=2, hxv_kernel=2)
+    Ns = p.Ns
+    for nup, ndw in all_sectors(Ns):
+        smap = oracle.build_sector(Ns, nup, ndw)
+        s = ctx.sector(nup, ndw)
+        assert np.array_equal(s.map(), smap)                         # the reference map is layout independent
+        v = rng.normal(size=smap.size) + 1j * rng.normal(size=smap.size)
+        ref = oracle.direct_hxv(model, smap, v)
+        got = s.hxv_host(v)
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(got - ref).max() < HXV_TOL * scale, (name, nup, ndw)
+        x = s.vec(v.real)
+        assert np.array_equal(x.download(), v.real)                  # import/export permutation round trip
+        x.free(); s.free()
+    ctx.close()
+
+
+@pytest.mark.parametrize("Norb,Nbath,sec", [(1, 9, (5, 5)), (1, 9, (6, 5)), (2, 4, (5, 5)), (2, 4, (4, 6)), (3, 2, (4, 5))])
+def test_star_hxv_medium_sectors(oracle, edb, Norb, Nbath, sec):
+    case = dict(Norb=Norb, Nbath=Nbath, uloc=tuple([2.0] * Norb), ust=0.7 if Norb > 1 else 0.0, jh=0.1 if Norb > 1 else 0.0)
+    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2)
+    smap = oracle.build_sector(p.Ns, *sec)
+    s = ctx.sector(*sec)
+    v = rng.normal(size=smap.size)
+    ref = oracle.direct_hxv(model, smap, v).real
+    x, y = s.vec(v), s.vec()
+    s.hxv(x, y)
+    assert np.abs(y.download() - ref).max() < HXV_TOL * np.abs(ref).max()
+    # chain + observables + seeds work in the permuted layout
+    a_ref, b_ref, _ = oracle.lanc_tridiag(model, smap, v / np.linalg.norm(v), 12)
+    a, b, _ = s.lanczos_tridiag(x, 12)
+    assert np.abs(a - a_ref).max() < 1e-9 and np.abs(b - b_ref).max() < 1e-9
+    for t in (x, y):
+        t.free()
+    s.free()
+    ctx.close()
+
+
+def test_star_apply_c_and_observables(oracle, edb):
+    p, model, ctx, rng = make(oracle, edb, CASES["2orb_hund"], layout=2, hxv_kernel=2)
+    Ns = p.Ns
+    for (nup, ndw), isite, dagger in [((3, 3), 2, 1), ((3, 2), 8, 0), ((2, 4), 1, 1), ((3, 3), 7, 0)]:
+        mapI = oracle.build_sector(Ns, nup, ndw)
+        g = rng.normal(size=mapI.size)
+        g /= np.linalg.norm(g)
+        d = 1 if dagger else -1
+        jup, jdw = (nup + d, ndw) if isite <= Ns else (nup, ndw + d)
+        mapJ = oracle.build_sector(Ns, jup, jdw)
+        vv_ref, n2_ref = oracle.apply_op(Ns, isite, dagger, mapI, mapJ, g)
+        si, sj = ctx.sector(nup, ndw), ctx.sector(jup, jdw)
+        vin, vout = si.vec(g), sj.vec()
+        n2 = edb.apply_c(si, sj, isite, dagger, vin, vout, normalise=False)
+        assert abs(n2 - n2_ref) < 1e-13 and np.array_equal(vout.download(), vv_ref.real)
+        obs = si.observables(vin)
+        up = np.array([[(int(m) >> a) & 1 for a in range(p.Norb)] for m in mapI], dtype=float)
+        dw = np.array([[(int(m) >> (a + Ns)) & 1 for a in range(p.Norb)] for m in mapI], dtype=float)
+        assert np.abs(obs["dens"] - ((up + dw) * (g ** 2)[:, None]).sum(0)).max() < 1e-12
+        assert np.abs(obs["docc"] - ((up * dw) * (g ** 2)[:, None]).sum(0)).max() < 1e-12
+        vin.free(); vout.free(); si.free(); sj.free()
+    ctx.close()
+
+
+def test_star_equals_generic_at_cfg3_size(oracle, edb):
+    """Ns=14 half filling (11.8M states): tiled star kernels vs the generic kernel on the same Philox vector,
+    plus symmetry of H as a size-independent property."""
+    case = dict(Norb=2, Nbath=6, uloc=(2.0, 2.0), ust=1.5, jh=0.25)
+    out = {}
+    for tag, layout, kern in (("generic", 1, 1), ("star", 2, 2)):
+        p, model, ctx, rng = make(oracle, edb, case, layout=layout, hxv_kernel=kern)
+        s = ctx.sector(7, 7)
+        x, y, z, hz = s.vec().fill_normal(20240607), s.vec(), s.vec().fill_normal(99), s.vec()
+        s.hxv(x, y)
+        s.hxv(z, hz)
+        out[tag] = y.download()
+        assert abs(z.dot(y) - hz.dot(x)) < 1e-9 * abs(z.dot(y))     # <z|Hx> = <Hz|x>
+        for t in (x, y, z, hz):
+            t.free()
+        s.free()
+        ctx.close()
+    assert np.abs(out["star"] - out["generic"]).max() < HXV_TOL * np.abs(out["generic"]).max()
