@@ -319,10 +319,19 @@ extern "C" int edgpu_vec_scale(edgpu_vec *a, double alpha)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Tiled star kernels: two launches per occupation block, worth it once the sector is large; small sectors (the
+// many sectors of an ed_solve scan) are launch-bound and use the single-launch generic kernel.
+static bool use_star(const edgpu_sector *s)
+{
+    const edgpu_ctx *ctx = s->ctx;
+    if (s->up->layout != 2 || s->dw->layout != 2 || ctx->par.hxv_kernel == 1 || ctx->ham.jhflag) return false;
+    return ctx->par.hxv_kernel == 2 || s->dim >= (1ll << 21);
+}
+
 int hxv_dispatch(edgpu_sector *s, const double *x, double *y)
 {
     if (s->csr) return hxv_csr(s, x, y);
-    if (s->up->layout == 2 && s->ctx->par.hxv_kernel != 1 && !s->ctx->ham.jhflag) return hxv_star(s, x, y);
+    if (use_star(s)) return hxv_star(s, x, y);
     return hxv_generic(s, x, y);
 }
 
@@ -435,7 +444,7 @@ extern "C" int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y
     if (launches) {
         int per = 1;
         if (s->csr) per = 1;
-        else if (s->up->layout == 2 && ctx->par.hxv_kernel != 1 && !ctx->ham.jhflag) per = hxv_star_launches(s);
+        else if (use_star(s)) per = hxv_star_launches(s);
         else per = 1 + (ctx->ham.jhflag ? 1 : 0);
         *launches = (int64_t)per * iters;
     }

@@ -28,6 +28,7 @@ uint64_t edgpu_binom(int n, int k);
 static constexpr int kMaxStarCfg = 1024;      // 2^(Nbath+1), Nbath <= 9
 static constexpr int kMaxH = 9;               // hops per star configuration <= Nbath
 static constexpr int kMaxBlocks = 4096;
+static constexpr int kBigBlock = 2048;        // up-blocks at least this large use the pipelined kernel
 
 struct StarBlock {             // one occupation tuple of one spin
     int off;                   // first internal index
@@ -36,6 +37,7 @@ struct StarBlock {             // one occupation tuple of one spin
     int sgn_lower[EDGPU_MAXORB];   // (-1)^{sum_{a'<a} n_a'} as 0/1
     uint32_t magic0;               // ceil(2^32 / D0): tid / D0 == __umulhi(tid, magic0) for tid < 1024
     int ny;                        // kNT / D0
+    int nouter;                    // size / D0
 };
 
 struct StarInfo {
@@ -51,12 +53,14 @@ struct StarInfo {
     double *d_estar = nullptr;                   // [norb][ncfg]    star diagonal energies
     double pair_e = 0.0;                         // (Ust-Jh): same-spin inter-orbital density term
     // tile schedule
-    int *d_upgroups = nullptr;                   // [ngroups][2] = (first block, count)
-    int ngroups = 0, max_group_elems = 0;
+    int *d_upgroups = nullptr;                   // [ngroups][2] = (start in d_uplist, count): groups of SMALL blocks
+    int *d_uplist = nullptr;                     // block ids of the groups
+    int ngroups = 0, max_small = 0;
+    std::vector<int> big_blocks;                 // blocks handled by the persistent pipelined up kernel
     int max_block = 0;
     ~StarInfo()
     {
-        cudaFree(d_blocks); cudaFree(d_hopj); cudaFree(d_hopd); cudaFree(d_hopc); cudaFree(d_hopv); cudaFree(d_estar); cudaFree(d_upgroups);
+        cudaFree(d_blocks); cudaFree(d_hopj); cudaFree(d_hopd); cudaFree(d_hopc); cudaFree(d_hopv); cudaFree(d_estar); cudaFree(d_upgroups); cudaFree(d_uplist);
     }
 };
 
@@ -192,6 +196,7 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
             const uint64_t d0 = (uint64_t)S->D[t[0]];
             B.magic0 = (uint32_t)(((1ull << 32) + d0 - 1) / d0);      // d0 == 1 gives 2^32 -> 0: handled in the kernel
             B.ny = 768 / (int)d0;
+            B.nouter = size / (int)d0;
         }
         blockoff[key] = cur;
         cur += size;
@@ -200,18 +205,23 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
     }
     if (cur != (int)b->dim) return edgpu_fail(ctx, "star layout: internal size mismatch (%d vs %lld)", cur, (long long)b->dim);
     if ((int)S->blocks.size() > kMaxBlocks) return edgpu_fail(ctx, "star layout: too many blocks");
-    // up-pass tile groups: consecutive blocks packed up to the largest block size
-    std::vector<int> groups;
+    // up-pass schedule: blocks of >= kBigBlock configurations get the persistent double-buffered kernel; the small
+    // ones are packed into groups (up to kBigBlock elements) that one CTA walks for 4 rows at a time
+    std::vector<int> groups, uplist;
     {
-        const int cap = std::max(S->max_block, 1);
-        int first = 0, acc = 0;
+        int acc = 0, start = 0;
         for (int i = 0; i < (int)S->blocks.size(); i++) {
-            if (acc > 0 && acc + S->blocks[i].size > cap) { groups.push_back(first); groups.push_back(i - first); first = i; acc = 0; }
-            acc += S->blocks[i].size;
+            const int sz = S->blocks[i].size;
+            if (sz >= kBigBlock) { S->big_blocks.push_back(i); continue; }
+            if (acc > 0 && acc + sz > kBigBlock) { groups.push_back(start); groups.push_back((int)uplist.size() - start); start = (int)uplist.size(); acc = 0; }
+            uplist.push_back(i);
+            acc += sz;
+            S->max_small = std::max(S->max_small, sz);
         }
-        groups.push_back(first); groups.push_back((int)S->blocks.size() - first);
+        if ((int)uplist.size() > start) { groups.push_back(start); groups.push_back((int)uplist.size() - start); }
         S->ngroups = (int)groups.size() / 2;
-        S->max_group_elems = cap;
+        if (groups.empty()) { groups.push_back(0); groups.push_back(0); }
+        if (uplist.empty()) uplist.push_back(0);
     }
     // upload
     cudaStream_t st = ctx->stream;
@@ -232,6 +242,7 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
     CUDA_TRY(ctx, cudaMalloc(&S->d_hopv, sizeof(double) * hopv.size()));
     CUDA_TRY(ctx, cudaMalloc(&S->d_estar, sizeof(double) * estar.size()));
     CUDA_TRY(ctx, cudaMalloc(&S->d_upgroups, sizeof(int) * groups.size()));
+    CUDA_TRY(ctx, cudaMalloc(&S->d_uplist, sizeof(int) * uplist.size()));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_blocks, S->blocks.data(), sizeof(StarBlock) * S->blocks.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_hopj, hopj.data(), hopj.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_hopd, hopd.data(), sizeof(int16_t) * hopd.size(), cudaMemcpyHostToDevice, st));
@@ -239,6 +250,7 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_hopv, hopv.data(), sizeof(double) * hopv.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_estar, estar.data(), sizeof(double) * estar.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_upgroups, groups.data(), sizeof(int) * groups.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(S->d_uplist, uplist.data(), sizeof(int) * uplist.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     cudaFree(d_srank); cudaFree(d_D); cudaFree(d_blockoff);
     b->star = S;
@@ -261,9 +273,10 @@ static constexpr int kVec = 4;          // outputs per thread and outer step (ro
 //   s_off[a][i][h]  byte offset of the h-th source inside a [element][2] double2 plane: (j - i) * stride_a * 16
 //   s_val[a][i][h]  signed amplitude V_{a,k} * (-1)^{popc(bath bits of the star below k)}
 //   s_cnt[a][i]     number of sources, s_e[a][i] star diagonal energy (up pass only)
+struct __align__(16) HopEnt { double val; int off; int pad; };
 struct TabPtrs {
-    int *off;
-    double *val, *e;
+    HopEnt *ent;
+    double *e;
     uint8_t *cnt;
 };
 
@@ -279,8 +292,11 @@ __device__ __forceinline__ void load_tabs(const StarKParams &P, const StarBlock 
     for (int a = 0; a < NORB; a++) {
         const int Da = D[a], c0 = P.coff[B.n[a]];
         for (int t = threadIdx.x; t < Da * H; t += kNT) {
-            T.off[a * maxD * H + t] = (int)hopd[(size_t)c0 * H + t] * stride * 16;
-            T.val[a * maxD * H + t] = hopv[((size_t)a * P.ncfg + c0) * H + t];
+            HopEnt en;
+            en.val = hopv[((size_t)a * P.ncfg + c0) * H + t];
+            en.off = (int)hopd[(size_t)c0 * H + t] * stride * 16;
+            en.pad = 0;
+            T.ent[a * maxD * H + t] = en;
         }
         for (int t = threadIdx.x; t < Da; t += kNT) {
             T.cnt[a * maxD + t] = hopc[c0 + t];
@@ -297,152 +313,256 @@ __device__ __forceinline__ double2 lds128(uint32_t addr)
     return v;
 }
 
-// acc[0..3] += sg * sum_h val[h] * tile[(e + delta_h)][0..3]   for one star; tile = two [e][2] planes
-__device__ __forceinline__ void star_gather(double (&acc)[4], uint32_t a0, uint32_t plane, const int *off, const double *val,
-                                            int cnt, double sg)
+// acc[0..VEC) += sg * sum_h val[h] * tile[(e + delta_h)][0..VEC)   for one star; tile = VEC/2 planes of [e][2]
+template <int VEC>
+__device__ __forceinline__ void star_gather(double (&acc)[VEC], uint32_t a0, uint32_t plane, const HopEnt *ent, int cnt, double sg)
 {
 #pragma unroll 4
     for (int h = 0; h < cnt; h++) {
-        const double v = sg * val[h];
-        const uint32_t a = a0 + (uint32_t)off[h];
-        const double2 p = lds128(a), q = lds128(a + plane);
-        acc[0] += v * p.x; acc[1] += v * p.y; acc[2] += v * q.x; acc[3] += v * q.y;
+        const HopEnt en = ent[h];                          // one 16-byte shared-memory load: amplitude + byte offset
+        const double v = sg * en.val;
+        const uint32_t a = a0 + (uint32_t)en.off;
+        const double2 p = lds128(a);
+        acc[0] += v * p.x; acc[1] += v * p.y;
+        if (VEC == 4) {
+            const double2 q = lds128(a + plane);
+            acc[2] += v * q.x; acc[3] += v * q.y;
+        }
     }
 }
 
-// One pass over a tile held in shared memory as two planes of [element][2] doubles (element = o*D0 + i0).
-// Thread (ty, i0) walks o = ty, ty+NY, ...; F(o*D0+i0, ui, esum, acc) consumes the 4 gathered sums, where ui are
-// the impurity bits of the element and esum the sum of the star energies (up pass).
-template <int NORB, bool WITH_E, class PRE, class F>
+// One pass over a tile held in shared memory as VEC/2 planes of [batch][element][2] doubles (element = o*D0 + i0).
+// A tile holds `nbatch` independent copies of the block (row pairs in the up pass, column strips in the down
+// pass).  Thread (ty, i0) walks the combined outer index (batch, o) = ty, ty+NY, ...;
+// early = pre(batch, e, smem address) is issued before the gathers, f(batch, e, early, ui, esum, acc) consumes the
+// VEC gathered sums; ui = impurity bits of the element, esum = sum of the star energies (up pass).
+template <int NORB, int VEC, bool WITH_E, int KCH, class EARLY, class PRE, class F>
 __device__ __forceinline__ void tile_pass(const StarBlock &B, const int *D, const int *A0, const TabPtrs &T, int maxD, int H,
-                                          uint32_t s_in_addr, uint32_t plane, PRE pre, F f)
+                                          uint32_t s_in_addr, uint32_t plane, int nbatch, PRE pre, F f)
 {
     const int tid = threadIdx.x, D0 = D[0];
     const int ty = (D0 == 1) ? tid : (int)__umulhi((uint32_t)tid, B.magic0);   // tid / D0 by multiplication
     const int i0 = tid - ty * D0;
     const int NY = B.ny;                                 // kNT / D0
     if (ty >= NY) return;
-    const int O = B.size / D0;
+    const int O = B.nouter;                              // size / D0
     const uint32_t imp0 = i0 >= A0[0] ? 1u : 0u;
     const double e0 = WITH_E ? T.e[i0] : 0.0;
     const int cnt0 = T.cnt[i0];
-    const int *off0 = T.off + i0 * H;
-    const double *val0 = T.val + i0 * H;
+    const HopEnt *ent0 = T.ent + i0 * H;
+    // star 0 is the thread's own axis: its <= kRegH hop entries are loop invariant -> keep them in registers
+    // (saves the per-lane-distinct 16-byte table reads, which cost 4-8 shared-memory wavefronts per warp and hop)
+    constexpr int kRegH = 8;
+    const bool reg0 = H <= kRegH;
+    double rval[kRegH];
+    int roff[kRegH];
+#pragma unroll
+    for (int h = 0; h < kRegH; h++) {
+        const bool on = reg0 && h < cnt0;
+        const HopEnt en = on ? ent0[h] : HopEnt{0.0, 0, 0};
+        rval[h] = en.val; roff[h] = en.off;
+    }
     const double c0s = (B.sgn_lower[0] & 1) ? -1.0 : 1.0;
     const double c1s = (NORB >= 2 && (B.sgn_lower[1] & 1)) ? -1.0 : 1.0;
     const double c2s = (NORB >= 3 && (B.sgn_lower[2] & 1)) ? -1.0 : 1.0;
     const double s0 = imp0 ? -1.0 : 1.0;
-    int i1 = 0, i2 = 0;
-    if (NORB == 2) i1 = ty;
-    if (NORB >= 3) { i1 = ty; while (i1 >= D[1]) { i1 -= D[1]; i2++; } }
-    for (int o = ty; o < O; o += NY) {
-        const int e = o * D0 + i0;
-        const uint32_t a0 = s_in_addr + (uint32_t)e * 16u;
-        uint32_t ui = imp0;
-        double es = e0, s1 = 1.0, s2 = 1.0;
-        if (NORB >= 2) { const bool b = i1 >= A0[1]; ui |= b ? 2u : 0u; s1 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[maxD + i1]; }
-        if (NORB >= 3) { const bool b = i2 >= A0[2]; ui |= b ? 4u : 0u; s2 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[2 * maxD + i2]; }
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const auto early = pre(e, a0);                       // loads issued before the gathers (latency overlap)
-        // sign of star a: (-1)^{sum_{a'<a} n_a'} * prod_{a' != a} (-1)^{imp_a'}   (c/cdg rule, ED_SETUP.f90:1080-1106)
-        star_gather(acc, a0, plane, off0, val0, cnt0, c0s * s1 * s2);
-        if (NORB >= 2) star_gather(acc, a0, plane, T.off + (maxD + i1) * H, T.val + (maxD + i1) * H, T.cnt[maxD + i1], c1s * s0 * s2);
-        if (NORB >= 3) star_gather(acc, a0, plane, T.off + (2 * maxD + i2) * H, T.val + (2 * maxD + i2) * H, T.cnt[2 * maxD + i2], c2s * s0 * s1);
-        f(e, early, ui, es, acc);
-        if (NORB == 2) i1 += NY;
-        if (NORB >= 3) { i1 += NY; while (i1 >= D[1]) { i1 -= D[1]; i2++; } }
+    // (bq, i2, i1) = mixed-radix digits of the outer index, advanced by NY per step
+    int i1 = ty, i2 = 0, bq = 0;
+    const int D1 = (NORB >= 2) ? D[1] : 1, D2 = (NORB >= 3) ? D[2] : 1;
+    const bool slow_digits = NY >= D1 * 4 || (D2 == 1 && NORB >= 3);      // tiny blocks: carry loops would spin
+    auto normalise = [&](int &j1, int &j2, int &jb) {
+        if (slow_digits) {
+            j2 += j1 / D1; j1 = j1 % D1;
+            jb += j2 / D2; j2 = j2 % D2;
+        } else {
+            while (j1 >= D1) { j1 -= D1; j2++; }
+            while (j2 >= D2) { j2 -= D2; jb++; }
+        }
+    };
+    normalise(i1, i2, bq);
+    const int total = nbatch * O;
+    for (int ot0 = ty; ot0 < total; ot0 += NY * KCH) {
+        // phase A: issue the long-latency loads of the next KCH steps (y of the up pass) so that ONE memory latency
+        // is exposed per chunk instead of one per step
+        EARLY early[KCH];
+        {
+            int j1 = i1, j2 = i2, jb = bq;
+#pragma unroll
+            for (int k = 0; k < KCH; k++) {
+                const int ot = ot0 + k * NY;
+                if (ot < total) early[k] = pre(jb, ot * D0 + i0 - jb * B.size);
+                j1 += NY;
+                normalise(j1, j2, jb);
+            }
+        }
+        // phase B: gathers
+#pragma unroll
+        for (int k = 0; k < KCH; k++) {
+            const int ot = ot0 + k * NY;
+            if (ot < total) {
+                const int et = ot * D0 + i0;                     // element index inside the whole tile
+                const int e = et - bq * B.size;                  // element index inside the block
+                const uint32_t a0 = s_in_addr + (uint32_t)et * 16u;
+                uint32_t ui = imp0;
+                double es = e0, s1 = 1.0, s2 = 1.0;
+                if (NORB >= 2) { const bool b = i1 >= A0[1]; ui |= b ? 2u : 0u; s1 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[maxD + i1]; }
+                if (NORB >= 3) { const bool b = i2 >= A0[2]; ui |= b ? 4u : 0u; s2 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[2 * maxD + i2]; }
+                double acc[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = 0.0;
+                // sign of star a: (-1)^{sum_{a'<a} n_a'} * prod_{a' != a} (-1)^{imp_a'}   (c/cdg rule, ED_SETUP.f90:1080-1106)
+                if (reg0) {
+                    const double sg = c0s * s1 * s2;
+#pragma unroll
+                    for (int h = 0; h < kRegH; h++) {
+                        if (h < cnt0) {
+                            const double v = sg * rval[h];
+                            const uint32_t a = a0 + (uint32_t)roff[h];
+                            const double2 p = lds128(a);
+                            acc[0] += v * p.x; acc[1] += v * p.y;
+                            if (VEC == 4) {
+                                const double2 q = lds128(a + plane);
+                                acc[2] += v * q.x; acc[3] += v * q.y;
+                            }
+                        }
+                    }
+                } else {
+                    star_gather<VEC>(acc, a0, plane, ent0, cnt0, c0s * s1 * s2);
+                }
+                if (NORB >= 2) star_gather<VEC>(acc, a0, plane, T.ent + (maxD + i1) * H, T.cnt[maxD + i1], c1s * s0 * s2);
+                if (NORB >= 3) star_gather<VEC>(acc, a0, plane, T.ent + (2 * maxD + i2) * H, T.cnt[2 * maxD + i2], c2s * s0 * s1);
+                f(bq, e, a0, early[k], ui, es, acc);
+            }
+            i1 += NY;
+            normalise(i1, i2, bq);
+        }
     }
 }
 
 __device__ __forceinline__ TabPtrs carve_tabs(unsigned char *base, int norb, int maxD, int H)
 {
     TabPtrs T;
-    T.val = reinterpret_cast<double *>(base);
-    T.e = T.val + norb * maxD * H;
-    T.off = reinterpret_cast<int *>(T.e + norb * maxD);
-    T.cnt = reinterpret_cast<uint8_t *>(T.off + norb * maxD * H);
+    T.ent = reinterpret_cast<HopEnt *>(base);
+    T.e = reinterpret_cast<double *>(T.ent + norb * maxD * H);
+    T.cnt = reinterpret_cast<uint8_t *>(T.e + norb * maxD);
     return T;
 }
 static size_t tabs_bytes(int norb, int maxD, int H)
 {
-    return sizeof(double) * ((size_t)norb * maxD * H + (size_t)norb * maxD) + sizeof(int) * (size_t)norb * maxD * H + (size_t)norb * maxD + 64;
+    return 16 * (size_t)norb * maxD * H + sizeof(double) * (size_t)norb * maxD + (size_t)norb * maxD + 64;
 }
 
-// y[rows][blk] += (E_up + E_dw[row] + X) x + H_up x   for 4 rows and one group of up-blocks (runs after the down pass).
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent, double-buffered up pass for one up-block: y[rows][blk] += (diag + H_up) x.
+// A tile = RP row pairs x the block, stored [rp][element][2] (the two rows of a pair interleaved).  Every CTA
+// loads the star tables once, then walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile streams in
+// with cp.async (LDGSTS) while the current one is processed, so the HBM pipe stays busy during the gathers.
 template <int NORB>
 __global__ void __launch_bounds__(kNT)
-k_star_up(StarKParams P, int64_t dim_dw, int64_t ld,
-          const StarBlock *__restrict__ blocks, const int *__restrict__ groups,
+k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP,
+          const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
-          const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD, int tile_elems)
+          const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_in = reinterpret_cast<double *>(smem_raw);                       // 2 planes of [tile_elems][2]
-    double *s_dg = s_in + (size_t)4 * tile_elems;                              // [4 rows][8 imp patterns] row diagonal terms
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_dg + 32), NORB, maxD, P.H);
-    const int tid = threadIdx.x;
-    const int g = blockIdx.x;
-    const int b0 = groups[2 * g], nb = groups[2 * g + 1];
-    const int64_t r0 = (int64_t)blockIdx.y * kVec;
+    const StarBlock B = blocks[block_index];
+    const int size = B.size, tid = threadIdx.x;
+    const int tile_elems = RP * size;
+    double *s_buf = reinterpret_cast<double *>(smem_raw);                      // [2 stages][RP][size][2]
+    double *s_dg = s_buf + (size_t)4 * tile_elems;                             // [2 stages][RP][2 rows][8]
+    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_dg + (size_t)32 * RP), NORB, maxD, P.H);
+    int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
+    load_tabs<NORB>(P, B, D, hopd, hopc, hopv, estar, T, maxD, true);
+    const uint32_t buf_addr = (uint32_t)__cvta_generic_to_shared(s_buf);
+    const uint32_t stage_bytes = (uint32_t)tile_elems * 16u;
     const uint32_t impmask = (1u << NORB) - 1u;
-    if (tid < 32) {
-        // s_dg[v][ui] = E_dw[row v] + X[imp_dw(row v)][ui] + (Ust-Jh) * C(nimp(ui), 2)
-        const int v = tid >> 3, ui = tid & 7;
-        const int64_t r = (r0 + v < dim_dw) ? r0 + v : dim_dw - 1;
-        const int nimp = __popc(ui);
-        s_dg[tid] = e_dw[r] + xtab[(cfg_dw[r] & impmask) * 32u + ui] + P.pair_e * (double)(nimp * (nimp - 1) / 2);
-    }
-    const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
-    const uint32_t plane = (uint32_t)tile_elems * 16u;
-    const double *xr[4];
-    double *yr[4];
-#pragma unroll
-    for (int v = 0; v < 4; v++) {
-        const int64_t r = (r0 + v < dim_dw) ? r0 + v : dim_dw - 1;     // tail rows duplicate the last row (never stored)
-        xr[v] = x + r * ld;
-        yr[v] = y + r * ld;
-    }
-    const int nvalid = (int)((dim_dw - r0) < 4 ? (dim_dw - r0) : 4);
-    for (int bi = b0; bi < b0 + nb; bi++) {
-        const StarBlock B = blocks[bi];
-        int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
-#pragma unroll
-        for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
-        __syncthreads();
-        load_tabs<NORB>(P, B, D, hopd, hopc, hopv, estar, T, maxD, true);
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const double *src = xr[v] + B.off;
-            double *dst = s_in + (size_t)(v >> 1) * 2 * tile_elems + (v & 1);
-            for (int e = tid; e < B.size; e += kNT) dst[2 * e] = src[e];
+    const int64_t npairs = (dim_dw + 1) / 2;
+    const int64_t ntiles = (npairs + RP - 1) / RP;
+    const int boff = B.off;
+    const int64_t last = dim_dw - 1;
+
+    auto issue = [&](int64_t t, int stage) {
+        const uint32_t dst = buf_addr + (uint32_t)stage * stage_bytes;
+        for (int q = 0; q < RP; q++) {
+            // rows past the end duplicate the last row (computed, never stored)
+            int64_t ra = 2 * (t * RP + q), rb = ra + 1;
+            ra = ra < last ? ra : last;
+            rb = rb < last ? rb : last;
+            const double *xa = x + ra * ld + boff, *xb = x + rb * ld + boff;
+            const uint32_t d2 = dst + (uint32_t)q * (uint32_t)size * 16u;
+            for (int e = tid; e < size; e += kNT) {
+                cp_async8(d2 + (uint32_t)e * 16u, xa + e);
+                cp_async8(d2 + (uint32_t)e * 16u + 8u, xb + e);
+            }
         }
-        __syncthreads();
-        const int boff = B.off;
-        struct Own { double2 p, q; double y0, y1, y2, y3; };
-        tile_pass<NORB, true>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
-            [&](int e, uint32_t a0) {
-                Own w; w.p = lds128(a0); w.q = lds128(a0 + plane);
-                w.y0 = yr[0][boff + e]; w.y1 = yr[1][boff + e]; w.y2 = yr[2][boff + e]; w.y3 = yr[3][boff + e];   // H_dw x from the down pass
+        for (int i = tid; i < 16 * RP; i += kNT) {
+            // s_dg[stage][q][v][ui] = E_dw[row] + X[imp_dw(row)][ui] + (Ust-Jh) * C(nimp(ui), 2)
+            const int q = i >> 4, v = (i >> 3) & 1, ui = i & 7;
+            int64_t r = 2 * (t * RP + q) + v;
+            r = r < last ? r : last;
+            const int nimp = __popc(ui);
+            s_dg[(size_t)stage * 16 * RP + i] = e_dw[r] + xtab[(cfg_dw[r] & impmask) * 32u + ui] + P.pair_e * (double)(nimp * (nimp - 1) / 2);
+        }
+    };
+
+    int64_t t = blockIdx.x;
+    if (t < ntiles) issue(t, 0);
+    cp_async_commit();
+    int stage = 0;
+    for (; t < ntiles; t += gridDim.x, stage ^= 1) {
+        const int64_t nxt = t + gridDim.x;
+        if (nxt < ntiles) issue(nxt, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();                                  // this thread's copies of the current stage have landed
+        __syncthreads();                                     // ... and everybody's; tables + s_dg visible too
+        const double *dg = s_dg + (size_t)stage * 16 * RP;
+        const int64_t row0 = 2 * t * RP;
+        struct Own { double y0, y1; };
+        auto rows = [&](int q, double *&ya, double *&yb, bool &oka, bool &okb) {
+            const int64_t ra = row0 + 2 * q;
+            oka = ra < dim_dw; okb = ra + 1 < dim_dw;
+            ya = y + (oka ? ra : last) * ld + boff;
+            yb = y + (okb ? ra + 1 : last) * ld + boff;
+        };
+        int curq = -1, curq2 = -1;                           // row pointers are recomputed only when the row pair changes
+        double *ya = nullptr, *yb = nullptr, *ya2 = nullptr, *yb2 = nullptr;
+        bool oka = false, okb = false, oka2 = false, okb2 = false;
+        tile_pass<NORB, 2, true, 1, Own>(B, D, A0, T, maxD, P.H, buf_addr + (uint32_t)stage * stage_bytes, 0u, RP,
+            [&](int q, int e) {
+                if (q != curq2) { curq2 = q; rows(q, ya2, yb2, oka2, okb2); }
+                Own w;
+                w.y0 = ya2[e];                               // H_dw x written by the down pass
+                w.y1 = yb2[e];
                 return w;
             },
-            [&](int e, const Own &w, uint32_t ui, double es, double (&acc)[4]) {
-                const double2 p = w.p, q = w.q;
-                const double o0 = w.y0 + acc[0] + (es + s_dg[ui]) * p.x, o1 = w.y1 + acc[1] + (es + s_dg[8 + ui]) * p.y;
-                const double o2 = w.y2 + acc[2] + (es + s_dg[16 + ui]) * q.x, o3 = w.y3 + acc[3] + (es + s_dg[24 + ui]) * q.y;
-                yr[0][boff + e] = o0;
-                if (nvalid > 1) yr[1][boff + e] = o1;
-                if (nvalid > 2) yr[2][boff + e] = o2;
-                if (nvalid > 3) yr[3][boff + e] = o3;
+            [&](int q, int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
+                if (q != curq) { curq = q; rows(q, ya, yb, oka, okb); }
+                const double2 p = lds128(a0);
+                const double *dq = dg + q * 16 + ui;
+                if (oka) ya[e] = w.y0 + acc[0] + (es + dq[0]) * p.x;
+                if (okb) yb[e] = w.y1 + acc[1] + (es + dq[8]) * p.y;
             });
+        __syncthreads();                                     // all reads of this stage done before it is refilled
     }
+    cp_async_wait<0>();
 }
 
-// y[blk rows][c..c+4) = H_dw x  for one down-block (runs FIRST; every row belongs to exactly one down-block, so
-// this pass writes every element of y once); each CTA walks `spc` strips of 4 columns.
+// y[blk rows][strips] = H_dw x  for one down-block (runs FIRST; every row belongs to exactly one down-block, so
+// this pass writes every element of y once).  A tile = SP strips of 4 columns x the block rows, stored as two
+// planes [strip][row][2] (columns 0-1 and 2-3 of each strip).
 template <int NORB>
 __global__ void __launch_bounds__(kNT)
-k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int spc,
+k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ x, double *__restrict__ y, int maxD)
@@ -450,47 +570,54 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int spc,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StarBlock B = blocks[block_index];
     const int R = B.size;
-    double *s_in = reinterpret_cast<double *>(smem_raw);                       // 2 planes of [R][2]
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_in + (size_t)4 * R), NORB, maxD, P.H);
+    const int tile_rows = SP * R;
+    double *s_in = reinterpret_cast<double *>(smem_raw);                       // 2 planes of [SP][R][2]
+    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_in + (size_t)4 * tile_rows), NORB, maxD, P.H);
     const int tid = threadIdx.x;
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
     load_tabs<NORB>(P, B, D, hopd, hopc, hopv, nullptr, T, maxD, false);
     const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
-    const uint32_t plane = (uint32_t)R * 16u;
-    for (int sidx = 0; sidx < spc; sidx++) {
-        const int64_t c0 = ((int64_t)blockIdx.x * spc + sidx) * 4;
-        if (c0 >= dim_up) break;                                               // uniform across the CTA
-        __syncthreads();
-        // stage the strip: 4 contiguous doubles (32 bytes) per row; ld is a multiple of 4 so every row segment is
-        // 32-byte aligned; pad columns beyond dim_up are zero in x and are never written in y
-        const double *xs = x + (int64_t)B.off * ld + c0;
-        for (int r = tid; r < R; r += kNT) {
-            const double2 a = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld);
-            const double2 b = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + 2);
-            *reinterpret_cast<double2 *>(s_in + (size_t)2 * r) = a;
-            *reinterpret_cast<double2 *>(s_in + (size_t)2 * R + (size_t)2 * r) = b;
+    const uint32_t plane = (uint32_t)tile_rows * 16u;
+    const int64_t cbase = (int64_t)blockIdx.x * SP * 4;
+    // stage the strips: 4 contiguous doubles (32 bytes) per row and strip; ld is a multiple of 4 so every row segment
+    // is 32-byte aligned; pad columns beyond dim_up are zero in x and are never written in y
+    const double *xs = x + (int64_t)B.off * ld;
+    for (int q = 0; q < SP; q++) {
+        const int64_t c0 = cbase + 4 * q;
+        if (c0 >= dim_up) {
+            for (int r = tid; r < R; r += kNT) {
+                *reinterpret_cast<double2 *>(s_in + (size_t)2 * (q * R + r)) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = make_double2(0.0, 0.0);
+            }
+            continue;
         }
-        __syncthreads();
-        double *ys = y + (int64_t)B.off * ld + c0;
-        const int64_t left = dim_up - c0;
-        tile_pass<NORB, false>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
-            [&](int, uint32_t) { return 0; },
-            [&](int e, int, uint32_t, double, double (&acc)[4]) {
-                double *yp = ys + (int64_t)e * ld;
-                double2 a, b;
-                a.x = acc[0]; a.y = acc[1]; b.x = acc[2]; b.y = acc[3];
-                if (left >= 4) {
-                    *reinterpret_cast<double2 *>(yp) = a;
-                    *reinterpret_cast<double2 *>(yp + 2) = b;
-                } else {                                                   // last strip: keep the pad columns at zero
-                    yp[0] = a.x;
-                    if (left > 1) yp[1] = a.y;
-                    if (left > 2) yp[2] = b.x;
-                }
-            });
+        for (int r = tid; r < R; r += kNT) {
+            const double2 a = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + c0);
+            const double2 b = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + c0 + 2);
+            *reinterpret_cast<double2 *>(s_in + (size_t)2 * (q * R + r)) = a;
+            *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = b;
+        }
     }
+    __syncthreads();
+    double *ys = y + (int64_t)B.off * ld;
+    tile_pass<NORB, 4, false, 1, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane, SP,
+        [&](int, int) { return 0; },
+        [&](int q, int e, uint32_t, int, uint32_t, double, double (&acc)[4]) {
+            const int64_t c0 = cbase + 4 * q;
+            const int64_t left = dim_up - c0;
+            if (left <= 0) return;
+            double *yp = ys + (int64_t)e * ld + c0;
+            if (left >= 4) {
+                *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);
+                *reinterpret_cast<double2 *>(yp + 2) = make_double2(acc[2], acc[3]);
+            } else {                                                       // last strip: keep the pad columns at zero
+                yp[0] = acc[0];
+                if (left > 1) yp[1] = acc[1];
+                if (left > 2) yp[2] = acc[2];
+            }
+        });
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -500,6 +627,8 @@ static void fill_kparams(const StarInfo &S, StarKParams &P)
     P.norb = S.norb; P.H = S.H; P.ncfg = S.ncfg; P.pair_e = S.pair_e;
     for (int m = 0; m < 16; m++) { P.D[m] = S.D[m]; P.A0[m] = S.A0[m]; P.coff[m] = S.coff[m]; }
 }
+
+static constexpr int kStageElems = 4900;     // elements (x 16 B) per pipeline stage of the up pass / per tile of the down pass
 
 template <int NORB>
 static int launch_star(edgpu_sector *s, const double *x, double *y)
@@ -513,43 +642,47 @@ static int launch_star(edgpu_sector *s, const double *x, double *y)
     for (int m = 0; m <= U.nbath + 1; m++) maxD = std::max(maxD, U.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
     const size_t tab = tabs_bytes(NORB, maxD, U.H);
-    // ---- down pass: one launch per down-block
+    static size_t set_dw[4] = {0, 0, 0, 0}, set_up[4] = {0, 0, 0, 0};
+    // ---- down pass first (y = H_dw x): one launch per down-block
     {
         const int64_t nstrips = (s->dim_up + 3) / 4;
         for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {
             const StarBlock &B = Dn.blocks[bi];
-            const size_t smem = sizeof(double) * (size_t)B.size * 4 + tab;
+            // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
+            int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
+            SP = std::max<int64_t>(1, std::min<int64_t>(SP, nstrips / (4 * (int64_t)ctx->sm_count)));
+            const size_t smem = sizeof(double) * (size_t)B.size * 4 * SP + tab;
             if (smem > 227 * 1024) return edgpu_fail(ctx, "star down pass: block of %d rows does not fit in shared memory", B.size);
-            static size_t set_dw[4] = {0, 0, 0, 0};
             if (smem > set_dw[NORB]) {
                 CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_dw<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 set_dw[NORB] = smem;
             }
-            // strips per CTA: ~16K tile elements of work per CTA, but keep at least 4 CTAs per SM in flight
-            int64_t spc = std::max<int64_t>(1, 16384 / ((int64_t)B.size * 4));
-            spc = std::max<int64_t>(1, std::min<int64_t>(spc, nstrips / (4 * (int64_t)ctx->sm_count)));
-            const unsigned nctas = (unsigned)((nstrips + spc - 1) / spc);
-            k_star_dw<NORB><<<nctas, kNT, smem, ctx->stream>>>(PD, s->dim_up, s->ld, (int)bi, (int)spc, Dn.d_blocks, Dn.d_hopd,
+            const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
+            k_star_dw<NORB><<<nctas, kNT, smem, ctx->stream>>>(PD, s->dim_up, s->ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd,
                                                               Dn.d_hopc, Dn.d_hopv, x, y, maxD);
             CUDA_TRY(ctx, cudaGetLastError());
         }
     }
-    // ---- up pass
+    // ---- up pass (y += (diag + H_up) x): persistent double-buffered kernel, one launch per up-block
     {
-        const int tile_elems = U.max_block;
-        const size_t smem = sizeof(double) * ((size_t)4 * tile_elems + 32) + tab;
-        if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", U.max_block);
-        static size_t set_up[4] = {0, 0, 0, 0};
-        if (smem > set_up[NORB]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_up[NORB] = smem;
+        const int64_t npairs = (s->dim_dw + 1) / 2;
+        for (size_t bi = 0; bi < U.blocks.size(); bi++) {
+            const StarBlock &B = U.blocks[bi];
+            int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
+            RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
+            const size_t smem = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
+            if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
+            if (smem > set_up[NORB]) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                set_up[NORB] = smem;
+            }
+            const int64_t ntiles = (npairs + RP - 1) / RP;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / smem));
+            const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+            k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, s->dim_dw, s->ld, (int)bi, (int)RP, U.d_blocks, U.d_hopd, U.d_hopc,
+                                                              U.d_hopv, U.d_estar, s->dw->ediag, s->dw->cfg, ctx->d_xtab, x, y, maxD);
+            CUDA_TRY(ctx, cudaGetLastError());
         }
-        dim3 grid((unsigned)U.ngroups, (unsigned)((s->dim_dw + kVec - 1) / kVec));
-        if (grid.y > 65535) return edgpu_fail(ctx, "star up pass: too many row groups");
-        k_star_up<NORB><<<grid, kNT, smem, ctx->stream>>>(PU, s->dim_dw, s->ld, U.d_blocks, U.d_upgroups,
-                                                         U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar, s->dw->ediag, s->dw->cfg,
-                                                         ctx->d_xtab, x, y, maxD, tile_elems);
-        CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
 }
@@ -567,5 +700,5 @@ int hxv_star(edgpu_sector *s, const double *x, double *y)
 
 int hxv_star_launches(const edgpu_sector *s)
 {
-    return 1 + (int)s->dw->star->blocks.size();
+    return (int)s->up->star->blocks.size() + (int)s->dw->star->blocks.size();
 }

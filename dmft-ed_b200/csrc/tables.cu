@@ -245,7 +245,9 @@ int build_spin_basis(edgpu_ctx *ctx, int pspin, int n, std::shared_ptr<SpinBasis
     for (auto &p : pairs) if (p.star < 0) all_star = false;
 
     int layout = ctx->par.layout;
-    if (layout == 0) layout = (ctx->par.hxv_kernel == 2) ? 2 : 1;
+    // auto: the star-product order whenever the hop structure allows it (all BASELINE configs); it serves both the
+    // tiled star kernels and the generic table kernel
+    if (layout == 0) layout = (all_star && h.norb <= 3 && h.nbath <= 9 && ctx->par.hxv_kernel != 1) ? 2 : 1;
     if (layout == 2 && !all_star)
         return edgpu_fail(ctx, "star-product layout requested but impHloc has inter-orbital hopping");
     b->layout = layout;

