@@ -1,0 +1,211 @@
+!> ED_GPU_BINDING -- ISO_C_BINDING interface of libedgpu.so (include/edgpu.h) for dmft-ed.
+!>
+!> Thin layer: one `bind(C)` interface per C entry point plus the three wrapper routines that replace the bodies of
+!> the hot-path call sites of the reference:
+!>   gpu_lanc_eigh     <- sp_lanc_eigh / sp_eigh          ED_DIAG.f90:149-181
+!>   gpu_lanc_gf_chain <- seed loop + sp_lanc_tridiag     ED_GF_NORMAL.f90:159-192 , 212-245
+!>   gpu_observables   <- observables core                 ED_OBSERVABLES.f90:127-158
+!> It cannot be compiled in the development image (no Fortran compiler, SURVEY F3); INTEGRATION.md shows where each
+!> routine is called from.  All handles are opaque type(c_ptr); every C function returns 0 on success.
+MODULE ED_GPU_BINDING
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE ED_INPUT_VARS, only: Norb,Nbath,Nspin,hfmode,Uloc,Ust,Jh,Jx,Jp,xmu
+  USE ED_VARS_GLOBAL, only: Ns,impHloc
+  implicit none
+  private
+
+  type,bind(C) :: edgpu_params
+     integer(c_int32_t) :: norb,nbath,nspin,hfmode,layout,hxv_kernel
+     integer(c_int32_t) :: reserved(8)
+  end type edgpu_params
+
+  type(c_ptr),save :: gpu_ctx = c_null_ptr
+
+  interface
+     integer(c_int) function edgpu_init(p,device,stream,ctx) bind(C,name="edgpu_init")
+       import :: edgpu_params,c_int,c_ptr
+       type(edgpu_params),intent(in) :: p
+       integer(c_int),value          :: device
+       type(c_ptr),value             :: stream
+       type(c_ptr),intent(out)       :: ctx
+     end function edgpu_init
+     integer(c_int) function edgpu_finalize(ctx) bind(C,name="edgpu_finalize")
+       import :: c_int,c_ptr
+       type(c_ptr),value :: ctx
+     end function edgpu_finalize
+     type(c_ptr) function edgpu_last_error(ctx) bind(C,name="edgpu_last_error")
+       import :: c_ptr
+       type(c_ptr),value :: ctx
+     end function edgpu_last_error
+     integer(c_int) function edgpu_set_hamiltonian(ctx,bath,bath_len,hloc,uloc,ust,jh,jx,jp,xmu) bind(C,name="edgpu_set_hamiltonian")
+       import :: c_int,c_ptr,c_double,c_int32_t,c_double_complex
+       type(c_ptr),value                 :: ctx
+       real(c_double),intent(in)         :: bath(*)
+       integer(c_int32_t),value          :: bath_len
+       complex(c_double_complex),intent(in) :: hloc(*)
+       real(c_double),intent(in)         :: uloc(*)
+       real(c_double),value              :: ust,jh,jx,jp,xmu
+     end function edgpu_set_hamiltonian
+     integer(c_int) function edgpu_sector_build(ctx,nup,ndw,s) bind(C,name="edgpu_sector_build")
+       import :: c_int,c_ptr,c_int32_t
+       type(c_ptr),value        :: ctx
+       integer(c_int32_t),value :: nup,ndw
+       type(c_ptr),intent(out)  :: s
+     end function edgpu_sector_build
+     integer(c_int) function edgpu_sector_free(s) bind(C,name="edgpu_sector_free")
+       import :: c_int,c_ptr
+       type(c_ptr),value :: s
+     end function edgpu_sector_free
+     integer(c_int) function edgpu_sector_build_csr(s) bind(C,name="edgpu_sector_build_csr")
+       import :: c_int,c_ptr
+       type(c_ptr),value :: s
+     end function edgpu_sector_build_csr
+     integer(c_int) function edgpu_vec_alloc(s,v) bind(C,name="edgpu_vec_alloc")
+       import :: c_int,c_ptr
+       type(c_ptr),value       :: s
+       type(c_ptr),intent(out) :: v
+     end function edgpu_vec_alloc
+     integer(c_int) function edgpu_vec_free(v) bind(C,name="edgpu_vec_free")
+       import :: c_int,c_ptr
+       type(c_ptr),value :: v
+     end function edgpu_vec_free
+     integer(c_int) function edgpu_vec_fill_uniform(v,seed) bind(C,name="edgpu_vec_fill_uniform")
+       import :: c_int,c_ptr,c_int64_t
+       type(c_ptr),value        :: v
+       integer(c_int64_t),value :: seed
+     end function edgpu_vec_fill_uniform
+     integer(c_int) function edgpu_vec_download(v,host,is_cplx) bind(C,name="edgpu_vec_download")
+       import :: c_int,c_ptr,c_int32_t,c_double_complex
+       type(c_ptr),value                     :: v
+       complex(c_double_complex),intent(out) :: host(*)
+       integer(c_int32_t),value              :: is_cplx
+     end function edgpu_vec_download
+     integer(c_int) function edgpu_hxv(s,nloc,v,hv) bind(C,name="edgpu_hxv")
+       import :: c_int,c_ptr,c_int64_t,c_double_complex
+       type(c_ptr),value                     :: s
+       integer(c_int64_t),value              :: nloc
+       complex(c_double_complex),intent(in)  :: v(*)
+       complex(c_double_complex),intent(out) :: hv(*)
+     end function edgpu_hxv
+     integer(c_int) function edgpu_lanczos_gs(s,v0,nitermax,threshold,ncheck,e0,nlanc,alanc,blanc) bind(C,name="edgpu_lanczos_gs")
+       import :: c_int,c_ptr,c_int32_t,c_double
+       type(c_ptr),value               :: s,v0
+       integer(c_int32_t),value        :: nitermax,ncheck
+       real(c_double),value            :: threshold
+       real(c_double),intent(out)      :: e0
+       integer(c_int32_t),intent(out)  :: nlanc
+       type(c_ptr),value               :: alanc,blanc          ! c_null_ptr: not wanted
+     end function edgpu_lanczos_gs
+     integer(c_int) function edgpu_lanczos_tridiag(s,v,nlanc,threshold,alfa,beta,nused) bind(C,name="edgpu_lanczos_tridiag")
+       import :: c_int,c_ptr,c_int32_t,c_double
+       type(c_ptr),value              :: s,v
+       integer(c_int32_t),value       :: nlanc
+       real(c_double),value           :: threshold
+       real(c_double),intent(out)     :: alfa(*),beta(*)
+       integer(c_int32_t),intent(out) :: nused
+     end function edgpu_lanczos_tridiag
+     integer(c_int) function edgpu_apply_c(si,so,isite,dagger,vin,vout,normalise,norm2) bind(C,name="edgpu_apply_c")
+       import :: c_int,c_ptr,c_int32_t,c_double
+       type(c_ptr),value          :: si,so,vin,vout
+       integer(c_int32_t),value   :: isite,dagger,normalise
+       real(c_double),intent(out) :: norm2
+     end function edgpu_apply_c
+     integer(c_int) function edgpu_observables(s,gs,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot) bind(C,name="edgpu_observables")
+       import :: c_int,c_ptr,c_double
+       type(c_ptr),value            :: s,gs
+       real(c_double),value         :: peso
+       real(c_double),intent(inout) :: dens(*),dens_up(*),dens_dw(*),docc(*),magz(*),sz2(*),n2(*),s2tot
+     end function edgpu_observables
+  end interface
+
+  public :: gpu_ctx
+  public :: gpu_init, gpu_finalize, gpu_set_hamiltonian, gpu_check
+  public :: gpu_lanc_eigh, gpu_lanc_gf_chain, gpu_observables
+  public :: edgpu_sector_build, edgpu_sector_free, edgpu_vec_free, edgpu_hxv
+
+contains
+
+  !> `stop` with the library's message: the reference's error model (e.g. ED_HAMILTONIAN_DIRECT_HxV.f90:45,50)
+  subroutine gpu_check(ierr,where)
+    integer(c_int)   :: ierr
+    character(len=*) :: where
+    character(kind=c_char),pointer :: msg(:)
+    integer :: i
+    if(ierr==0)return
+    call c_f_pointer(edgpu_last_error(gpu_ctx),msg,[1024])
+    i=1
+    do while(i<1024 .AND. msg(i)/=c_null_char)
+       i=i+1
+    enddo
+    write(*,*)"ED GPU ERROR in "//where//": ",msg(1:i-1)
+    stop
+  end subroutine gpu_check
+
+  !> called once from ed_init_solver after init_ed_structure (ED_MAIN.f90:73)
+  subroutine gpu_init(device)
+    integer,optional   :: device
+    type(edgpu_params) :: p
+    integer(c_int)     :: dev
+    dev=-1;if(present(device))dev=device
+    p%norb=Norb; p%nbath=Nbath; p%nspin=Nspin; p%hfmode=merge(1,0,hfmode)
+    p%layout=0; p%hxv_kernel=0; p%reserved=0
+    call gpu_check(edgpu_init(p,dev,c_null_ptr,gpu_ctx),"gpu_init")
+  end subroutine gpu_init
+
+  subroutine gpu_finalize()
+    integer(c_int) :: ierr
+    ierr=edgpu_finalize(gpu_ctx)
+    gpu_ctx=c_null_ptr
+  end subroutine gpu_finalize
+
+  !> called from ed_solve after set_dmft_bath (ED_MAIN.f90:267): `bath` is the user bath vector
+  subroutine gpu_set_hamiltonian(bath)
+    real(8),dimension(:),intent(in) :: bath
+    call gpu_check(edgpu_set_hamiltonian(gpu_ctx,bath,int(size(bath),c_int32_t),impHloc,Uloc,Ust,Jh,Jx,Jp,xmu),"gpu_set_hamiltonian")
+  end subroutine gpu_set_hamiltonian
+
+  !> replaces  call build_Hv_sector(isector) ; call sp_lanc_eigh(spHtimesV_cc,e,vec,Nitermax,threshold=lanc_tolerance) ;
+  !>           call delete_Hv_sector()                                            (ED_DIAG.f90:134-186)
+  !> The eigenvector stays on the device: (sec,vec) are handles to be stored in the state list instead of cvec.
+  subroutine gpu_lanc_eigh(nup,ndw,sparse_H,Nitermax,tol,e0,sec,vec)
+    integer,intent(in)      :: nup,ndw,Nitermax
+    logical,intent(in)      :: sparse_H
+    real(8),intent(in)      :: tol
+    real(8),intent(out)     :: e0
+    type(c_ptr),intent(out) :: sec,vec
+    integer(c_int32_t)      :: nlanc
+    call gpu_check(edgpu_sector_build(gpu_ctx,int(nup,c_int32_t),int(ndw,c_int32_t),sec),"build_Hv_sector")
+    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec),"ed_buildH_c")
+    call gpu_check(edgpu_vec_alloc(sec,vec),"gpu_lanc_eigh")
+    call gpu_check(edgpu_vec_fill_uniform(vec,1234567_c_int64_t),"gpu_lanc_eigh")
+    call gpu_check(edgpu_lanczos_gs(sec,vec,int(Nitermax,c_int32_t),tol,10_c_int32_t,e0,nlanc,c_null_ptr,c_null_ptr),"sp_lanc_eigh")
+  end subroutine gpu_lanc_eigh
+
+  !> replaces one half of lanc_build_gf_normal_c (ED_GF_NORMAL.f90:150-200 for cdg, :203-253 for c):
+  !> seed = c^+_isite|gs> or c_isite|gs>, normalise, tridiagonalise in the target sector (jup,jdw).
+  subroutine gpu_lanc_gf_chain(sec_i,vec_i,jup,jdw,isite,dagger,sparse_H,nlanc,norm2,alfa_,beta_)
+    type(c_ptr),intent(in)  :: sec_i,vec_i
+    integer,intent(in)      :: jup,jdw,isite,nlanc
+    logical,intent(in)      :: dagger,sparse_H
+    real(8),intent(out)     :: norm2,alfa_(nlanc),beta_(nlanc)
+    type(c_ptr)             :: sec_j,vv
+    integer(c_int32_t)      :: nused
+    integer(c_int)          :: ierr
+    call gpu_check(edgpu_sector_build(gpu_ctx,int(jup,c_int32_t),int(jdw,c_int32_t),sec_j),"build_sector")
+    call gpu_check(edgpu_vec_alloc(sec_j,vv),"gpu_lanc_gf_chain")
+    call gpu_check(edgpu_apply_c(sec_i,sec_j,int(isite,c_int32_t),merge(1_c_int32_t,0_c_int32_t,dagger),vec_i,vv,1_c_int32_t,norm2),"apply_c")
+    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_j),"ed_buildH_c")
+    call gpu_check(edgpu_lanczos_tridiag(sec_j,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    ierr=edgpu_vec_free(vv)
+    ierr=edgpu_sector_free(sec_j)
+  end subroutine gpu_lanc_gf_chain
+
+  !> replaces the i-loop of observables_impurity (ED_OBSERVABLES.f90:127-158) for one state
+  subroutine gpu_observables(sec,vec,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot)
+    type(c_ptr),intent(in) :: sec,vec
+    real(8),intent(in)     :: peso
+    real(8),intent(inout)  :: dens(Norb),dens_up(Norb),dens_dw(Norb),docc(Norb),magz(Norb),sz2(Norb,Norb),n2(Norb,Norb),s2tot
+    call gpu_check(edgpu_observables(sec,vec,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot),"observables_impurity")
+  end subroutine gpu_observables
+
+END MODULE ED_GPU_BINDING
