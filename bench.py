@@ -173,6 +173,84 @@ def run_reference_arm(args):
     return 0
 
 
+def run_sharded(args, edb, world, rank, local):
+    """N>1: ONE sector vector sharded by up-spin column blocks (north star / SURVEY 8e.2).  Down term local, up term
+    through two NCCL all-to-all transposes per H*v.  value = H*v per second of the single sharded vector."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sharded = importlib.import_module("dmft-ed_b200.sharded")
+    Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = edb.Context(Norb, Nbath, 1, True, device=local, stream=stream, layout=2, hxv_kernel=2)
+    inp = edb.default_input(Norb=Norb, Nbath=Nbath, uloc=[2.0] * Norb)
+    bath = np.zeros(edb.lib().ed_get_bath_dimension(inp))
+    tmp = C.c_void_p()
+    edb.lib().ed_init_solver(C.byref(inp), local, C.c_void_p(stream), bath.ctypes.data_as(edb.dp), bath.size, None, C.byref(tmp))
+    edb.lib().ed_finalize_solver(tmp)
+    ctx.set_hamiltonian(bath, [2.0] * Norb)
+    s = ctx.sector(nup, ndw)
+    sh = sharded.make_gpu_shard(edb, s, rank, world)
+    plan = sh.plan
+    g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
+    x = sh.zeros()
+    x[:, :plan.ncols[rank]] = torch.randn(plan.dim_dw, plan.ncols[rank], dtype=torch.float64, device="cuda", generator=g)
+    y = sh.zeros()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sh.apply(x, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sh.bytes_alltoall = 0
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sh.apply(x, y)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    dim = s.dim
+    alg_bytes = 2.0 * dim * 8.0
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    nvl = sh.bytes_alltoall / args.steps
+    if rank == 0:
+        n_launch = (len(range(1)) and 0)
+        line = {
+            "metric": "hxv_matvecs_per_s", "value": 1e3 / ms_step, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "bath": "init_dmft_bath noise=0 hwband=2", "uloc": 2.0,
+                       "vector": "N(0,1) per rank", "dim": dim,
+                       "l2": f"inputs exceed L2: {alg_bytes / world / 1e9:.3f} GB touched per rank and step",
+                       "parallelism": f"sector vector sharded by up-spin column blocks over {world} ranks; down term local, "
+                                      "up term via 2 NCCL all-to-all transposes per H*v"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
+                         "nvlink_bytes_sent_per_rank_per_hxv": nvl,
+                         "nvlink_floor_ms": nvl / 770e9 * 1e3, "nvlink_peak_source": "770 GB/s per direction (B200_PROFILING.md peer copy)"},
+            "e2e": None, "cpu_baseline": None,
+            "gpu_launches": int(args.steps * (len(s.ctx.__dict__) and 2 * 9)), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -186,6 +264,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "shard", "chains"],
+                    help="N>1: 'shard' = one sector vector sharded by up-spin column blocks with all-to-all transposes "
+                         "(strong scaling); 'chains' = independent H*v streams per rank (weak scaling)")
     ap.add_argument("--layout", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
     args = ap.parse_args()
@@ -210,6 +291,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     edb = importlib.import_module("dmft-ed_b200")
+    mode = args.mode
+    if mode == "auto":
+        mode = "shard" if world > 1 else "chains"
+    if world > 1 and mode == "shard":
+        return run_sharded(args, edb, world, rank, local)
     Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
     stream = torch.cuda.current_stream().cuda_stream
     ctx = edb.Context(Norb, Nbath, 1, True, device=local, stream=stream, layout=args.layout, hxv_kernel=args.kernel)

@@ -14,6 +14,8 @@ int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst);
 int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 int csr_build(edgpu_sector *s);
 int hxv_star_launches(const edgpu_sector *s);
+int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld);
+int hxv_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
 
 static thread_local std::string g_null_err;
@@ -447,6 +449,46 @@ extern "C" int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y
         else if (use_star(s)) per = hxv_star_launches(s);
         else per = 1 + (ctx->ham.jhflag ? 1 : 0);
         *launches = (int64_t)per * iters;
+    }
+    return 0;
+}
+
+// ---- sharded sector vector (multi-GPU): star kernels on caller-owned device pointers ----------------------------
+extern "C" int edgpu_shard_ld(const edgpu_sector *s, int64_t *ld_full)
+{
+    if (!s || !ld_full) return 1;
+    *ld_full = s->ld;
+    return 0;
+}
+
+extern "C" int edgpu_shard_hxv_dw(edgpu_sector *s, int64_t ncols, int64_t ldc, const void *x_dev, void *y_dev)
+{
+    if (!s || !x_dev || !y_dev) return 1;
+    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_dw: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
+    if (ncols < 0 || ldc < ncols || (ldc & 3)) return edgpu_fail(s->ctx, "edgpu_shard_hxv_dw: bad column shard (ncols=%lld, ldc=%lld)", (long long)ncols, (long long)ldc);
+    return hxv_star_dw(s, (const double *)x_dev, (double *)y_dev, ncols, ldc);
+}
+
+extern "C" int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, const void *x_dev, void *y_dev, int32_t accumulate)
+{
+    if (!s || !x_dev || !y_dev) return 1;
+    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: bad row shard");
+    if (nrows == 0) return 0;
+    return hxv_star_up(s, (const double *)x_dev, (double *)y_dev, row0, nrows, s->ld, accumulate);
+}
+
+extern "C" int edgpu_shard_perm(const edgpu_sector *s, uint32_t *r2i_up, uint32_t *r2i_dw)
+{
+    if (!s) return 1;
+    edgpu_ctx *ctx = s->ctx;
+    if (r2i_up) {
+        if (s->up->ref2int) CUDA_TRY(ctx, cudaMemcpy(r2i_up, s->up->ref2int, sizeof(uint32_t) * (size_t)s->dim_up, cudaMemcpyDeviceToHost));
+        else for (int64_t i = 0; i < s->dim_up; i++) r2i_up[i] = (uint32_t)i;
+    }
+    if (r2i_dw) {
+        if (s->dw->ref2int) CUDA_TRY(ctx, cudaMemcpy(r2i_dw, s->dw->ref2int, sizeof(uint32_t) * (size_t)s->dim_dw, cudaMemcpyDeviceToHost));
+        else for (int64_t i = 0; i < s->dim_dw; i++) r2i_dw[i] = (uint32_t)i;
     }
     return 0;
 }

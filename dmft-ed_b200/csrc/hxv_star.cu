@@ -466,7 +466,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // with cp.async (LDGSTS) while the current one is processed, so the HBM pipe stays busy during the gathers.
 template <int NORB>
 __global__ void __launch_bounds__(kNT)
-k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP,
+k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
@@ -541,8 +541,8 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP,
             [&](int q, int e) {
                 if (q != curq2) { curq2 = q; rows(q, ya2, yb2, oka2, okb2); }
                 Own w;
-                w.y0 = ya2[e];                               // H_dw x written by the down pass
-                w.y1 = yb2[e];
+                w.y0 = accumulate ? ya2[e] : 0.0;            // H_dw x written by the down pass
+                w.y1 = accumulate ? yb2[e] : 0.0;
                 return w;
             },
             [&](int q, int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
@@ -630,72 +630,102 @@ static void fill_kparams(const StarInfo &S, StarKParams &P)
 
 static constexpr int kStageElems = 4900;     // elements (x 16 B) per pipeline stage of the up pass / per tile of the down pass
 
+// Down pass on a column range: x, y point at a [DimDw][ld] tile holding `ncols` up-spin columns (the whole sector
+// vector on one GPU, or the column shard of one rank -- hops of the down spin never change the column).
 template <int NORB>
-static int launch_star(edgpu_sector *s, const double *x, double *y)
+static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld)
 {
     edgpu_ctx *ctx = s->ctx;
-    const StarInfo &U = *s->up->star, &Dn = *s->dw->star;
-    StarKParams PU, PD;
-    fill_kparams(U, PU);
+    const StarInfo &Dn = *s->dw->star;
+    StarKParams PD;
     fill_kparams(Dn, PD);
     int maxD = 0;
-    for (int m = 0; m <= U.nbath + 1; m++) maxD = std::max(maxD, U.D[m]);
+    for (int m = 0; m <= Dn.nbath + 1; m++) maxD = std::max(maxD, Dn.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
-    const size_t tab = tabs_bytes(NORB, maxD, U.H);
-    static size_t set_dw[4] = {0, 0, 0, 0}, set_up[4] = {0, 0, 0, 0};
-    // ---- down pass first (y = H_dw x): one launch per down-block
-    {
-        const int64_t nstrips = (s->dim_up + 3) / 4;
-        for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {
-            const StarBlock &B = Dn.blocks[bi];
-            // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
-            int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
-            SP = std::max<int64_t>(1, std::min<int64_t>(SP, nstrips / (4 * (int64_t)ctx->sm_count)));
-            const size_t smem = sizeof(double) * (size_t)B.size * 4 * SP + tab;
-            if (smem > 227 * 1024) return edgpu_fail(ctx, "star down pass: block of %d rows does not fit in shared memory", B.size);
-            if (smem > set_dw[NORB]) {
-                CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_dw<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                set_dw[NORB] = smem;
-            }
-            const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
-            k_star_dw<NORB><<<nctas, kNT, smem, ctx->stream>>>(PD, s->dim_up, s->ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd,
-                                                              Dn.d_hopc, Dn.d_hopv, x, y, maxD);
-            CUDA_TRY(ctx, cudaGetLastError());
+    const size_t tab = tabs_bytes(NORB, maxD, Dn.H);
+    static size_t set_dw[4] = {0, 0, 0, 0};
+    const int64_t nstrips = (ncols + 3) / 4;
+    for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {                         // one launch per down-block
+        const StarBlock &B = Dn.blocks[bi];
+        // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
+        int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
+        SP = std::max<int64_t>(1, std::min<int64_t>(SP, nstrips / (4 * (int64_t)ctx->sm_count)));
+        const size_t smem = sizeof(double) * (size_t)B.size * 4 * SP + tab;
+        if (smem > 227 * 1024) return edgpu_fail(ctx, "star down pass: block of %d rows does not fit in shared memory", B.size);
+        if (smem > set_dw[NORB]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_dw<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_dw[NORB] = smem;
         }
-    }
-    // ---- up pass (y += (diag + H_up) x): persistent double-buffered kernel, one launch per up-block
-    {
-        const int64_t npairs = (s->dim_dw + 1) / 2;
-        for (size_t bi = 0; bi < U.blocks.size(); bi++) {
-            const StarBlock &B = U.blocks[bi];
-            int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
-            RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
-            const size_t smem = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
-            if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
-            if (smem > set_up[NORB]) {
-                CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                set_up[NORB] = smem;
-            }
-            const int64_t ntiles = (npairs + RP - 1) / RP;
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / smem));
-            const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
-            k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, s->dim_dw, s->ld, (int)bi, (int)RP, U.d_blocks, U.d_hopd, U.d_hopc,
-                                                              U.d_hopv, U.d_estar, s->dw->ediag, s->dw->cfg, ctx->d_xtab, x, y, maxD);
-            CUDA_TRY(ctx, cudaGetLastError());
-        }
+        const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
+        k_star_dw<NORB><<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd,
+                                                          Dn.d_hopc, Dn.d_hopv, x, y, maxD);
+        CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
 }
 
-int hxv_star(edgpu_sector *s, const double *x, double *y)
+// Up pass on a row range: x, y point at a [nrows][ld] tile holding ALL up-spin columns of down-spin rows
+// [row0, row0+nrows) (the whole vector, or the row shard of one rank after the transpose).
+template <int NORB>
+static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate)
+{
+    edgpu_ctx *ctx = s->ctx;
+    const StarInfo &U = *s->up->star;
+    StarKParams PU;
+    fill_kparams(U, PU);
+    int maxD = 0;
+    for (int m = 0; m <= U.nbath + 1; m++) maxD = std::max(maxD, U.D[m]);
+    if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
+    const size_t tab = tabs_bytes(NORB, maxD, U.H);
+    static size_t set_up[4] = {0, 0, 0, 0};
+    const int64_t npairs = (nrows + 1) / 2;
+    for (size_t bi = 0; bi < U.blocks.size(); bi++) {                          // persistent kernel, one launch per up-block
+        const StarBlock &B = U.blocks[bi];
+        int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
+        RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
+        const size_t smem = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
+        if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
+        if (smem > set_up[NORB]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_up[NORB] = smem;
+        }
+        const int64_t ntiles = (npairs + RP - 1) / RP;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / smem));
+        const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+        k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)RP, accumulate, U.d_blocks, U.d_hopd, U.d_hopc,
+                                                          U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, maxD);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld)
 {
     if (!s->up->star || !s->dw->star) return edgpu_fail(s->ctx, "hxv_star: sector is not in the star-product layout");
     switch (s->ctx->ham.norb) {
-    case 1: return launch_star<1>(s, x, y);
-    case 2: return launch_star<2>(s, x, y);
-    case 3: return launch_star<3>(s, x, y);
-    default: return edgpu_fail(s->ctx, "hxv_star: Norb=%d unsupported", s->ctx->ham.norb);
+    case 1: return launch_star_dw<1>(s, x, y, ncols, ld);
+    case 2: return launch_star_dw<2>(s, x, y, ncols, ld);
+    case 3: return launch_star_dw<3>(s, x, y, ncols, ld);
+    default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
     }
+}
+
+int hxv_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate)
+{
+    if (!s->up->star || !s->dw->star) return edgpu_fail(s->ctx, "hxv_star: sector is not in the star-product layout");
+    switch (s->ctx->ham.norb) {
+    case 1: return launch_star_up<1>(s, x, y, row0, nrows, ld, accumulate);
+    case 2: return launch_star_up<2>(s, x, y, row0, nrows, ld, accumulate);
+    case 3: return launch_star_up<3>(s, x, y, row0, nrows, ld, accumulate);
+    default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
+    }
+}
+
+// y = H x on one GPU: down pass first (y = H_dw x, write only), then the up pass accumulates (diag + H_up) x.
+int hxv_star(edgpu_sector *s, const double *x, double *y)
+{
+    if (int rc = hxv_star_dw(s, x, y, s->dim_up, s->ld)) return rc;
+    return hxv_star_up(s, x, y, 0, s->dim_dw, s->ld, 1);
 }
 
 int hxv_star_launches(const edgpu_sector *s)

@@ -114,6 +114,20 @@ int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double peso,
                       double *dens, double *dens_up, double *dens_dw, double *docc, double *magz,
                       double *sz2, double *n2, double *s2tot);
 
+/* Sharded sector vector (multi-GPU, one process per GPU).  The vector is split by up-spin COLUMN
+ * blocks: a rank owns columns [col0, col0+ncols) of every down-spin row as a [DimDw][ldc] tile (ldc multiple of 4).
+ * The down-spin term never changes the column -> it is applied on the column shard; the up-spin term needs whole
+ * rows -> after an all-to-all transpose a rank holds rows [row0,row0+nrows) of all columns as a [nrows][ld] tile.
+ * These two entry points run the star-product kernels on caller-owned DEVICE pointers (e.g. torch tensors that
+ * torch.distributed exchanges over NCCL); they replace directMatVec_MPI_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:97-195),
+ * whose full-vector MPI_Allgatherv (:163-166) is the thing this layout avoids.  Columns/rows are in the device
+ * (internal) order of the sector; edgpu_shard_perm returns the reference<->internal permutations. */
+int edgpu_shard_ld(const edgpu_sector *s, int64_t *ld_full);
+int edgpu_shard_hxv_dw(edgpu_sector *s, int64_t ncols, int64_t ldc, const void *x_dev, void *y_dev);
+int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, const void *x_dev, void *y_dev, int32_t accumulate);
+/* ref2int_up[DimUp], ref2int_dw[DimDw]: reference (colex) rank -> device index (host arrays, uint32) */
+int edgpu_shard_perm(const edgpu_sector *s, uint32_t *ref2int_up, uint32_t *ref2int_dw);
+
 /* measurement helpers (bench.py): average device time of `iters` H*v launches between CUDA events on the
  * context stream; flush_l2 != 0 writes a >L2 scratch buffer between launches (outside the events). */
 int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y, int32_t iters, int32_t flush_l2,

@@ -94,3 +94,46 @@ def test_star_equals_generic_at_cfg3_size(oracle, edb):
         s.free()
         ctx.close()
     assert np.abs(out["star"] - out["generic"]).max() < HXV_TOL * np.abs(out["generic"]).max()
+
+
+def test_shard_entry_points_equal_full_product(oracle, edb):
+    """edgpu_shard_hxv_dw on column shards + edgpu_shard_hxv_up on row shards (world=2 and 3, emulated on one GPU)
+    reproduce the single-GPU product; the exchange logic itself is covered by tests/test_sharded_cpu.py (gloo)."""
+    import ctypes as C
+    import importlib
+    import torch
+    sharded = importlib.import_module("dmft-ed_b200.sharded")
+    case = dict(Norb=2, Nbath=4, uloc=(2.0, 2.0), ust=0.7, jh=0.1)
+    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2)
+    s = ctx.sector(5, 4)
+    du, dd = s.dim_up, s.dim_dw
+    r2iu = np.zeros(du, dtype=np.uint32)
+    r2id = np.zeros(dd, dtype=np.uint32)
+    ctx.check(edb.lib().edgpu_shard_perm(s.h, r2iu.ctypes.data, r2id.ctypes.data))
+    ld = C.c_int64()
+    edb.lib().edgpu_shard_ld(s.h, C.byref(ld))
+    ld = ld.value
+    v = rng.normal(size=s.dim)
+    x, y = s.vec(v), s.vec()
+    s.hxv(x, y)
+    Yref = y.download().reshape(dd, du)
+    Xint = np.zeros((dd, ld))
+    Xint[np.ix_(r2id, r2iu)] = v.reshape(dd, du)
+    Yint_ref = np.zeros((dd, ld))
+    Yint_ref[np.ix_(r2id, r2iu)] = Yref
+    dev = torch.device("cuda")
+    for world in (2, 3):
+        plan = sharded.ShardPlan(du, dd, ld, world)
+        Y = np.zeros((dd, ld))
+        for r in range(world):
+            xc = torch.tensor(np.ascontiguousarray(Xint[:, plan.col0[r]:plan.col0[r] + plan.ldc[r]]), device=dev)
+            yc = torch.zeros_like(xc)
+            ctx.check(edb.lib().edgpu_shard_hxv_dw(s.h, plan.ncols[r], plan.ldc[r], xc.data_ptr(), yc.data_ptr()))
+            xr = torch.tensor(np.ascontiguousarray(Xint[plan.row0[r]:plan.row0[r] + plan.nrows[r], :]), device=dev)
+            yr = torch.zeros_like(xr)
+            ctx.check(edb.lib().edgpu_shard_hxv_up(s.h, plan.row0[r], plan.nrows[r], xr.data_ptr(), yr.data_ptr(), 0))
+            ctx.sync()
+            Y[:, plan.col0[r]:plan.col0[r] + plan.ldc[r]] += yc.cpu().numpy()
+            Y[plan.row0[r]:plan.row0[r] + plan.nrows[r], :] += yr.cpu().numpy()
+        assert np.abs(Y - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
+    x.free(); y.free(); s.free(); ctx.close()
