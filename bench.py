@@ -173,6 +173,12 @@ def run_reference_arm(args):
     return 0
 
 
+def star_blocks(norb, nbath, n):
+    """number of star-occupation blocks (= kernel launches of one spin pass) for n particles"""
+    import itertools
+    return sum(1 for t in itertools.product(range(nbath + 2), repeat=norb) if sum(t) == n)
+
+
 def run_sharded(args, edb, world, rank, local):
     """N>1: ONE sector vector sharded by up-spin column blocks (north star / SURVEY 8e.2).  Down term local, up term
     through two NCCL all-to-all transposes per H*v.  value = H*v per second of the single sharded vector."""
@@ -229,7 +235,6 @@ def run_sharded(args, edb, world, rank, local):
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     nvl = sh.bytes_alltoall / args.steps
     if rank == 0:
-        n_launch = (len(range(1)) and 0)
         line = {
             "metric": "hxv_matvecs_per_s", "value": 1e3 / ms_step, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -244,7 +249,7 @@ def run_sharded(args, edb, world, rank, local):
                          "nvlink_bytes_sent_per_rank_per_hxv": nvl,
                          "nvlink_floor_ms": nvl / 770e9 * 1e3, "nvlink_peak_source": "770 GB/s per direction (B200_PROFILING.md peer copy)"},
             "e2e": None, "cpu_baseline": None,
-            "gpu_launches": int(args.steps * (len(s.ctx.__dict__) and 2 * 9)), "clocks": clocks,
+            "gpu_launches": int(args.steps * (star_blocks(Norb, Nbath, nup) + star_blocks(Norb, Nbath, ndw))), "clocks": clocks,
         }
         print(json.dumps(line))
     dist.destroy_process_group()
@@ -263,6 +268,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-solve", action="store_true", help="skip the ed_solve wall-time section")
+    ap.add_argument("--solve-cfg3", action="store_true", help="also time a full ed_solve of BASELINE config 3 (Ns=14, 225 sectors)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mode", default="auto", choices=["auto", "shard", "chains"],
                     help="N>1: 'shard' = one sector vector sharded by up-spin column blocks with all-to-all transposes "
@@ -388,6 +395,26 @@ def main():
                "call": f"edgpu_vec_upload(complex(8) host) + edgpu_lanczos_tridiag(nlanc={nlanc}) = sp_lanc_tridiag at "
                        "ED_GF_NORMAL.f90:187-192", "s_per_call": te}
 
+    # ---- ed_solve wall time (BASELINE metric, second half): full sector scan + GF + Sigma + observables ------------
+    solve = None
+    if rank == 0 and world == 1 and not args.no_solve:
+        solve = {}
+        cases = [("cfg1", dict(Norb=1, Nbath=4)), ("cfg2", dict(Norb=1, Nbath=9))]
+        if args.solve_cfg3:
+            cases.append(("cfg3", dict(Norb=2, Nbath=6, uloc=[2.0, 2.0])))
+        for name, kw in cases:
+            si = edb.default_input(lanc_method="lanczos", lanc_nstates_sector=1, ed_sparse_H=0, Lmats=1024, Lreal=1024, **kw)
+            so = edb.Solver(si, device=local, stream=stream)
+            so.solve()                                    # warm-up (table builds, allocator)
+            t0 = time.perf_counter()
+            so.solve()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            st, zeta, egs = so.states()
+            solve[name] = {"wall_s": dt, "phases_s": so.timings(), "egs": egs, "n_gs": len(st),
+                           "sectors": (si.Nbath * si.Norb + si.Norb + 1) ** 2, "scan": "all sectors, lanc_method=lanczos, direct H*v"}
+            so.close()
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -407,7 +434,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes,
                          "ms_per_hxv_events": ms_kernel},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches * args.steps / max(5, args.steps)),
+            "e2e": e2e, "cpu_baseline": cpu, "ed_solve": solve, "gpu_launches": int(launches * args.steps / max(5, args.steps)),
             "clocks": clocks,
         }
         print(json.dumps(line))
