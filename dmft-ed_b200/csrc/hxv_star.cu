@@ -195,7 +195,7 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
         {
             const uint64_t d0 = (uint64_t)S->D[t[0]];
             B.magic0 = (uint32_t)(((1ull << 32) + d0 - 1) / d0);      // d0 == 1 gives 2^32 -> 0: handled in the kernel
-            B.ny = 768 / (int)d0;
+            B.ny = 512 / (int)d0;
             B.nouter = size / (int)d0;
         }
         blockoff[key] = cur;
@@ -266,7 +266,7 @@ struct StarKParams {
     double pair_e;
 };
 
-static constexpr int kNT = 768;         // threads per CTA of the tiled kernels
+static constexpr int kNT = 512;         // threads per CTA of the tiled kernels
 static constexpr int kVec = 4;          // outputs per thread and outer step (rows in the up pass, columns in the down pass)
 
 // Shared-memory star tables of one block (all NORB stars): per configuration i of star a
@@ -439,6 +439,112 @@ __device__ __forceinline__ void tile_pass(const StarBlock &B, const int *D, cons
     }
 }
 
+// Lean single-batch pass (large blocks: one row pair / one strip per tile).  Same math as tile_pass, minimal index
+// arithmetic: all addresses advance by constant strides, star-0 hop entries live in registers, and the sign of a
+// star (constant over its hops) is applied once to the partial sum instead of once per hop.
+//   VEC = 2: up pass (tile = one [element][2] plane);  VEC = 4: down pass (two planes `plane` bytes apart)
+// pre(e) -> EARLY is issued before the gathers; f(e, early, ui, esum, acc) stores the VEC results.
+template <int NORB, int VEC, bool WITH_E, class EARLY, class PRE, class F>
+__device__ __forceinline__ void lean_pass(const StarBlock &B, const int *D, const int *A0, const TabPtrs &T, int maxD, int H,
+                                          uint32_t s_in_addr, uint32_t plane, PRE pre, F f)
+{
+    const int tid = threadIdx.x, D0 = D[0];
+    const int ty = (D0 == 1) ? tid : (int)__umulhi((uint32_t)tid, B.magic0);
+    const int i0 = tid - ty * D0;
+    const int NY = B.ny;
+    if (ty >= NY) return;
+    const int O = B.nouter;
+    constexpr int kRegH = 8;
+    const int cnt0 = T.cnt[i0];
+    double rval[kRegH];
+    int roff[kRegH];
+    {
+        const HopEnt *ent0 = T.ent + i0 * H;
+#pragma unroll
+        for (int h = 0; h < kRegH; h++) {
+            const HopEnt en = (h < cnt0) ? ent0[h] : HopEnt{0.0, 0, 0};
+            rval[h] = en.val; roff[h] = en.off;
+        }
+    }
+    const bool imp0 = i0 >= A0[0];
+    const double e0 = WITH_E ? T.e[i0] : 0.0;
+    const double c0s = (B.sgn_lower[0] & 1) ? -1.0 : 1.0;
+    const double c1s = ((NORB >= 2 && (B.sgn_lower[1] & 1)) ? -1.0 : 1.0) * (imp0 ? -1.0 : 1.0);     // includes s0
+    const double c2s = ((NORB >= 3 && (B.sgn_lower[2] & 1)) ? -1.0 : 1.0) * (imp0 ? -1.0 : 1.0);
+    const int D1 = (NORB >= 2) ? D[1] : 1;
+    int i1 = ty, i2 = 0;
+    if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+    int e = ty * D0 + i0;
+    const int estep = NY * D0;
+    uint32_t a0 = s_in_addr + (uint32_t)e * 16u;
+    const uint32_t astep = (uint32_t)estep * 16u;
+    EARLY nxt = pre(e);                                   // software pipeline: the loads of step o+NY are in flight during step o
+    for (int o = ty; o < O; o += NY) {
+        const EARLY early = nxt;
+        if (o + NY < O) nxt = pre(e + estep);
+        uint32_t ui = imp0 ? 1u : 0u;
+        double es = e0, s1 = 1.0, s2 = 1.0;
+        if (NORB >= 2) { const bool b = i1 >= A0[1]; ui |= b ? 2u : 0u; s1 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[maxD + i1]; }
+        if (NORB >= 3) { const bool b = i2 >= A0[2]; ui |= b ? 4u : 0u; s2 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[2 * maxD + i2]; }
+        double acc[VEC], part[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) part[v] = 0.0;
+#pragma unroll
+        for (int h = 0; h < kRegH; h++) {
+            if (h < cnt0) {
+                const uint32_t a = a0 + (uint32_t)roff[h];
+                const double2 p = lds128(a);
+                part[0] += rval[h] * p.x; part[1] += rval[h] * p.y;
+                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += rval[h] * q.x; part[3] += rval[h] * q.y; }
+            }
+        }
+        {
+            const double sg = c0s * s1 * s2;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = sg * part[v];
+        }
+        if (NORB >= 2) {
+            const HopEnt *ent = T.ent + (maxD + i1) * H;
+            const int cnt = T.cnt[maxD + i1];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) part[v] = 0.0;
+#pragma unroll 4
+            for (int h = 0; h < cnt; h++) {
+                const HopEnt en = ent[h];
+                const uint32_t a = a0 + (uint32_t)en.off;
+                const double2 p = lds128(a);
+                part[0] += en.val * p.x; part[1] += en.val * p.y;
+                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += en.val * q.x; part[3] += en.val * q.y; }
+            }
+            const double sg = c1s * s2;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] += sg * part[v];
+        }
+        if (NORB >= 3) {
+            const HopEnt *ent = T.ent + (2 * maxD + i2) * H;
+            const int cnt = T.cnt[2 * maxD + i2];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) part[v] = 0.0;
+#pragma unroll 4
+            for (int h = 0; h < cnt; h++) {
+                const HopEnt en = ent[h];
+                const uint32_t a = a0 + (uint32_t)en.off;
+                const double2 p = lds128(a);
+                part[0] += en.val * p.x; part[1] += en.val * p.y;
+                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += en.val * q.x; part[3] += en.val * q.y; }
+            }
+            const double sg = c2s * s1;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] += sg * part[v];
+        }
+        f(e, a0, early, ui, es, acc);
+        e += estep;
+        a0 += astep;
+        i1 += NY;
+        if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+    }
+}
+
 __device__ __forceinline__ TabPtrs carve_tabs(unsigned char *base, int norb, int maxD, int H)
 {
     TabPtrs T;
@@ -466,7 +572,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // with cp.async (LDGSTS) while the current one is processed, so the HBM pipe stays busy during the gathers.
 template <int NORB>
 __global__ void __launch_bounds__(kNT)
-k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate,
+k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate, int nstage,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
@@ -477,8 +583,8 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
     const int size = B.size, tid = threadIdx.x;
     const int tile_elems = RP * size;
     double *s_buf = reinterpret_cast<double *>(smem_raw);                      // [2 stages][RP][size][2]
-    double *s_dg = s_buf + (size_t)4 * tile_elems;                             // [2 stages][RP][2 rows][8]
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_dg + (size_t)32 * RP), NORB, maxD, P.H);
+    double *s_dg = s_buf + (size_t)2 * nstage * tile_elems;                    // [stages][RP][2 rows][8]
+    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_dg + (size_t)16 * nstage * RP), NORB, maxD, P.H);
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
@@ -515,19 +621,44 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
         }
     };
 
+    // nstage == 2: one CTA per SM, the next tile streams in while the current one is processed.
+    // nstage == 1: two CTAs per SM overlap each other's load and compute phases (large blocks: twice the warps).
     int64_t t = blockIdx.x;
-    if (t < ntiles) issue(t, 0);
-    cp_async_commit();
-    int stage = 0;
-    for (; t < ntiles; t += gridDim.x, stage ^= 1) {
-        const int64_t nxt = t + gridDim.x;
-        if (nxt < ntiles) issue(nxt, stage ^ 1);
+    if (nstage == 2) {
+        if (t < ntiles) issue(t, 0);
         cp_async_commit();
-        cp_async_wait<1>();                                  // this thread's copies of the current stage have landed
+    }
+    int stage = 0;
+    for (; t < ntiles; t += gridDim.x, stage ^= (nstage - 1)) {
+        if (nstage == 2) {
+            const int64_t nxt = t + gridDim.x;
+            if (nxt < ntiles) issue(nxt, stage ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();                              // this thread's copies of the current stage have landed
+        } else {
+            issue(t, 0);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         __syncthreads();                                     // ... and everybody's; tables + s_dg visible too
         const double *dg = s_dg + (size_t)stage * 16 * RP;
         const int64_t row0 = 2 * t * RP;
         struct Own { double y0, y1; };
+        if (RP == 1 && P.H <= 8) {
+            // large block: one row pair per tile -> lean pass with constant-stride addressing
+            const int64_t ra = row0;
+            const bool oka1 = ra < dim_dw, okb1 = ra + 1 < dim_dw;
+            double *pa = y + (oka1 ? ra : last) * ld + boff, *pb = y + (okb1 ? ra + 1 : last) * ld + boff;
+            const double *dgp = dg;
+            const int acc_y = accumulate;
+            lean_pass<NORB, 2, true, Own>(B, D, A0, T, maxD, P.H, buf_addr + (uint32_t)stage * stage_bytes, 0u,
+                [=](int e) { Own w; w.y0 = acc_y ? pa[e] : 0.0; w.y1 = acc_y ? pb[e] : 0.0; return w; },
+                [=](int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
+                    const double2 p = lds128(a0);
+                    if (oka1) pa[e] = w.y0 + acc[0] + (es + dgp[ui]) * p.x;
+                    if (okb1) pb[e] = w.y1 + acc[1] + (es + dgp[8 + ui]) * p.y;
+                });
+        } else {
         auto rows = [&](int q, double *&ya, double *&yb, bool &oka, bool &okb) {
             const int64_t ra = row0 + 2 * q;
             oka = ra < dim_dw; okb = ra + 1 < dim_dw;
@@ -552,6 +683,7 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
                 if (oka) ya[e] = w.y0 + acc[0] + (es + dq[0]) * p.x;
                 if (okb) yb[e] = w.y1 + acc[1] + (es + dq[8]) * p.y;
             });
+        }
         __syncthreads();                                     // all reads of this stage done before it is refilled
     }
     cp_async_wait<0>();
@@ -602,6 +734,25 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
     }
     __syncthreads();
     double *ys = y + (int64_t)B.off * ld;
+    if (SP == 1 && P.H <= 8) {
+        const int64_t left = dim_up - cbase;
+        double *yc = ys + cbase;
+        const int64_t ldv = ld;
+        lean_pass<NORB, 4, false, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
+            [=](int) { return 0; },
+            [=](int e, uint32_t, int, uint32_t, double, double (&acc)[4]) {
+                double *yp = yc + (int64_t)e * ldv;
+                if (left >= 4) {
+                    *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);
+                    *reinterpret_cast<double2 *>(yp + 2) = make_double2(acc[2], acc[3]);
+                } else if (left > 0) {                                     // last strip: keep the pad columns at zero
+                    yp[0] = acc[0];
+                    if (left > 1) yp[1] = acc[1];
+                    if (left > 2) yp[2] = acc[2];
+                }
+            });
+        return;
+    }
     tile_pass<NORB, 4, false, 1, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane, SP,
         [&](int, int) { return 0; },
         [&](int q, int e, uint32_t, int, uint32_t, double, double (&acc)[4]) {
@@ -683,16 +834,20 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         const StarBlock &B = U.blocks[bi];
         int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
-        const size_t smem = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
+        // single stage + 2 CTAs per SM when two tiles (and two table sets) fit; else double-buffered, 1 CTA per SM
+        const size_t smem1 = sizeof(double) * ((size_t)2 * B.size * RP + (size_t)16 * RP) + tab;
+        const int nstage = 2;      // (nstage 1 = two CTAs per SM needs <= 64 registers per thread; the lean pass uses ~120)
+        (void)smem1;
+        const size_t smem = nstage == 1 ? smem1 : sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
         if (smem > set_up[NORB]) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set_up[NORB] = smem;
         }
         const int64_t ntiles = (npairs + RP - 1) / RP;
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / smem));
+        const int per_sm = nstage == 1 ? 2 : 1;
         const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
-        k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)RP, accumulate, U.d_blocks, U.d_hopd, U.d_hopc,
+        k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)RP, accumulate, nstage, U.d_blocks, U.d_hopd, U.d_hopc,
                                                           U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, maxD);
         CUDA_TRY(ctx, cudaGetLastError());
     }
