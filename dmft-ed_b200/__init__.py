@@ -166,9 +166,10 @@ def _p(a):
 # object wrappers over the C-ABI (edgpu.h)
 # ----------------------------------------------------------------------------------------------------------
 class Context:
-    def __init__(self, norb, nbath, nspin=1, hfmode=True, device=-1, stream=None, layout=0, hxv_kernel=0):
+    def __init__(self, norb, nbath, nspin=1, hfmode=True, device=-1, stream=None, layout=0, hxv_kernel=0, debug_flags=0):
         L = lib()
         p = edgpu_params(norb=norb, nbath=nbath, nspin=nspin, hfmode=int(hfmode), layout=layout, hxv_kernel=hxv_kernel)
+        p.reserved[0] = debug_flags      # bit 0: 2-column down strips, bit 1: single-stage up pass (test hooks)
         h = C.c_void_p()
         if L.edgpu_init(C.byref(p), device, C.c_void_p(stream or 0), C.byref(h)) != 0:
             raise EdgpuError(L.edgpu_last_error(None).decode())

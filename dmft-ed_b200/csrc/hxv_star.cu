@@ -306,6 +306,17 @@ __device__ __forceinline__ void load_tabs(const StarKParams &P, const StarBlock 
     }
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a 32-byte row segment of a column strip moves in ONE request
+// per thread instead of two, halving the L1TEX sector work of the (inherently 32-byte-granular) down pass.
+__device__ __forceinline__ void ldg256(const double *p, double2 &a, double2 &b)
+{
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double *p, double a0, double a1, double a2, double a3)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a0), "d"(a1), "d"(a2), "d"(a3) : "memory");
+}
+
 __device__ __forceinline__ double2 lds128(uint32_t addr)
 {
     double2 v;
@@ -479,6 +490,7 @@ __device__ __forceinline__ void lean_pass(const StarBlock &B, const int *D, cons
     uint32_t a0 = s_in_addr + (uint32_t)e * 16u;
     const uint32_t astep = (uint32_t)estep * 16u;
     EARLY nxt = pre(e);                                   // software pipeline: the loads of step o+NY are in flight during step o
+#pragma unroll 2
     for (int o = ty; o < O; o += NY) {
         const EARLY early = nxt;
         if (o + NY < O) nxt = pre(e + estep);
@@ -690,9 +702,11 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
 }
 
 // y[blk rows][strips] = H_dw x  for one down-block (runs FIRST; every row belongs to exactly one down-block, so
-// this pass writes every element of y once).  A tile = SP strips of 4 columns x the block rows, stored as two
-// planes [strip][row][2] (columns 0-1 and 2-3 of each strip).
-template <int NORB>
+// this pass writes every element of y once).  A tile = SP strips of W columns x the block rows.
+//   W = 4: two planes [strip][row][2] (columns 0-1 and 2-3 of each strip), 32-byte row segments (256-bit ld/st)
+//   W = 2: one plane, 16-byte row segments -- for blocks whose 4-column tile exceeds shared memory (Norb=3, Nbath=5:
+//          8000 rows x 32 B = 256 KB)
+template <int NORB, int W>
 __global__ void __launch_bounds__(kNT)
 k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
           const StarBlock *__restrict__ blocks,
@@ -703,8 +717,8 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
     const StarBlock B = blocks[block_index];
     const int R = B.size;
     const int tile_rows = SP * R;
-    double *s_in = reinterpret_cast<double *>(smem_raw);                       // 2 planes of [SP][R][2]
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_in + (size_t)4 * tile_rows), NORB, maxD, P.H);
+    double *s_in = reinterpret_cast<double *>(smem_raw);                       // W/2 planes of [SP][R][2]
+    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_in + (size_t)W * tile_rows), NORB, maxD, P.H);
     const int tid = threadIdx.x;
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
@@ -712,62 +726,49 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
     load_tabs<NORB>(P, B, D, hopd, hopc, hopv, nullptr, T, maxD, false);
     const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
     const uint32_t plane = (uint32_t)tile_rows * 16u;
-    const int64_t cbase = (int64_t)blockIdx.x * SP * 4;
-    // stage the strips: 4 contiguous doubles (32 bytes) per row and strip; ld is a multiple of 4 so every row segment
-    // is 32-byte aligned; pad columns beyond dim_up are zero in x and are never written in y
+    const int64_t cbase = (int64_t)blockIdx.x * SP * W;
+    // stage the strips: W contiguous doubles per row and strip; ld is a multiple of 4 so every row segment is aligned to
+    // its size; pad columns beyond dim_up are zero in x and are never written in y
     const double *xs = x + (int64_t)B.off * ld;
     for (int q = 0; q < SP; q++) {
-        const int64_t c0 = cbase + 4 * q;
-        if (c0 >= dim_up) {
-            for (int r = tid; r < R; r += kNT) {
-                *reinterpret_cast<double2 *>(s_in + (size_t)2 * (q * R + r)) = make_double2(0.0, 0.0);
-                *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = make_double2(0.0, 0.0);
-            }
-            continue;
-        }
+        const int64_t c0 = cbase + W * q;
+        const bool live = c0 < dim_up;
         for (int r = tid; r < R; r += kNT) {
-            const double2 a = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + c0);
-            const double2 b = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + c0 + 2);
+            double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+            if (live) {
+                if (W == 4) ldg256(xs + (int64_t)r * ld + c0, a, b);
+                else a = *reinterpret_cast<const double2 *>(xs + (int64_t)r * ld + c0);
+            }
             *reinterpret_cast<double2 *>(s_in + (size_t)2 * (q * R + r)) = a;
-            *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = b;
+            if (W == 4) *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = b;
         }
     }
     __syncthreads();
     double *ys = y + (int64_t)B.off * ld;
+    const int64_t ldv = ld;
+    auto store = [=](double *yp, int64_t left, const double (&acc)[W]) {
+        if (left >= W) {
+            if (W == 4) stg256(yp, acc[0], acc[1], acc[W - 2], acc[W - 1]);
+            else *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);
+        } else if (left > 0) {                                             // last strip: keep the pad columns at zero
+            yp[0] = acc[0];
+            if (left > 1) yp[1] = acc[1];
+            if (W == 4 && left > 2) yp[2] = acc[W - 2];
+        }
+    };
     if (SP == 1 && P.H <= 8) {
         const int64_t left = dim_up - cbase;
         double *yc = ys + cbase;
-        const int64_t ldv = ld;
-        lean_pass<NORB, 4, false, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
+        lean_pass<NORB, W, false, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
             [=](int) { return 0; },
-            [=](int e, uint32_t, int, uint32_t, double, double (&acc)[4]) {
-                double *yp = yc + (int64_t)e * ldv;
-                if (left >= 4) {
-                    *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);
-                    *reinterpret_cast<double2 *>(yp + 2) = make_double2(acc[2], acc[3]);
-                } else if (left > 0) {                                     // last strip: keep the pad columns at zero
-                    yp[0] = acc[0];
-                    if (left > 1) yp[1] = acc[1];
-                    if (left > 2) yp[2] = acc[2];
-                }
-            });
+            [=](int e, uint32_t, int, uint32_t, double, double (&acc)[W]) { store(yc + (int64_t)e * ldv, left, acc); });
         return;
     }
-    tile_pass<NORB, 4, false, 1, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane, SP,
+    tile_pass<NORB, W, false, 1, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane, SP,
         [&](int, int) { return 0; },
-        [&](int q, int e, uint32_t, int, uint32_t, double, double (&acc)[4]) {
-            const int64_t c0 = cbase + 4 * q;
-            const int64_t left = dim_up - c0;
-            if (left <= 0) return;
-            double *yp = ys + (int64_t)e * ld + c0;
-            if (left >= 4) {
-                *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);
-                *reinterpret_cast<double2 *>(yp + 2) = make_double2(acc[2], acc[3]);
-            } else {                                                       // last strip: keep the pad columns at zero
-                yp[0] = acc[0];
-                if (left > 1) yp[1] = acc[1];
-                if (left > 2) yp[2] = acc[2];
-            }
+        [&](int q, int e, uint32_t, int, uint32_t, double, double (&acc)[W]) {
+            const int64_t c0 = cbase + W * q;
+            store(ys + (int64_t)e * ldv + c0, dim_up - c0, acc);
         });
 }
 
@@ -794,22 +795,25 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
     for (int m = 0; m <= Dn.nbath + 1; m++) maxD = std::max(maxD, Dn.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
     const size_t tab = tabs_bytes(NORB, maxD, Dn.H);
-    static size_t set_dw[4] = {0, 0, 0, 0};
-    const int64_t nstrips = (ncols + 3) / 4;
+    static size_t set_dw[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const bool force_narrow = (ctx->par.reserved[0] & 1) != 0;                 // test hook: exercise the 2-column path
     for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {                         // one launch per down-block
         const StarBlock &B = Dn.blocks[bi];
+        const int W = (!force_narrow && sizeof(double) * (size_t)B.size * 4 + tab <= 227 * 1024) ? 4 : 2;
+        const int64_t nstrips = (ncols + W - 1) / W;
         // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
         int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
         SP = std::max<int64_t>(1, std::min<int64_t>(SP, nstrips / (4 * (int64_t)ctx->sm_count)));
-        const size_t smem = sizeof(double) * (size_t)B.size * 4 * SP + tab;
+        const size_t smem = sizeof(double) * (size_t)B.size * W * SP + tab;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star down pass: block of %d rows does not fit in shared memory", B.size);
-        if (smem > set_dw[NORB]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_dw<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_dw[NORB] = smem;
+        auto kern = (W == 4) ? k_star_dw<NORB, 4> : k_star_dw<NORB, 2>;
+        size_t &set = set_dw[NORB][W == 4 ? 1 : 0];
+        if (smem > set) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = smem;
         }
         const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
-        k_star_dw<NORB><<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd,
-                                                          Dn.d_hopc, Dn.d_hopv, x, y, maxD);
+        kern<<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, x, y, maxD);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
@@ -836,9 +840,10 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
         // single stage + 2 CTAs per SM when two tiles (and two table sets) fit; else double-buffered, 1 CTA per SM
         const size_t smem1 = sizeof(double) * ((size_t)2 * B.size * RP + (size_t)16 * RP) + tab;
-        const int nstage = 2;      // (nstage 1 = two CTAs per SM needs <= 64 registers per thread; the lean pass uses ~120)
-        (void)smem1;
-        const size_t smem = nstage == 1 ? smem1 : sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
+        // double-buffered when two stages fit (nstage 1: single stage, e.g. 8000-configuration blocks of Norb=3, Nbath=5)
+        const size_t smem2 = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
+        const int nstage = (smem2 <= 227 * 1024 && !(ctx->par.reserved[0] & 2)) ? 2 : 1;
+        const size_t smem = nstage == 1 ? smem1 : smem2;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
         if (smem > set_up[NORB]) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

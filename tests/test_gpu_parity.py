@@ -20,7 +20,7 @@ CASES = {
 }
 
 
-def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, hloc_diag=True, layout=0, hxv_kernel=0):
+def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, hloc_diag=True, layout=0, hxv_kernel=0, debug_flags=0):
     kw = dict(lanc_method="lanczos", lanc_nstates_sector=1, Lmats=64, Lreal=64)
     kw.update(case)
     p = oracle.Params(**kw)
@@ -35,7 +35,7 @@ def make(oracle, edb, case, seed=11, generic_bath=True, hloc_offdiag=False, hloc
         if hloc_offdiag and p.Norb > 1:
             hloc[s, s, 0, 1] = hloc[s, s, 1, 0] = 0.15
     model = oracle.Model(p, bath, hloc)
-    ctx = edb.Context(p.Norb, p.Nbath, p.Nspin, p.hfmode, layout=layout, hxv_kernel=hxv_kernel)
+    ctx = edb.Context(p.Norb, p.Nbath, p.Nspin, p.hfmode, layout=layout, hxv_kernel=hxv_kernel, debug_flags=debug_flags)
     ctx.set_hamiltonian(bath, p.uloc, p.ust, p.jh, p.jx, p.jp, p.xmu, hloc=hloc)
     return p, model, ctx, rng
 

@@ -31,10 +31,11 @@ def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name):
     ctx.close()
 
 
+@pytest.mark.parametrize("flags", [0, 3])           # 3 = fallback paths: 2-column down strips + single-stage up pass
 @pytest.mark.parametrize("Norb,Nbath,sec", [(1, 9, (5, 5)), (1, 9, (6, 5)), (2, 4, (5, 5)), (2, 4, (4, 6)), (3, 2, (4, 5))])
-def test_star_hxv_medium_sectors(oracle, edb, Norb, Nbath, sec):
+def test_star_hxv_medium_sectors(oracle, edb, Norb, Nbath, sec, flags):
     case = dict(Norb=Norb, Nbath=Nbath, uloc=tuple([2.0] * Norb), ust=0.7 if Norb > 1 else 0.0, jh=0.1 if Norb > 1 else 0.0)
-    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2)
+    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2, debug_flags=flags)
     smap = oracle.build_sector(p.Ns, *sec)
     s = ctx.sector(*sec)
     v = rng.normal(size=smap.size)
