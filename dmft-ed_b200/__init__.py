@@ -55,7 +55,7 @@ EDGPU_SYMBOLS = [
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
     "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_observables",
-    "edgpu_shard_ld", "edgpu_shard_hxv_dw", "edgpu_shard_hxv_up", "edgpu_shard_perm",
+    "edgpu_shard_ld", "edgpu_shard_hxv_dw", "edgpu_shard_hxv_up", "edgpu_shard_hxv_up_slabs", "edgpu_shard_perm",
     "edgpu_bench_hxv", "edgpu_device_info", "edgpu_sync",
 ]
 ED_SYMBOLS = [
@@ -123,6 +123,7 @@ def lib():
     L.edgpu_shard_ld.argtypes = [vp, i64p]
     L.edgpu_shard_hxv_dw.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
     L.edgpu_shard_hxv_up.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, C.c_int32]
+    L.edgpu_shard_hxv_up_slabs.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, i64p, i64p, vp, vp, C.c_int32]
     L.edgpu_shard_perm.argtypes = [vp, vp, vp]
     L.edgpu_bench_hxv.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, dp, i64p]
     L.edgpu_device_info.argtypes = [vp, i32p, i64p, i64p]

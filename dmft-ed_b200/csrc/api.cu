@@ -16,6 +16,8 @@ int csr_build(edgpu_sector *s);
 int hxv_star_launches(const edgpu_sector *s);
 int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld);
 int hxv_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate);
+int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int nslab,
+                      const int64_t *col0, const int64_t *ldc, int accumulate);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
 
 static thread_local std::string g_null_err;
@@ -476,6 +478,16 @@ extern "C" int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, 
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: bad row shard");
     if (nrows == 0) return 0;
     return hxv_star_up(s, (const double *)x_dev, (double *)y_dev, row0, nrows, s->ld, accumulate);
+}
+
+extern "C" int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nslab, const int64_t *col0,
+                                        const int64_t *ldc, const void *x_dev, void *y_dev, int32_t accumulate)
+{
+    if (!s || !x_dev || !y_dev || !col0 || !ldc) return 1;
+    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: needs the star-product layout");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: bad row shard");
+    if (nrows == 0) return 0;
+    return hxv_star_up_slabs(s, (const double *)x_dev, (double *)y_dev, row0, nrows, nslab, col0, ldc, accumulate);
 }
 
 extern "C" int edgpu_shard_perm(const edgpu_sector *s, uint32_t *r2i_up, uint32_t *r2i_dw)

@@ -578,13 +578,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Row shard of a multi-GPU run: after the all-to-all the rows of this rank arrive as one slab per source rank
+// ([nrows][ldc_p] each, source rank p owns columns [col0_p, col0_p + ldc_p)); the up pass reads and writes the slabs
+// in place instead of paying an unpack and a pack pass.  n == 1 (single GPU / contiguous rows) is the plain layout.
+struct SlabMap {
+    int n, ldc0;
+    unsigned magic;                 // ceil(2^32 / ldc0): column / ldc0 by multiplication
+    int col0[8], ldc[8];
+    long long base[8];              // element offset of slab p
+};
+__device__ __forceinline__ int64_t slab_off(const SlabMap &M, int64_t row, int c)
+{
+    int p = (int)__umulhi((unsigned)c, M.magic);
+    p = p < M.n - 1 ? p : M.n - 1;
+    return M.base[p] + row * M.ldc[p] + (c - M.col0[p]);
+}
+
 // Persistent, double-buffered up pass for one up-block: y[rows][blk] += (diag + H_up) x.
 // A tile = RP row pairs x the block, stored [rp][element][2] (the two rows of a pair interleaved).  Every CTA
 // loads the star tables once, then walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile streams in
 // with cp.async (LDGSTS) while the current one is processed, so the HBM pipe stays busy during the gathers.
-template <int NORB>
+template <int NORB, bool SLAB>
 __global__ void __launch_bounds__(kNT)
-k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate, int nstage,
+k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate, int nstage,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
@@ -619,8 +635,13 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
             const double *xa = x + ra * ld + boff, *xb = x + rb * ld + boff;
             const uint32_t d2 = dst + (uint32_t)q * (uint32_t)size * 16u;
             for (int e = tid; e < size; e += kNT) {
-                cp_async8(d2 + (uint32_t)e * 16u, xa + e);
-                cp_async8(d2 + (uint32_t)e * 16u + 8u, xb + e);
+                if (SLAB) {
+                    cp_async8(d2 + (uint32_t)e * 16u, x + slab_off(M, ra, boff + e));
+                    cp_async8(d2 + (uint32_t)e * 16u + 8u, x + slab_off(M, rb, boff + e));
+                } else {
+                    cp_async8(d2 + (uint32_t)e * 16u, xa + e);
+                    cp_async8(d2 + (uint32_t)e * 16u + 8u, xb + e);
+                }
             }
         }
         for (int i = tid; i < 16 * RP; i += kNT) {
@@ -663,19 +684,36 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
             double *pa = y + (oka1 ? ra : last) * ld + boff, *pb = y + (okb1 ? ra + 1 : last) * ld + boff;
             const double *dgp = dg;
             const int acc_y = accumulate;
+            const int64_t rra = oka1 ? ra : last, rrb = okb1 ? ra + 1 : last;
+            double *yy = y;
             lean_pass<NORB, 2, true, Own>(B, D, A0, T, maxD, P.H, buf_addr + (uint32_t)stage * stage_bytes, 0u,
-                [=](int e) { Own w; w.y0 = acc_y ? pa[e] : 0.0; w.y1 = acc_y ? pb[e] : 0.0; return w; },
+                [=](int e) {
+                    Own w;
+                    if (SLAB) { w.y0 = acc_y ? yy[slab_off(M, rra, boff + e)] : 0.0; w.y1 = acc_y ? yy[slab_off(M, rrb, boff + e)] : 0.0; }
+                    else { w.y0 = acc_y ? pa[e] : 0.0; w.y1 = acc_y ? pb[e] : 0.0; }
+                    return w;
+                },
                 [=](int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
                     const double2 p = lds128(a0);
-                    if (oka1) pa[e] = w.y0 + acc[0] + (es + dgp[ui]) * p.x;
-                    if (okb1) pb[e] = w.y1 + acc[1] + (es + dgp[8 + ui]) * p.y;
+                    const double o0 = w.y0 + acc[0] + (es + dgp[ui]) * p.x, o1 = w.y1 + acc[1] + (es + dgp[8 + ui]) * p.y;
+                    if (SLAB) {
+                        if (oka1) yy[slab_off(M, rra, boff + e)] = o0;
+                        if (okb1) yy[slab_off(M, rrb, boff + e)] = o1;
+                    } else {
+                        if (oka1) pa[e] = o0;
+                        if (okb1) pb[e] = o1;
+                    }
                 });
         } else {
         auto rows = [&](int q, double *&ya, double *&yb, bool &oka, bool &okb) {
             const int64_t ra = row0 + 2 * q;
             oka = ra < dim_dw; okb = ra + 1 < dim_dw;
-            ya = y + (oka ? ra : last) * ld + boff;
-            yb = y + (okb ? ra + 1 : last) * ld + boff;
+            // SLAB: the "pointers" carry the row number; the element address is resolved per access
+            ya = SLAB ? reinterpret_cast<double *>(oka ? ra : last) : y + (oka ? ra : last) * ld + boff;
+            yb = SLAB ? reinterpret_cast<double *>(okb ? ra + 1 : last) : y + (okb ? ra + 1 : last) * ld + boff;
+        };
+        auto at = [&](double *rowp, int e) -> double * {
+            return SLAB ? y + slab_off(M, reinterpret_cast<int64_t>(rowp), boff + e) : rowp + e;
         };
         int curq = -1, curq2 = -1;                           // row pointers are recomputed only when the row pair changes
         double *ya = nullptr, *yb = nullptr, *ya2 = nullptr, *yb2 = nullptr;
@@ -684,16 +722,16 @@ k_star_up(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int RP, in
             [&](int q, int e) {
                 if (q != curq2) { curq2 = q; rows(q, ya2, yb2, oka2, okb2); }
                 Own w;
-                w.y0 = accumulate ? ya2[e] : 0.0;            // H_dw x written by the down pass
-                w.y1 = accumulate ? yb2[e] : 0.0;
+                w.y0 = accumulate ? *at(ya2, e) : 0.0;       // H_dw x written by the down pass
+                w.y1 = accumulate ? *at(yb2, e) : 0.0;
                 return w;
             },
             [&](int q, int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
                 if (q != curq) { curq = q; rows(q, ya, yb, oka, okb); }
                 const double2 p = lds128(a0);
                 const double *dq = dg + q * 16 + ui;
-                if (oka) ya[e] = w.y0 + acc[0] + (es + dq[0]) * p.x;
-                if (okb) yb[e] = w.y1 + acc[1] + (es + dq[8]) * p.y;
+                if (oka) *at(ya, e) = w.y0 + acc[0] + (es + dq[0]) * p.x;
+                if (okb) *at(yb, e) = w.y1 + acc[1] + (es + dq[8]) * p.y;
             });
         }
         __syncthreads();                                     // all reads of this stage done before it is refilled
@@ -822,7 +860,8 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
 // Up pass on a row range: x, y point at a [nrows][ld] tile holding ALL up-spin columns of down-spin rows
 // [row0, row0+nrows) (the whole vector, or the row shard of one rank after the transpose).
 template <int NORB>
-static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate)
+static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate,
+                          const SlabMap *slabs = nullptr)
 {
     edgpu_ctx *ctx = s->ctx;
     const StarInfo &U = *s->up->star;
@@ -832,7 +871,10 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
     for (int m = 0; m <= U.nbath + 1; m++) maxD = std::max(maxD, U.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
     const size_t tab = tabs_bytes(NORB, maxD, U.H);
-    static size_t set_up[4] = {0, 0, 0, 0};
+    static size_t set_up[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    SlabMap M;
+    memset(&M, 0, sizeof(M));
+    if (slabs) M = *slabs; else { M.n = 1; M.ldc0 = (int)ld; M.magic = 0; M.ldc[0] = (int)ld; }
     const int64_t npairs = (nrows + 1) / 2;
     for (size_t bi = 0; bi < U.blocks.size(); bi++) {                          // persistent kernel, one launch per up-block
         const StarBlock &B = U.blocks[bi];
@@ -845,14 +887,16 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         const int nstage = (smem2 <= 227 * 1024 && !(ctx->par.reserved[0] & 2)) ? 2 : 1;
         const size_t smem = nstage == 1 ? smem1 : smem2;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
-        if (smem > set_up[NORB]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_star_up<NORB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_up[NORB] = smem;
+        auto kern = slabs ? k_star_up<NORB, true> : k_star_up<NORB, false>;
+        size_t &set = set_up[NORB][slabs ? 1 : 0];
+        if (smem > set) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = smem;
         }
         const int64_t ntiles = (npairs + RP - 1) / RP;
         const int per_sm = nstage == 1 ? 2 : 1;
         const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
-        k_star_up<NORB><<<nctas, kNT, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)RP, accumulate, nstage, U.d_blocks, U.d_hopd, U.d_hopc,
+        kern<<<nctas, kNT, smem, ctx->stream>>>(PU, M, nrows, ld, (int)bi, (int)RP, accumulate, nstage, U.d_blocks, U.d_hopd, U.d_hopc,
                                                           U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, maxD);
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -866,6 +910,35 @@ int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int6
     case 1: return launch_star_dw<1>(s, x, y, ncols, ld);
     case 2: return launch_star_dw<2>(s, x, y, ncols, ld);
     case 3: return launch_star_dw<3>(s, x, y, ncols, ld);
+    default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
+    }
+}
+
+// Up pass on a row shard stored as per-source-rank slabs (x and y share the slab layout): nslab slabs, slab p holds
+// columns [col0[p], col0[p]+ldc[p]) of the nrows rows, [nrows][ldc[p]] each, packed back to back.
+int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int nslab,
+                      const int64_t *col0, const int64_t *ldc, int accumulate)
+{
+    if (!s->up->star || !s->dw->star) return edgpu_fail(s->ctx, "hxv_star: sector is not in the star-product layout");
+    if (nslab < 1 || nslab > 8) return edgpu_fail(s->ctx, "hxv_star_up_slabs: 1..8 slabs supported (got %d)", nslab);
+    SlabMap M;
+    memset(&M, 0, sizeof(M));
+    M.n = nslab;
+    M.ldc0 = (int)ldc[0];
+    if (M.ldc0 <= 0) return edgpu_fail(s->ctx, "hxv_star_up_slabs: empty first slab");
+    M.magic = (unsigned)(((1ull << 32) + (uint64_t)M.ldc0 - 1) / (uint64_t)M.ldc0);
+    if (M.ldc0 == 1) return edgpu_fail(s->ctx, "hxv_star_up_slabs: slab width must be > 1");
+    long long base = 0;
+    for (int p = 0; p < nslab; p++) {
+        if (p < nslab - 1 && ldc[p] != ldc[0]) return edgpu_fail(s->ctx, "hxv_star_up_slabs: all but the last slab must have equal width");
+        if (col0[p] != (int64_t)p * ldc[0]) return edgpu_fail(s->ctx, "hxv_star_up_slabs: slabs must tile the columns in order");
+        M.col0[p] = (int)col0[p]; M.ldc[p] = (int)ldc[p]; M.base[p] = base;
+        base += (long long)nrows * ldc[p];
+    }
+    switch (s->ctx->ham.norb) {
+    case 1: return launch_star_up<1>(s, x, y, row0, nrows, s->ld, accumulate, &M);
+    case 2: return launch_star_up<2>(s, x, y, row0, nrows, s->ld, accumulate, &M);
+    case 3: return launch_star_up<3>(s, x, y, row0, nrows, s->ld, accumulate, &M);
     default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
     }
 }

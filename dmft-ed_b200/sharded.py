@@ -71,15 +71,28 @@ class ShardedHxv:
     def zeros(self):
         return torch.zeros(self.plan.dim_dw, self.ldc, dtype=torch.float64, device=self.device)
 
-    def _all_to_all(self, out, inp, out_split, in_split):
+    def _all_to_all(self, out, inp, out_split, in_split, async_op=False):
         if self.plan.world == 1:
             out.copy_(inp)
-            return
-        dist.all_to_all_single(out, inp, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
+            return None
         self.bytes_alltoall += 8 * (sum(in_split) - in_split[self.rank])
+        return dist.all_to_all_single(out, inp, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group,
+                                      async_op=async_op)
 
     def apply(self, x_cols: torch.Tensor, y_cols: torch.Tensor):
         P = self.plan
+        if hasattr(self.ops, "up_slabs"):
+            # transpose #1 runs on NCCL's stream WHILE the down-spin term (local: down hops keep the column) runs on
+            # the compute stream; the up-spin term then works directly on the received slabs and writes the slabs
+            # that transpose #2 sends back -- no pack/unpack passes.
+            work = self._all_to_all(self.recv_cols, x_cols.reshape(-1), self.out_split, self.in_split, async_op=True)
+            self.ops.dw(x_cols, y_cols)
+            if work is not None:
+                work.wait()
+            self.ops.up_slabs(P.row0[self.rank], self.nrows, P.col0, P.ldc, self.recv_cols, self.send_rows)
+            self._all_to_all(self.tmp_cols.reshape(-1), self.send_rows, self.in_split, self.out_split)
+            y_cols += self.tmp_cols
+            return y_cols
         # 1. down-spin term on the column shard (local: down hops keep the column)
         self.ops.dw(x_cols, y_cols)
         # 2. transpose #1: slab of rows [row0[p], row0[p]+nrows[p]) of my columns -> rank p (slabs are contiguous)
@@ -141,6 +154,13 @@ class GpuOps:
     def up(self, row0, nrows, x_rows, y_rows):
         assert x_rows.is_contiguous() and y_rows.is_contiguous()
         self.s.ctx.check(self.edb.lib().edgpu_shard_hxv_up(self.s.h, row0, nrows, x_rows.data_ptr(), y_rows.data_ptr(), 0))
+
+    def up_slabs(self, row0, nrows, col0, ldc, x_slabs, y_slabs):
+        import ctypes as C
+        n = len(col0)
+        c0 = (C.c_int64 * n)(*col0)
+        lc = (C.c_int64 * n)(*ldc)
+        self.s.ctx.check(self.edb.lib().edgpu_shard_hxv_up_slabs(self.s.h, row0, nrows, n, c0, lc, x_slabs.data_ptr(), y_slabs.data_ptr(), 0))
 
 
 def make_gpu_shard(edb, sector, rank, world, group=None):

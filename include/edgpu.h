@@ -125,6 +125,11 @@ int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double peso,
 int edgpu_shard_ld(const edgpu_sector *s, int64_t *ld_full);
 int edgpu_shard_hxv_dw(edgpu_sector *s, int64_t ncols, int64_t ldc, const void *x_dev, void *y_dev);
 int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, const void *x_dev, void *y_dev, int32_t accumulate);
+/* Same as edgpu_shard_hxv_up, but x and y are the all-to-all buffers themselves: nslab slabs packed back to back,
+ * slab p = columns [col0[p], col0[p]+ldc[p]) of the nrows rows as [nrows][ldc[p]] (what rank p sent) -- saves the
+ * unpack/pack passes around the up-spin term. */
+int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nslab, const int64_t *col0,
+                             const int64_t *ldc, const void *x_dev, void *y_dev, int32_t accumulate);
 /* ref2int_up[DimUp], ref2int_dw[DimDw]: reference (colex) rank -> device index (host arrays, uint32) */
 int edgpu_shard_perm(const edgpu_sector *s, uint32_t *ref2int_up, uint32_t *ref2int_dw);
 

@@ -136,5 +136,20 @@ def test_shard_entry_points_equal_full_product(oracle, edb):
             ctx.sync()
             Y[:, plan.col0[r]:plan.col0[r] + plan.ldc[r]] += yc.cpu().numpy()
             Y[plan.row0[r]:plan.row0[r] + plan.nrows[r], :] += yr.cpu().numpy()
+            # the same row shard handed over as all-to-all slabs (what transpose #1 delivers)
+            rows = slice(plan.row0[r], plan.row0[r] + plan.nrows[r])
+            xs = torch.cat([torch.tensor(np.ascontiguousarray(Xint[rows, plan.col0[q]:plan.col0[q] + plan.ldc[q]]), device=dev).reshape(-1)
+                            for q in range(world)])
+            ys = torch.zeros_like(xs)
+            c0 = (C.c_int64 * world)(*plan.col0)
+            lc = (C.c_int64 * world)(*plan.ldc)
+            ctx.check(edb.lib().edgpu_shard_hxv_up_slabs(s.h, plan.row0[r], plan.nrows[r], world, c0, lc, xs.data_ptr(), ys.data_ptr(), 0))
+            ctx.sync()
+            off = 0
+            for q in range(world):
+                n = plan.nrows[r] * plan.ldc[q]
+                blk = ys[off:off + n].view(plan.nrows[r], plan.ldc[q]).cpu().numpy()
+                assert np.array_equal(blk, yr.cpu().numpy()[:, plan.col0[q]:plan.col0[q] + plan.ldc[q]])
+                off += n
         assert np.abs(Y - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
     x.free(); y.free(); s.free(); ctx.close()
