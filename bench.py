@@ -13,8 +13,9 @@ workload (default: BASELINE config 4 -- Norb=2, Nbath=7, Ns=16, half-filling sec
           bandwidth (MEASURED_PEAKS.json).
 `cpu_baseline` / `--impl reference` = the CPU oracle (literal C restatement of directMatVec_cc; the Fortran
           reference cannot be built in this image) on all host cores over a bounded row sample.
-With N>1 (torchrun) every rank owns one GPU and runs independent H*v streams (the GF-chain level of
-parallelism of the north star: chains are independent, no data-path collective) -> "scaling": "weak".
+With N>1 (torchrun) the default is ONE sector vector sharded by up-spin column blocks over the ranks (down term
+local, up term through two NCCL all-to-all transposes per H*v) -> "scaling": "strong"; `--mode chains` runs
+independent H*v streams per rank instead (the GF-chain level of parallelism, no collective) -> "weak".
 """
 from __future__ import annotations
 
