@@ -22,6 +22,7 @@
 #include "edgpu_internal.h"
 #include <algorithm>
 #include <cstring>
+#include <map>
 
 uint64_t edgpu_binom(int n, int k);
 
@@ -38,6 +39,7 @@ struct StarBlock {             // one occupation tuple of one spin
     uint32_t magic0;               // ceil(2^32 / D0): tid / D0 == __umulhi(tid, magic0) for tid < 1024
     int ny;                        // kNT / D0
     int nouter;                    // size / D0
+    int nh;                        // largest hop count of any configuration of any star of this block
 };
 
 struct StarInfo {
@@ -197,6 +199,8 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
             B.magic0 = (uint32_t)(((1ull << 32) + d0 - 1) / d0);      // d0 == 1 gives 2^32 -> 0: handled in the kernel
             B.ny = 512 / (int)d0;
             B.nouter = size / (int)d0;
+            for (int a = 0; a < norb; a++)
+                for (int i = 0; i < S->D[t[a]]; i++) B.nh = std::max(B.nh, (int)hopc[S->coff[t[a]] + i]);
         }
         blockoff[key] = cur;
         cur += size;
@@ -310,7 +314,7 @@ __device__ __forceinline__ void load_tabs(const StarKParams &P, const StarBlock 
 // per thread instead of two, halving the L1TEX sector work of the (inherently 32-byte-granular) down pass.
 __device__ __forceinline__ void ldg256(const double *p, double2 &a, double2 &b)
 {
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
 __device__ __forceinline__ void stg256(double *p, double a0, double a1, double a2, double a3)
 {
@@ -450,111 +454,163 @@ __device__ __forceinline__ void tile_pass(const StarBlock &B, const int *D, cons
     }
 }
 
-// Lean single-batch pass (large blocks: one row pair / one strip per tile).  Same math as tile_pass, minimal index
-// arithmetic: all addresses advance by constant strides, star-0 hop entries live in registers, and the sign of a
-// star (constant over its hops) is applied once to the partial sum instead of once per hop.
-//   VEC = 2: up pass (tile = one [element][2] plane);  VEC = 4: down pass (two planes `plane` bytes apart)
-// pre(e) -> EARLY is issued before the gathers; f(e, early, ui, esum, acc) stores the VEC results.
-template <int NORB, int VEC, bool WITH_E, class EARLY, class PRE, class F>
-__device__ __forceinline__ void lean_pass(const StarBlock &B, const int *D, const int *A0, const TabPtrs &T, int maxD, int H,
-                                          uint32_t s_in_addr, uint32_t plane, PRE pre, F f)
+// ------------------------------------------------------------------------------------------------------------
+// Lean kernels (large blocks: one row pair / one column strip per tile).  Same math as tile_pass, written as
+// straight-line code: the hop lists are PADDED to NH entries per configuration (unrolled NH times, slots beyond the
+// configuration's hop count are predicated off so they cost no shared-memory wavefronts), the block sign (-1)^{sum_{a'<a} n_a'} is folded into the amplitudes, the star-0 hop
+// list of a thread lives in registers, all shared-memory accesses use 32-bit addresses that advance by constants,
+// and the sign of a star (constant over its hops) multiplies the partial sum once.
+//   lent[a][i][h] = {val, off}   off = (j - i) * stride_a * 16 bytes inside an [element][2] plane
+//   laux[a][i]    = {star diagonal energy, (-1)^imp}
+struct LeanTabs { uint32_t ent, aux; };                       // shared-memory byte addresses
+
+static size_t lean_tabs_bytes(int norb, int maxD, int NH) { return (size_t)16 * norb * maxD * (NH + 1) + 64; }
+
+template <int NORB, int NH>
+__device__ __forceinline__ LeanTabs load_lean_tabs(const StarKParams &P, const StarBlock &B, const int *D, const int *A0,
+                                                   const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc,
+                                                   const double *__restrict__ hopv, const double *__restrict__ estar,
+                                                   unsigned char *base, int maxD)
 {
-    const int tid = threadIdx.x, D0 = D[0];
-    const int ty = (D0 == 1) ? tid : (int)__umulhi((uint32_t)tid, B.magic0);
-    const int i0 = tid - ty * D0;
-    const int NY = B.ny;
-    if (ty >= NY) return;
-    const int O = B.nouter;
-    constexpr int kRegH = 8;
-    const int cnt0 = T.cnt[i0];
-    double rval[kRegH];
-    int roff[kRegH];
+    HopEnt *ent = reinterpret_cast<HopEnt *>(base);
+    double2 *aux = reinterpret_cast<double2 *>(ent + NORB * maxD * NH);
+    const int H = P.H;
+    int stride = 1;
+#pragma unroll
+    for (int a = 0; a < NORB; a++) {
+        const int Da = D[a], c0 = P.coff[B.n[a]];
+        const double sgn = (B.sgn_lower[a] & 1) ? -1.0 : 1.0;
+        for (int t = threadIdx.x; t < Da * NH; t += kNT) {
+            const int i = t / NH, h = t - i * NH;
+            const int cnt = (int)hopc[c0 + i];
+            HopEnt en = {0.0, 0, cnt};                       // pad carries the hop count of the configuration
+            if (h < cnt) {
+                en.val = sgn * hopv[((size_t)a * P.ncfg + c0 + i) * H + h];
+                en.off = (int)hopd[(size_t)(c0 + i) * H + h] * stride * 16;
+            }
+            ent[(a * maxD + i) * NH + h] = en;
+        }
+        for (int t = threadIdx.x; t < Da; t += kNT)
+            aux[a * maxD + t] = make_double2(estar ? estar[(size_t)a * P.ncfg + c0 + t] : 0.0, t >= A0[a] ? -1.0 : 1.0);
+        stride *= Da;
+    }
+    LeanTabs T;
+    T.ent = (uint32_t)__cvta_generic_to_shared(ent);
+    T.aux = (uint32_t)__cvta_generic_to_shared(aux);
+    return T;
+}
+
+// predicated load (no branch): *p when flag != 0, else 0.0
+__device__ __forceinline__ double ldg_if(const double *p, int flag)
+{
+    double v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.f64 %0, [%1];\n\t}" : "=d"(v) : "l"(p), "r"(flag) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double lds64(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Per-thread invariants of the lean passes: thread (ty, i0) owns star-0 configuration i0 and walks the outer index
+// o = ty, ty + NY, ... of the block.
+template <int NH>
+struct LeanThread {
+    int ty, i0, NY, O;
+    bool active;
+    double rval[NH];
+    int roff[NH];
+    int cnt0;
+    double e0, s0;
+    uint32_t dgoff0;                 // byte offset of the thread's impurity bit inside a dg row (8 doubles)
+    __device__ __forceinline__ void init(const StarBlock &B, const int *D, const int *A0, const LeanTabs &T)
     {
-        const HopEnt *ent0 = T.ent + i0 * H;
+        const int tid = threadIdx.x, D0 = D[0];
+        ty = (D0 == 1) ? tid : (int)__umulhi((uint32_t)tid, B.magic0);
+        i0 = tid - ty * D0;
+        NY = B.ny;
+        O = B.nouter;
+        active = ty < NY && ty < O;                      // threads beyond the block's outer range have no element
+        const int ii = active ? i0 : 0;
 #pragma unroll
-        for (int h = 0; h < kRegH; h++) {
-            const HopEnt en = (h < cnt0) ? ent0[h] : HopEnt{0.0, 0, 0};
-            rval[h] = en.val; roff[h] = en.off;
+        for (int h = 0; h < NH; h++) {
+            const double2 w = lds128(T.ent + (uint32_t)(ii * NH + h) * 16u);
+            rval[h] = w.x;
+            roff[h] = __double2loint(w.y);
+            if (h == 0) cnt0 = __double2hiint(w.y);
+        }
+        const double2 ax = lds128(T.aux + (uint32_t)ii * 16u);
+        e0 = ax.x; s0 = ax.y;
+        dgoff0 = ii >= A0[0] ? 8u : 0u;
+    }
+};
+
+// acc[v] (+)= sg * sum_h val[h] * tile[e + delta_h][v]  for star a >= 1 of the element whose star index is ia
+template <int NH, int VEC, bool FIRST>
+__device__ __forceinline__ void lean_star(double (&acc)[VEC], uint32_t a0, uint32_t plane, uint32_t ent_addr, double sg)
+{
+    double p[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) p[v] = 0.0;
+    int cnt = NH;
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+        const double2 w = lds128(ent_addr + (uint32_t)h * 16u);            // {amplitude, byte offset | count}: uniform over most of the warp
+        if (h == 0) cnt = __double2hiint(w.y);
+        if (h < cnt) {
+            const uint32_t a = a0 + (uint32_t)__double2loint(w.y);
+            const double2 u = lds128(a);
+            p[0] = fma(w.x, u.x, p[0]); p[1] = fma(w.x, u.y, p[1]);
+            if (VEC == 4) {
+                const double2 q = lds128(a + plane);
+                p[2] = fma(w.x, q.x, p[2]); p[3] = fma(w.x, q.y, p[3]);
+            }
         }
     }
-    const bool imp0 = i0 >= A0[0];
-    const double e0 = WITH_E ? T.e[i0] : 0.0;
-    const double c0s = (B.sgn_lower[0] & 1) ? -1.0 : 1.0;
-    const double c1s = ((NORB >= 2 && (B.sgn_lower[1] & 1)) ? -1.0 : 1.0) * (imp0 ? -1.0 : 1.0);     // includes s0
-    const double c2s = ((NORB >= 3 && (B.sgn_lower[2] & 1)) ? -1.0 : 1.0) * (imp0 ? -1.0 : 1.0);
-    const int D1 = (NORB >= 2) ? D[1] : 1;
-    int i1 = ty, i2 = 0;
-    if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
-    int e = ty * D0 + i0;
-    const int estep = NY * D0;
-    uint32_t a0 = s_in_addr + (uint32_t)e * 16u;
-    const uint32_t astep = (uint32_t)estep * 16u;
-    EARLY nxt = pre(e);                                   // software pipeline: the loads of step o+NY are in flight during step o
-#pragma unroll 2
-    for (int o = ty; o < O; o += NY) {
-        const EARLY early = nxt;
-        if (o + NY < O) nxt = pre(e + estep);
-        uint32_t ui = imp0 ? 1u : 0u;
-        double es = e0, s1 = 1.0, s2 = 1.0;
-        if (NORB >= 2) { const bool b = i1 >= A0[1]; ui |= b ? 2u : 0u; s1 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[maxD + i1]; }
-        if (NORB >= 3) { const bool b = i2 >= A0[2]; ui |= b ? 4u : 0u; s2 = b ? -1.0 : 1.0; if (WITH_E) es += T.e[2 * maxD + i2]; }
-        double acc[VEC], part[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; v++) part[v] = 0.0;
-#pragma unroll
-        for (int h = 0; h < kRegH; h++) {
-            if (h < cnt0) {
-                const uint32_t a = a0 + (uint32_t)roff[h];
-                const double2 p = lds128(a);
-                part[0] += rval[h] * p.x; part[1] += rval[h] * p.y;
-                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += rval[h] * q.x; part[3] += rval[h] * q.y; }
-            }
-        }
-        {
-            const double sg = c0s * s1 * s2;
-#pragma unroll
-            for (int v = 0; v < VEC; v++) acc[v] = sg * part[v];
-        }
-        if (NORB >= 2) {
-            const HopEnt *ent = T.ent + (maxD + i1) * H;
-            const int cnt = T.cnt[maxD + i1];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) part[v] = 0.0;
-#pragma unroll 4
-            for (int h = 0; h < cnt; h++) {
-                const HopEnt en = ent[h];
-                const uint32_t a = a0 + (uint32_t)en.off;
-                const double2 p = lds128(a);
-                part[0] += en.val * p.x; part[1] += en.val * p.y;
-                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += en.val * q.x; part[3] += en.val * q.y; }
-            }
-            const double sg = c1s * s2;
-#pragma unroll
-            for (int v = 0; v < VEC; v++) acc[v] += sg * part[v];
-        }
-        if (NORB >= 3) {
-            const HopEnt *ent = T.ent + (2 * maxD + i2) * H;
-            const int cnt = T.cnt[2 * maxD + i2];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) part[v] = 0.0;
-#pragma unroll 4
-            for (int h = 0; h < cnt; h++) {
-                const HopEnt en = ent[h];
-                const uint32_t a = a0 + (uint32_t)en.off;
-                const double2 p = lds128(a);
-                part[0] += en.val * p.x; part[1] += en.val * p.y;
-                if (VEC == 4) { const double2 q = lds128(a + plane); part[2] += en.val * q.x; part[3] += en.val * q.y; }
-            }
-            const double sg = c2s * s1;
-#pragma unroll
-            for (int v = 0; v < VEC; v++) acc[v] += sg * part[v];
-        }
-        f(e, a0, early, ui, es, acc);
-        e += estep;
-        a0 += astep;
-        i1 += NY;
-        if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+    for (int v = 0; v < VEC; v++) acc[v] = FIRST ? sg * p[v] : fma(sg, p[v], acc[v]);
+}
+
+// The gathers of one element: acc = sum over stars.  Returns the summed star energy in `es` and the dg byte offset.
+template <int NORB, int NH, int VEC>
+__device__ __forceinline__ void lean_element(const LeanThread<NH> &L, const LeanTabs &T, const int *A0, int maxD, uint32_t a0, uint32_t plane,
+                                             int i1, int i2, const double (&init)[VEC], double (&acc)[VEC], double &es, uint32_t &dgo)
+{
+    double sg0 = 1.0, sg1 = L.s0, sg2 = L.s0;
+    es = L.e0;
+    dgo = L.dgoff0;
+    if (NORB >= 2) {
+        const double2 ax = lds128(T.aux + (uint32_t)(maxD + i1) * 16u);
+        es += ax.x; sg0 = ax.y; sg2 *= ax.y;
+        dgo += i1 >= A0[1] ? 16u : 0u;
     }
+    if (NORB >= 3) {
+        const double2 ax = lds128(T.aux + (uint32_t)(2 * maxD + i2) * 16u);
+        es += ax.x; sg0 *= ax.y; sg1 *= ax.y;
+        dgo += i2 >= A0[2] ? 32u : 0u;
+    }
+    double p[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) p[v] = 0.0;
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+        if (h < L.cnt0) {
+            const uint32_t a = a0 + (uint32_t)L.roff[h];
+            const double2 u = lds128(a);
+            p[0] = fma(L.rval[h], u.x, p[0]); p[1] = fma(L.rval[h], u.y, p[1]);
+            if (VEC == 4) {
+                const double2 q = lds128(a + plane);
+                p[2] = fma(L.rval[h], q.x, p[2]); p[3] = fma(L.rval[h], q.y, p[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = fma(sg0, p[v], init[v]);
+    if (NORB >= 2) lean_star<NH, VEC, false>(acc, a0, plane, T.ent + (uint32_t)((maxD + i1) * NH) * 16u, sg1);
+    if (NORB >= 3) lean_star<NH, VEC, false>(acc, a0, plane, T.ent + (uint32_t)((2 * maxD + i2) * NH) * 16u, sg2);
 }
 
 __device__ __forceinline__ TabPtrs carve_tabs(unsigned char *base, int norb, int maxD, int H)
@@ -598,26 +654,37 @@ __device__ __forceinline__ int64_t slab_off(const SlabMap &M, int64_t row, int c
 // A tile = RP row pairs x the block, stored [rp][element][2] (the two rows of a pair interleaved).  Every CTA
 // loads the star tables once, then walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile streams in
 // with cp.async (LDGSTS) while the current one is processed, so the HBM pipe stays busy during the gathers.
-template <int NORB, bool SLAB>
+//   NH > 0: lean path (RP == 1, hop lists padded to NH);  NH == 0: generic tile_pass path (small blocks, Nbath = 9)
+template <int NORB, bool SLAB, int NH>
 __global__ void __launch_bounds__(kNT)
-k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate, int nstage,
+k_star_up(StarKParams P, SlabMap Mpar, int64_t dim_dw, int64_t ld, int block_index, int RP, int accumulate, int nstage,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
           const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SlabMap s_M;
+    if (SLAB) {
+        if (threadIdx.x == 0) s_M = Mpar;
+        __syncthreads();
+    }
+    const SlabMap &M = s_M;
     const StarBlock B = blocks[block_index];
     const int size = B.size, tid = threadIdx.x;
     const int tile_elems = RP * size;
     double *s_buf = reinterpret_cast<double *>(smem_raw);                      // [2 stages][RP][size][2]
     double *s_dg = s_buf + (size_t)2 * nstage * tile_elems;                    // [stages][RP][2 rows][8]
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_dg + (size_t)16 * nstage * RP), NORB, maxD, P.H);
+    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_dg + (size_t)16 * nstage * RP);
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
-    load_tabs<NORB>(P, B, D, hopd, hopc, hopv, estar, T, maxD, true);
+    TabPtrs T;
+    LeanTabs LT;
+    if (NH > 0) LT = load_lean_tabs<NORB, (NH > 0 ? NH : 1)>(P, B, D, A0, hopd, hopc, hopv, estar, tab_base, maxD);
+    else { T = carve_tabs(tab_base, NORB, maxD, P.H); load_tabs<NORB>(P, B, D, hopd, hopc, hopv, estar, T, maxD, true); }
     const uint32_t buf_addr = (uint32_t)__cvta_generic_to_shared(s_buf);
+    const uint32_t dg_addr = (uint32_t)__cvta_generic_to_shared(s_dg);
     const uint32_t stage_bytes = (uint32_t)tile_elems * 16u;
     const uint32_t impmask = (1u << NORB) - 1u;
     const int64_t npairs = (dim_dw + 1) / 2;
@@ -644,6 +711,15 @@ k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index,
                 }
             }
         }
+        if (NH > 0 && !SLAB && accumulate && tid < 2) {
+            // pull the y rows of that tile (written by the down pass, long evicted) into L2 now, so that the
+            // read-modify-write of the gather loop sees an L2 hit latency instead of a loaded-DRAM one
+            int64_t r = 2 * t + tid;
+            r = r < last ? r : last;
+            const uintptr_t p0 = reinterpret_cast<uintptr_t>(y + r * ld + boff) & ~(uintptr_t)15;
+            const uint32_t bytes = ((uint32_t)size * 8u + 31u) & ~15u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(bytes) : "memory");
+        }
         for (int i = tid; i < 16 * RP; i += kNT) {
             // s_dg[stage][q][v][ui] = E_dw[row] + X[imp_dw(row)][ui] + (Ust-Jh) * C(nimp(ui), 2)
             const int q = i >> 4, v = (i >> 3) & 1, ui = i & 7;
@@ -654,8 +730,14 @@ k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index,
         }
     };
 
+    LeanThread<(NH > 0 ? NH : 1)> L;
+    if (NH > 0) {
+        __syncthreads();                                     // lean tables visible
+        L.init(B, D, A0, LT);
+    }
+
     // nstage == 2: one CTA per SM, the next tile streams in while the current one is processed.
-    // nstage == 1: two CTAs per SM overlap each other's load and compute phases (large blocks: twice the warps).
+    // nstage == 1: single stage (blocks whose two stages exceed shared memory).
     int64_t t = blockIdx.x;
     if (nstage == 2) {
         if (t < ntiles) issue(t, 0);
@@ -674,37 +756,65 @@ k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index,
             cp_async_wait<0>();
         }
         __syncthreads();                                     // ... and everybody's; tables + s_dg visible too
-        const double *dg = s_dg + (size_t)stage * 16 * RP;
         const int64_t row0 = 2 * t * RP;
-        struct Own { double y0, y1; };
-        if (RP == 1 && P.H <= 8) {
-            // large block: one row pair per tile -> lean pass with constant-stride addressing
-            const int64_t ra = row0;
-            const bool oka1 = ra < dim_dw, okb1 = ra + 1 < dim_dw;
-            double *pa = y + (oka1 ? ra : last) * ld + boff, *pb = y + (okb1 ? ra + 1 : last) * ld + boff;
-            const double *dgp = dg;
-            const int acc_y = accumulate;
-            const int64_t rra = oka1 ? ra : last, rrb = okb1 ? ra + 1 : last;
-            double *yy = y;
-            lean_pass<NORB, 2, true, Own>(B, D, A0, T, maxD, P.H, buf_addr + (uint32_t)stage * stage_bytes, 0u,
-                [=](int e) {
-                    Own w;
-                    if (SLAB) { w.y0 = acc_y ? yy[slab_off(M, rra, boff + e)] : 0.0; w.y1 = acc_y ? yy[slab_off(M, rrb, boff + e)] : 0.0; }
-                    else { w.y0 = acc_y ? pa[e] : 0.0; w.y1 = acc_y ? pb[e] : 0.0; }
-                    return w;
-                },
-                [=](int e, uint32_t a0, const Own &w, uint32_t ui, double es, double (&acc)[2]) {
-                    const double2 p = lds128(a0);
-                    const double o0 = w.y0 + acc[0] + (es + dgp[ui]) * p.x, o1 = w.y1 + acc[1] + (es + dgp[8 + ui]) * p.y;
-                    if (SLAB) {
-                        if (oka1) yy[slab_off(M, rra, boff + e)] = o0;
-                        if (okb1) yy[slab_off(M, rrb, boff + e)] = o1;
-                    } else {
-                        if (oka1) pa[e] = o0;
-                        if (okb1) pb[e] = o1;
+        if (NH > 0) {
+            // large block: one row pair per tile.  A row past the end (odd dim_dw) aliases the last row: both slots
+            // then compute and store the same value.
+            constexpr int NHc = NH > 0 ? NH : 1;
+            const int64_t rra = row0 < last ? row0 : last, rrb = row0 + 1 < last ? row0 + 1 : last;
+            double *pa = y + rra * ld + boff, *pb = y + rrb * ld + boff;
+            const uint32_t xs = buf_addr + (uint32_t)stage * stage_bytes;
+            const uint32_t dgs = dg_addr + (uint32_t)stage * 128u;
+            if (L.active) {
+                const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
+                int i1 = L.ty, i2 = 0;
+                if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+                int e = L.ty * D0 + L.i0;
+                const int estep = NY * D0;
+                uint32_t a0 = xs + (uint32_t)e * 16u;
+                // y addresses: uniform row base + 32-bit byte offset (one IMAD.WIDE per access instead of 64-bit index math)
+                char *const ba = reinterpret_cast<char *>(pa), *const bb = reinterpret_cast<char *>(pb);
+                auto yaddr = [&](int64_t row, char *rowb, int ee) -> double * {
+                    return SLAB ? y + slab_off(M, row, boff + ee) : reinterpret_cast<double *>(rowb + (uint32_t)ee * 8u);
+                };
+                // software pipeline: the y values of the next PF steps are in flight during this one (slots past the
+                // end re-read the thread's current element, which is harmless)
+                constexpr int PF = 3;
+                double2 ring[PF];
+#pragma unroll
+                for (int k = 0; k < PF; k++) {
+                    const int ek = (L.ty + k * NY < O) ? e + k * estep : e;
+                    ring[k].x = ldg_if(yaddr(rra, ba, ek), accumulate);
+                    ring[k].y = ldg_if(yaddr(rrb, bb, ek), accumulate);
+                }
+                int o = L.ty;
+                while (o < O) {
+#pragma unroll
+                    for (int k = 0; k < PF; k++) {
+                        if (o < O) {
+                            const double init[2] = {ring[k].x, ring[k].y};
+                            const int en = (o + PF * NY < O) ? e + PF * estep : e;
+                            ring[k].x = ldg_if(yaddr(rra, ba, en), accumulate);
+                            ring[k].y = ldg_if(yaddr(rrb, bb, en), accumulate);
+                            double acc[2], es;
+                            uint32_t dgo;
+                            lean_element<NORB, NHc, 2>(L, LT, A0, maxD, a0, 0u, i1, i2, init, acc, es, dgo);
+                            const double2 own = lds128(a0);
+                            const double da = lds64(dgs + dgo), db = lds64(dgs + 64u + dgo);
+                            *yaddr(rra, ba, e) = fma(es + da, own.x, acc[0]);
+                            *yaddr(rrb, bb, e) = fma(es + db, own.y, acc[1]);
+                            e += estep;
+                            a0 += (uint32_t)estep * 16u;
+                            i1 += NY;
+                            if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+                            o += NY;
+                        }
                     }
-                });
+                }
+            }
         } else {
+        const double *dg = s_dg + (size_t)stage * 16 * RP;
+        struct Own { double y0, y1; };
         auto rows = [&](int q, double *&ya, double *&yb, bool &oka, bool &okb) {
             const int64_t ra = row0 + 2 * q;
             oka = ra < dim_dw; okb = ra + 1 < dim_dw;
@@ -744,7 +854,7 @@ k_star_up(StarKParams P, SlabMap M, int64_t dim_dw, int64_t ld, int block_index,
 //   W = 4: two planes [strip][row][2] (columns 0-1 and 2-3 of each strip), 32-byte row segments (256-bit ld/st)
 //   W = 2: one plane, 16-byte row segments -- for blocks whose 4-column tile exceeds shared memory (Norb=3, Nbath=5:
 //          8000 rows x 32 B = 256 KB)
-template <int NORB, int W>
+template <int NORB, int W, int NH>
 __global__ void __launch_bounds__(kNT)
 k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
           const StarBlock *__restrict__ blocks,
@@ -756,12 +866,15 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
     const int R = B.size;
     const int tile_rows = SP * R;
     double *s_in = reinterpret_cast<double *>(smem_raw);                       // W/2 planes of [SP][R][2]
-    const TabPtrs T = carve_tabs(reinterpret_cast<unsigned char *>(s_in + (size_t)W * tile_rows), NORB, maxD, P.H);
+    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_in + (size_t)W * tile_rows);
     const int tid = threadIdx.x;
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
-    load_tabs<NORB>(P, B, D, hopd, hopc, hopv, nullptr, T, maxD, false);
+    TabPtrs T;
+    LeanTabs LT;
+    if (NH > 0) LT = load_lean_tabs<NORB, (NH > 0 ? NH : 1)>(P, B, D, A0, hopd, hopc, hopv, nullptr, tab_base, maxD);
+    else { T = carve_tabs(tab_base, NORB, maxD, P.H); load_tabs<NORB>(P, B, D, hopd, hopc, hopv, nullptr, T, maxD, false); }
     const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
     const uint32_t plane = (uint32_t)tile_rows * 16u;
     const int64_t cbase = (int64_t)blockIdx.x * SP * W;
@@ -794,12 +907,33 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
             if (W == 4 && left > 2) yp[2] = acc[W - 2];
         }
     };
-    if (SP == 1 && P.H <= 8) {
+    if (NH > 0) {
+        // large block: one strip per tile, straight-line gathers
+        constexpr int NHc = NH > 0 ? NH : 1;
+        LeanThread<NHc> L;
+        L.init(B, D, A0, LT);
+        if (!L.active) return;
         const int64_t left = dim_up - cbase;
-        double *yc = ys + cbase;
-        lean_pass<NORB, W, false, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane,
-            [=](int) { return 0; },
-            [=](int e, uint32_t, int, uint32_t, double, double (&acc)[W]) { store(yc + (int64_t)e * ldv, left, acc); });
+        const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
+        int i1 = L.ty, i2 = 0;
+        if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+        const int e0 = L.ty * D0 + L.i0;
+        const int estep = NY * D0;
+        uint32_t a0 = s_in_addr + (uint32_t)e0 * 16u;
+        double *yp = ys + cbase + (int64_t)e0 * ldv;
+        const int64_t ystep = (int64_t)estep * ldv;
+        const double zero[W] = {};
+#pragma unroll 2
+        for (int o = L.ty; o < O; o += NY) {
+            double acc[W], es;
+            uint32_t dgo;
+            lean_element<NORB, NHc, W>(L, LT, A0, maxD, a0, plane, i1, i2, zero, acc, es, dgo);
+            store(yp, left, acc);
+            yp += ystep;
+            a0 += (uint32_t)estep * 16u;
+            i1 += NY;
+            if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+        }
         return;
     }
     tile_pass<NORB, W, false, 1, int>(B, D, A0, T, maxD, P.H, s_in_addr, plane, SP,
@@ -820,6 +954,56 @@ static void fill_kparams(const StarInfo &S, StarKParams &P)
 
 static constexpr int kStageElems = 4900;     // elements (x 16 B) per pipeline stage of the up pass / per tile of the down pass
 
+// hop lists of the lean kernels are padded to one of these lengths (0: no lean kernel, generic tile_pass)
+static int round_nh(int nh) { return nh <= 4 ? 4 : nh <= 5 ? 5 : nh <= 6 ? 6 : nh <= 8 ? 8 : 0; }
+
+static int ensure_smem(edgpu_ctx *ctx, const void *kern, size_t smem)
+{
+    static std::map<const void *, size_t> set;
+    size_t &cur = set[kern];
+    if (smem > cur) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    return 0;
+}
+
+using DwKernel = void (*)(StarKParams, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
+                          const double *, double *, int);
+using UpKernel = void (*)(StarKParams, SlabMap, int64_t, int64_t, int, int, int, int, const StarBlock *, const int16_t *, const uint8_t *,
+                          const double *, const double *, const double *, const uint32_t *, const double *, const double *, double *, int);
+
+template <int NORB>
+static DwKernel pick_dw(int W, int NH)
+{
+    if (W == 4) switch (NH) {
+        case 4: return k_star_dw<NORB, 4, 4>;
+        case 5: return k_star_dw<NORB, 4, 5>;
+        case 6: return k_star_dw<NORB, 4, 6>;
+        case 8: return k_star_dw<NORB, 4, 8>;
+        default: return k_star_dw<NORB, 4, 0>;
+    }
+    switch (NH) {
+        case 4: return k_star_dw<NORB, 2, 4>;
+        case 5: return k_star_dw<NORB, 2, 5>;
+        case 6: return k_star_dw<NORB, 2, 6>;
+        case 8: return k_star_dw<NORB, 2, 8>;
+        default: return k_star_dw<NORB, 2, 0>;
+    }
+}
+
+template <int NORB, bool SLAB>
+static UpKernel pick_up(int NH)
+{
+    switch (NH) {
+        case 4: return k_star_up<NORB, SLAB, 4>;
+        case 5: return k_star_up<NORB, SLAB, 5>;
+        case 6: return k_star_up<NORB, SLAB, 6>;
+        case 8: return k_star_up<NORB, SLAB, 8>;
+        default: return k_star_up<NORB, SLAB, 0>;
+    }
+}
+
 // Down pass on a column range: x, y point at a [DimDw][ld] tile holding `ncols` up-spin columns (the whole sector
 // vector on one GPU, or the column shard of one rank -- hops of the down spin never change the column).
 template <int NORB>
@@ -832,26 +1016,25 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
     int maxD = 0;
     for (int m = 0; m <= Dn.nbath + 1; m++) maxD = std::max(maxD, Dn.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
-    const size_t tab = tabs_bytes(NORB, maxD, Dn.H);
-    static size_t set_dw[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     const bool force_narrow = (ctx->par.reserved[0] & 1) != 0;                 // test hook: exercise the 2-column path
+    const bool force_generic = (ctx->par.reserved[0] & 4) != 0;                // test hook: generic tile_pass everywhere
     for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {                         // one launch per down-block
         const StarBlock &B = Dn.blocks[bi];
-        const int W = (!force_narrow && sizeof(double) * (size_t)B.size * 4 + tab <= 227 * 1024) ? 4 : 2;
-        const int64_t nstrips = (ncols + W - 1) / W;
         // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
         int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
-        SP = std::max<int64_t>(1, std::min<int64_t>(SP, nstrips / (4 * (int64_t)ctx->sm_count)));
+        SP = std::max<int64_t>(1, std::min<int64_t>(SP, ((ncols + 3) / 4) / (4 * (int64_t)ctx->sm_count)));
+        const int NH = (SP == 1 && !force_generic) ? round_nh(B.nh) : 0;
+        int bD = 1;                                                            // table stride: largest star of THIS block
+        for (int a = 0; a < NORB; a++) bD = std::max(bD, Dn.D[B.n[a]]);
+        const size_t tab = NH ? lean_tabs_bytes(NORB, bD, NH) : tabs_bytes(NORB, bD, Dn.H);
+        const int W = (!force_narrow && sizeof(double) * (size_t)B.size * 4 * SP + tab <= 227 * 1024) ? 4 : 2;
+        const int64_t nstrips = (ncols + W - 1) / W;
         const size_t smem = sizeof(double) * (size_t)B.size * W * SP + tab;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star down pass: block of %d rows does not fit in shared memory", B.size);
-        auto kern = (W == 4) ? k_star_dw<NORB, 4> : k_star_dw<NORB, 2>;
-        size_t &set = set_dw[NORB][W == 4 ? 1 : 0];
-        if (smem > set) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = smem;
-        }
+        auto kern = pick_dw<NORB>(W, NH);
+        if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
         const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
-        kern<<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, x, y, maxD);
+        kern<<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, x, y, bD);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
@@ -870,8 +1053,7 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
     int maxD = 0;
     for (int m = 0; m <= U.nbath + 1; m++) maxD = std::max(maxD, U.D[m]);
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
-    const size_t tab = tabs_bytes(NORB, maxD, U.H);
-    static size_t set_up[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const bool force_generic = (ctx->par.reserved[0] & 4) != 0;
     SlabMap M;
     memset(&M, 0, sizeof(M));
     if (slabs) M = *slabs; else { M.n = 1; M.ldc0 = (int)ld; M.magic = 0; M.ldc[0] = (int)ld; }
@@ -880,24 +1062,22 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         const StarBlock &B = U.blocks[bi];
         int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
-        // single stage + 2 CTAs per SM when two tiles (and two table sets) fit; else double-buffered, 1 CTA per SM
+        const int NH = (RP == 1 && !force_generic) ? round_nh(B.nh) : 0;
+        int bD = 1;
+        for (int a = 0; a < NORB; a++) bD = std::max(bD, U.D[B.n[a]]);
+        const size_t tab = NH ? lean_tabs_bytes(NORB, bD, NH) : tabs_bytes(NORB, bD, U.H);
         const size_t smem1 = sizeof(double) * ((size_t)2 * B.size * RP + (size_t)16 * RP) + tab;
         // double-buffered when two stages fit (nstage 1: single stage, e.g. 8000-configuration blocks of Norb=3, Nbath=5)
         const size_t smem2 = sizeof(double) * ((size_t)4 * B.size * RP + (size_t)32 * RP) + tab;
         const int nstage = (smem2 <= 227 * 1024 && !(ctx->par.reserved[0] & 2)) ? 2 : 1;
         const size_t smem = nstage == 1 ? smem1 : smem2;
         if (smem > 227 * 1024) return edgpu_fail(ctx, "star up pass: block of %d configurations does not fit in shared memory", B.size);
-        auto kern = slabs ? k_star_up<NORB, true> : k_star_up<NORB, false>;
-        size_t &set = set_up[NORB][slabs ? 1 : 0];
-        if (smem > set) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = smem;
-        }
+        auto kern = slabs ? pick_up<NORB, true>(NH) : pick_up<NORB, false>(NH);
+        if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
         const int64_t ntiles = (npairs + RP - 1) / RP;
-        const int per_sm = nstage == 1 ? 2 : 1;
-        const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+        const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
         kern<<<nctas, kNT, smem, ctx->stream>>>(PU, M, nrows, ld, (int)bi, (int)RP, accumulate, nstage, U.d_blocks, U.d_hopd, U.d_hopc,
-                                                          U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, maxD);
+                                                          U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
