@@ -470,7 +470,7 @@ template <int NORB, int NH>
 __device__ __forceinline__ LeanTabs load_lean_tabs(const StarKParams &P, const StarBlock &B, const int *D, const int *A0,
                                                    const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc,
                                                    const double *__restrict__ hopv, const double *__restrict__ estar,
-                                                   unsigned char *base, int maxD)
+                                                   unsigned char *base, int maxD, int esz = 16)
 {
     HopEnt *ent = reinterpret_cast<HopEnt *>(base);
     double2 *aux = reinterpret_cast<double2 *>(ent + NORB * maxD * NH);
@@ -486,7 +486,7 @@ __device__ __forceinline__ LeanTabs load_lean_tabs(const StarKParams &P, const S
             HopEnt en = {0.0, 0, cnt};                       // pad carries the hop count of the configuration
             if (h < cnt) {
                 en.val = sgn * hopv[((size_t)a * P.ncfg + c0 + i) * H + h];
-                en.off = (int)hopd[(size_t)(c0 + i) * H + h] * stride * 16;
+                en.off = (int)hopd[(size_t)(c0 + i) * H + h] * stride * esz;
             }
             ent[(a * maxD + i) * NH + h] = en;
         }
@@ -562,8 +562,9 @@ __device__ __forceinline__ void lean_star(double (&acc)[VEC], uint32_t a0, uint3
         if (h == 0) cnt = __double2hiint(w.y);
         if (h < cnt) {
             const uint32_t a = a0 + (uint32_t)__double2loint(w.y);
+            if (VEC == 1) { p[0] = fma(w.x, lds64(a), p[0]); continue; }
             const double2 u = lds128(a);
-            p[0] = fma(w.x, u.x, p[0]); p[1] = fma(w.x, u.y, p[1]);
+            p[0] = fma(w.x, u.x, p[0]); p[VEC > 1 ? 1 : 0] = fma(w.x, u.y, p[VEC > 1 ? 1 : 0]);
             if (VEC == 4) {
                 const double2 q = lds128(a + plane);
                 p[2] = fma(w.x, q.x, p[2]); p[3] = fma(w.x, q.y, p[3]);
@@ -599,8 +600,9 @@ __device__ __forceinline__ void lean_element(const LeanThread<NH> &L, const Lean
     for (int h = 0; h < NH; h++) {
         if (h < L.cnt0) {
             const uint32_t a = a0 + (uint32_t)L.roff[h];
+            if (VEC == 1) { p[0] = fma(L.rval[h], lds64(a), p[0]); continue; }
             const double2 u = lds128(a);
-            p[0] = fma(L.rval[h], u.x, p[0]); p[1] = fma(L.rval[h], u.y, p[1]);
+            p[0] = fma(L.rval[h], u.x, p[0]); p[VEC > 1 ? 1 : 0] = fma(L.rval[h], u.y, p[VEC > 1 ? 1 : 0]);
             if (VEC == 4) {
                 const double2 q = lds128(a + plane);
                 p[2] = fma(L.rval[h], q.x, p[2]); p[3] = fma(L.rval[h], q.y, p[3]);
@@ -849,6 +851,191 @@ k_star_up(StarKParams P, SlabMap Mpar, int64_t dim_dw, int64_t ld, int block_ind
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Up pass, bulk-copy (TMA) version for the single-GPU path:  y[rows][blk] += (diag + H_up) x.
+// A tile = G consecutive rows x the up-block.  All global traffic moves through the bulk async-copy engine:
+//   producer warp : cp.async.bulk  x row segment -> xbuf[stage],  y row segment (H_dw x of the down pass) -> ybuf[stage]
+//   16 consumer warps : gather from xbuf, read-modify-write ybuf IN PLACE (each element is owned by one thread)
+//   producer warp : cp.async.bulk  ybuf[stage] -> y row segment
+// so the LSU/L1 path (whose few in-flight lines throttled the cp.async version) carries shared-memory traffic
+// only, and the consumers never meet a CTA-wide barrier: stages are handed over through mbarriers
+// (full[stage]: copy bytes landed; done[stage]: one arrival per consumer warp).
+// Bulk copies need 16-byte aligned addresses and sizes; a block that starts at an odd column is copied from one
+// element earlier (`lead`), and an odd length is rounded up.  The extra elements belong to the neighbouring block or
+// the pad columns of the SAME row; they are stored back unchanged, which is safe because the launches of
+// different up-blocks are serialised on the stream and no other CTA of this launch touches the row.
+static constexpr int kNT3 = kNT + 32;                    // 16 consumer warps + 1 producer warp
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+template <int NORB, int NH>
+__global__ void __launch_bounds__(kNT3)
+k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
+           const StarBlock *__restrict__ blocks,
+           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
+           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
+           const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const StarBlock B = blocks[block_index];
+    const int size = B.size, tid = threadIdx.x;
+    const int lead = B.off & 1;                                                // copy starts one element early when the block starts odd
+    const int ncopy = (lead + size + 1) & ~1;                                  // elements per row segment moved (even)
+    const uint32_t rowb = (uint32_t)(ncopy + 2) * 8u;                          // bytes per row slot (16-byte multiple)
+    const uint32_t stageb = rowb * (uint32_t)G;
+    double *s_dg = reinterpret_cast<double *>(smem_raw + (size_t)4 * stageb);  // [2 stages][G][8]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_dg + (size_t)16 * G);     // full[2], done[2]
+    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_bar + 4);
+    int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
+    const LeanTabs LT = load_lean_tabs<NORB, NH>(P, B, D, A0, hopd, hopc, hopv, estar, tab_base, maxD, 8);
+    const uint32_t xbuf = (uint32_t)__cvta_generic_to_shared(smem_raw);        // [2][G][rowb]
+    const uint32_t ybuf = xbuf + 2u * stageb;
+    const uint32_t dg_addr = (uint32_t)__cvta_generic_to_shared(s_dg);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);                            // full[s]: the producer's expect_tx arrival
+        mbar_init(bar0 + 16, kNT / 32); mbar_init(bar0 + 24, kNT / 32);        // done[s]: one arrival per consumer warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                                                           // tables + barriers ready
+    const uint32_t impmask = (1u << NORB) - 1u;
+    const int64_t ntiles = (dim_dw + G - 1) / G;
+    const int64_t colb = (int64_t)B.off - lead;                                // first column moved (even)
+
+    if (tid >= kNT) {
+        // ---------------- producer warp ----------------
+        const int lane = tid - kNT;
+        int64_t t = blockIdx.x;
+        auto store_tile = [&](int64_t tt, int st) {
+            if (lane == 0) {
+                const int64_t r0 = tt * G;
+                const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
+                for (int g = 0; g < gc; g++)
+                    bulk_s2g(y + (r0 + g) * ld + colb, ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb, (uint32_t)ncopy * 8u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        };
+        int i = 0;
+        for (; t < ntiles; t += gridDim.x, i++) {
+            const int st = i & 1, k = i >> 1;
+            if (i >= 2) {
+                // the stage still holds tile i-2: wait for the consumers, write its result back, wait until the
+                // copy engine has read the buffer, then refill it
+                if (lane == 0) mbar_wait(bar0 + 16 + 8 * st, (uint32_t)(k - 1) & 1u);
+                __syncwarp();
+                store_tile(t - 2 * (int64_t)gridDim.x, st);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            const int64_t r0 = t * G;
+            const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
+            for (int j = lane; j < 8 * gc; j += 32) {
+                // s_dg[stage][g][ui] = E_dw[row] + X[imp_dw(row)][ui] + (Ust-Jh) * C(nimp(ui), 2)
+                const int g = j >> 3, ui = j & 7;
+                const int64_t r = r0 + g;
+                const int nimp = __popc(ui);
+                s_dg[(size_t)st * 8 * G + j] = e_dw[r] + xtab[(cfg_dw[r] & impmask) * 32u + ui] + P.pair_e * (double)(nimp * (nimp - 1) / 2);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t fb = bar0 + 8 * st;
+                mbar_expect_tx(fb, (uint32_t)gc * 2u * (uint32_t)ncopy * 8u);
+                for (int g = 0; g < gc; g++) {
+                    bulk_g2s(xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb, x + (r0 + g) * ld + colb, (uint32_t)ncopy * 8u, fb);
+                    bulk_g2s(ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb, y + (r0 + g) * ld + colb, (uint32_t)ncopy * 8u, fb);
+                }
+            }
+        }
+        // drain: the last (up to two) tiles are still in their stages
+        const int ntot = i;
+        for (int j = (ntot >= 2 ? ntot - 2 : 0); j < ntot; j++) {
+            const int st = j & 1, k = j >> 1;
+            if (lane == 0) mbar_wait(bar0 + 16 + 8 * st, (uint32_t)k & 1u);
+            __syncwarp();
+            store_tile((int64_t)blockIdx.x + (int64_t)j * gridDim.x, st);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    LeanThread<NH> L;
+    L.init(B, D, A0, LT);
+    const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
+    const int estep = NY * D0;
+    int i = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+        const int st = i & 1, k = i >> 1;
+        mbar_wait(bar0 + 8 * st, (uint32_t)k & 1u);
+        const int64_t r0 = t * G;
+        const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
+        if (L.active) {
+            for (int g = 0; g < gc; g++) {
+                const uint32_t xs = xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
+                const uint32_t ys = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
+                const uint32_t dgs = dg_addr + (uint32_t)(st * G + g) * 64u;
+                int i1 = L.ty, i2 = 0;
+                if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+                const uint32_t eb = (uint32_t)(L.ty * D0 + L.i0) * 8u;
+                uint32_t a0 = xs + eb, ya = ys + eb;
+#pragma unroll 2
+                for (int o = L.ty; o < O; o += NY) {
+                    const double init[1] = {lds64(ya)};
+                    double acc[1], es;
+                    uint32_t dgo;
+                    lean_element<NORB, NH, 1>(L, LT, A0, maxD, a0, 0u, i1, i2, init, acc, es, dgo);
+                    sts64(ya, fma(es + lds64(dgs + dgo), lds64(a0), acc[0]));
+                    a0 += (uint32_t)estep * 8u;
+                    ya += (uint32_t)estep * 8u;
+                    i1 += NY;
+                    if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // results visible to the copy engine
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar0 + 16 + 8 * st);
+    }
+}
+
 // y[blk rows][strips] = H_dw x  for one down-block (runs FIRST; every row belongs to exactly one down-block, so
 // this pass writes every element of y once).  A tile = SP strips of W columns x the block rows.
 //   W = 4: two planes [strip][row][2] (columns 0-1 and 2-3 of each strip), 32-byte row segments (256-bit ld/st)
@@ -952,6 +1139,7 @@ static void fill_kparams(const StarInfo &S, StarKParams &P)
     for (int m = 0; m < 16; m++) { P.D[m] = S.D[m]; P.A0[m] = S.A0[m]; P.coff[m] = S.coff[m]; }
 }
 
+static constexpr int kBulkMin = 256;         // up-blocks at least this large use the bulk-copy (TMA) up kernel
 static constexpr int kStageElems = 4900;     // elements (x 16 B) per pipeline stage of the up pass / per tile of the down pass
 
 // hop lists of the lean kernels are padded to one of these lengths (0: no lean kernel, generic tile_pass)
@@ -989,6 +1177,19 @@ static DwKernel pick_dw(int W, int NH)
         case 6: return k_star_dw<NORB, 2, 6>;
         case 8: return k_star_dw<NORB, 2, 8>;
         default: return k_star_dw<NORB, 2, 0>;
+    }
+}
+
+using Up3Kernel = void (*)(StarKParams, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
+                           const double *, const double *, const uint32_t *, const double *, const double *, double *, int);
+template <int NORB>
+static Up3Kernel pick_up3(int NH)
+{
+    switch (NH) {
+        case 4: return k_star_up3<NORB, 4>;
+        case 5: return k_star_up3<NORB, 5>;
+        case 6: return k_star_up3<NORB, 6>;
+        default: return k_star_up3<NORB, 8>;
     }
 }
 
@@ -1062,9 +1263,29 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         const StarBlock &B = U.blocks[bi];
         int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
-        const int NH = (RP == 1 && !force_generic) ? round_nh(B.nh) : 0;
         int bD = 1;
         for (int a = 0; a < NORB; a++) bD = std::max(bD, U.D[B.n[a]]);
+        if (!slabs && accumulate && !force_generic && !(ctx->par.reserved[0] & 8) && B.size >= ((ctx->par.reserved[0] & 16) ? 1 : kBulkMin) && round_nh(B.nh) &&
+            ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+            // bulk-copy pipeline: G rows per tile
+            const int NH3 = round_nh(B.nh);
+            int64_t G = std::max<int64_t>(1, kStageElems / B.size);
+            G = std::max<int64_t>(1, std::min<int64_t>(G, nrows / (2 * (int64_t)ctx->sm_count)));
+            const int lead = B.off & 1, ncopy = (lead + B.size + 1) & ~1;
+            const size_t rowb = (size_t)(ncopy + 2) * 8;
+            const size_t smem = 4 * rowb * G + sizeof(double) * 16 * G + 32 + lean_tabs_bytes(NORB, bD, NH3);
+            if (smem <= 227 * 1024) {
+                auto kern = pick_up3<NORB>(NH3);
+                if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
+                const int64_t ntiles = (nrows + G - 1) / G;
+                const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
+                kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)G, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
+                                                          s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD);
+                CUDA_TRY(ctx, cudaGetLastError());
+                continue;
+            }
+        }
+        const int NH = (RP == 1 && !force_generic) ? round_nh(B.nh) : 0;
         const size_t tab = NH ? lean_tabs_bytes(NORB, bD, NH) : tabs_bytes(NORB, bD, U.H);
         const size_t smem1 = sizeof(double) * ((size_t)2 * B.size * RP + (size_t)16 * RP) + tab;
         // double-buffered when two stages fit (nstage 1: single stage, e.g. 8000-configuration blocks of Norb=3, Nbath=5)

@@ -8,13 +8,15 @@ from test_gpu_parity import CASES as BASE_CASES, HXV_TOL, all_sectors, make
 pytestmark = pytest.mark.gpu
 
 STAR_CASES = ["cfg1", "nohf_mu", "2orb_hund", "nspin2", "3orb"]
+STAR_FLAGS = [0, 16]
 CASES = dict(BASE_CASES)
 CASES["3orb"] = dict(Norb=3, Nbath=1, uloc=(2.0, 1.0, 3.0), ust=1.0, jh=0.2)
 
 
+@pytest.mark.parametrize("flags", STAR_FLAGS)
 @pytest.mark.parametrize("name", STAR_CASES)
-def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name):
-    p, model, ctx, rng = make(oracle, edb, CASES[name], layout=2, hxv_kernel=2)
+def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name, flags):
+    p, model, ctx, rng = make(oracle, edb, CASES[name], layout=2, hxv_kernel=2, debug_flags=flags)
     Ns = p.Ns
     for nup, ndw in all_sectors(Ns):
         smap = oracle.build_sector(Ns, nup, ndw)
@@ -31,7 +33,9 @@ def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name):
     ctx.close()
 
 
-@pytest.mark.parametrize("flags", [0, 3])           # 3 = fallback paths: 2-column down strips + single-stage up pass
+# 3 = fallback paths (2-column down strips + single-stage up pass), 4 = generic tile_pass everywhere,
+# 8 = cp.async up kernel instead of the bulk-copy one, 16 = bulk-copy up kernel for every block size
+@pytest.mark.parametrize("flags", [0, 3, 4, 8, 16])
 @pytest.mark.parametrize("Norb,Nbath,sec", [(1, 9, (5, 5)), (1, 9, (6, 5)), (2, 4, (5, 5)), (2, 4, (4, 6)), (3, 2, (4, 5))])
 def test_star_hxv_medium_sectors(oracle, edb, Norb, Nbath, sec, flags):
     case = dict(Norb=Norb, Nbath=Nbath, uloc=tuple([2.0] * Norb), ust=0.7 if Norb > 1 else 0.0, jh=0.1 if Norb > 1 else 0.0)
