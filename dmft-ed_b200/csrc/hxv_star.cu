@@ -20,6 +20,7 @@
 // Algorithmic bytes per H*v are 2*Dim*8; this two-pass scheme moves 5*Dim*8 through HBM because a
 // tile closed under BOTH spins (70^4 doubles at Ns=16) fits no on-chip memory.
 #include "edgpu_internal.h"
+#include <cuda.h>
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -1046,7 +1047,7 @@ __global__ void __launch_bounds__(kNT)
 k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
           const StarBlock *__restrict__ blocks,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
-          const double *__restrict__ x, double *__restrict__ y, int maxD)
+          const double *__restrict__ x, double *__restrict__ y, int maxD, int pf_dist)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StarBlock B = blocks[block_index];
@@ -1080,6 +1081,13 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
             *reinterpret_cast<double2 *>(s_in + (size_t)2 * (q * R + r)) = a;
             if (W == 4) *reinterpret_cast<double2 *>(s_in + (size_t)2 * tile_rows + (size_t)2 * (q * R + r)) = b;
         }
+    }
+    if (NH > 0 && W == 4) {
+        // one CTA per SM and no second buffer: pull the strip that the NEXT CTA of this SM will stage into L2 while this
+        // one computes, so that its staging loads see an L2 hit instead of a loaded-DRAM latency
+        const int64_t cn = cbase + (int64_t)gridDim.y * 0 + (int64_t)pf_dist * SP * W;
+        if (cn < dim_up)
+            for (int r = tid; r < R; r += kNT) asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (int64_t)r * ld + cn));
     }
     __syncthreads();
     double *ys = y + (int64_t)B.off * ld;
@@ -1132,6 +1140,135 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Down pass, tensor-map (TMA) version:  y[blk rows][strip] = H_dw x.
+// A tile = the rows of one down-block x one strip of 4 columns = R segments of 32 bytes, ld*8 bytes apart.  The
+// LSU handles such a pattern one 32-byte sector per wavefront; here the copy engine gathers the tile
+// (cp.async.bulk.tensor.2d, boxes of 4 columns x BR rows of a 2-D tensor map over the vector) straight into a
+// dense [row][4] shared-memory image, a producer warp keeps `nstage` tiles in flight (and prefetches the tile after
+// into L2 when there is only one buffer), and 16 consumer warps gather from the image.
+// Thread (row, half): each thread owns 2 of the 4 columns of a row, so a quarter-warp of an LDS.128 touches
+// 4 consecutive rows x 32 bytes = one conflict-free 128-byte wavefront without any swizzle.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int NORB, int NH>
+__global__ void __launch_bounds__(kNT3)
+k_star_dw3(const __grid_constant__ CUtensorMap tmx, StarKParams P, int64_t dim_up, int64_t ld, int block_index, int BR, int nstage,
+           const StarBlock *__restrict__ blocks,
+           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
+           double *__restrict__ y, int maxD)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const StarBlock B = blocks[block_index];
+    const int R = B.size, tid = threadIdx.x;
+    const uint32_t tileb = ((uint32_t)R * 32u + 127u) & ~127u;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nstage * tileb);   // full[2], done[2]
+    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_bar + 4);
+    int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
+    const LeanTabs LT = load_lean_tabs<NORB, NH>(P, B, D, A0, hopd, hopc, hopv, nullptr, tab_base, maxD, 32);
+    const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        mbar_init(bar0 + 16, kNT / 32); mbar_init(bar0 + 24, kNT / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t ntiles = (dim_up + 3) / 4;
+
+    if (tid >= kNT) {
+        // ---------------- producer warp ----------------
+        if (tid == kNT) {
+            const int nbox = R / BR;
+            int i = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+                const int st = i % nstage, k = i / nstage;
+                if (i >= nstage) mbar_wait(bar0 + 16 + 8 * st, (uint32_t)(k - 1) & 1u);      // consumers left the buffer
+                const uint32_t fb = bar0 + 8 * st;
+                mbar_expect_tx(fb, (uint32_t)R * 32u);
+                const uint32_t dst = tile0 + (uint32_t)st * tileb;
+                for (int b = 0; b < nbox; b++) tma_load_2d(dst + (uint32_t)b * (uint32_t)BR * 32u, &tmx, (int)(4 * t), B.off + b * BR, fb);
+                const int64_t tn = t + (int64_t)nstage * gridDim.x;                          // the tile that follows in this buffer
+                if (tn < ntiles)
+                    for (int b = 0; b < nbox; b++) tma_prefetch_2d(&tmx, (int)(4 * tn), B.off + b * BR);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: thread = (row slot, column half) ----------------
+    const int half = tid & 1, ri = tid >> 1;
+    const int D0 = D[0], D1 = D[1];
+    const int ty = (D0 == 1) ? ri : (int)__umulhi((uint32_t)ri, B.magic0);
+    const int i0 = ri - ty * D0;
+    const int NY = (kNT / 2) / D0, O = B.nouter;
+    const bool active = ty < NY && ty < O;
+    // star-0 hop list of the thread in registers
+    double rval[NH];
+    int roff[NH], cnt0 = 0;
+    double s0 = 1.0;
+    {
+        const int ii = active ? i0 : 0;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+            const double2 w = lds128(LT.ent + (uint32_t)(ii * NH + h) * 16u);
+            rval[h] = w.x; roff[h] = __double2loint(w.y);
+            if (h == 0) cnt0 = __double2hiint(w.y);
+        }
+        s0 = lds128(LT.aux + (uint32_t)ii * 16u).y;
+    }
+    const int estep = NY * D0;
+    int i = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+        const int st = i % nstage, k = i / nstage;
+        mbar_wait(bar0 + 8 * st, (uint32_t)k & 1u);
+        if (active) {
+            const uint32_t tb = tile0 + (uint32_t)st * tileb + (uint32_t)half * 16u;
+            int i1 = ty, i2 = 0;
+            if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+            const int e0 = ty * D0 + i0;
+            uint32_t a0 = tb + (uint32_t)e0 * 32u;
+            double *yp = y + ((int64_t)B.off + e0) * ld + 4 * t + 2 * half;
+            const int64_t ystep = (int64_t)estep * ld;
+#pragma unroll 2
+            for (int o = ty; o < O; o += NY) {
+                double sg0 = 1.0, sg1 = s0, sg2 = s0;
+                if (NORB >= 2) { const double s1 = lds128(LT.aux + (uint32_t)(maxD + i1) * 16u).y; sg0 = s1; sg2 *= s1; }
+                if (NORB >= 3) { const double s2 = lds128(LT.aux + (uint32_t)(2 * maxD + i2) * 16u).y; sg0 *= s2; sg1 *= s2; }
+                double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+                for (int h = 0; h < NH; h++) {
+                    if (h < cnt0) {
+                        const double2 u = lds128(a0 + (uint32_t)roff[h]);
+                        p0 = fma(rval[h], u.x, p0); p1 = fma(rval[h], u.y, p1);
+                    }
+                }
+                double acc[2] = {sg0 * p0, sg0 * p1};
+                if (NORB >= 2) lean_star<NH, 2, false>(acc, a0, 0u, LT.ent + (uint32_t)((maxD + i1) * NH) * 16u, sg1);
+                if (NORB >= 3) lean_star<NH, 2, false>(acc, a0, 0u, LT.ent + (uint32_t)((2 * maxD + i2) * NH) * 16u, sg2);
+                *reinterpret_cast<double2 *>(yp) = make_double2(acc[0], acc[1]);     // pad columns receive exact zeros
+                yp += ystep;
+                a0 += (uint32_t)estep * 32u;
+                i1 += NY;
+                if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar0 + 16 + 8 * st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 static void fill_kparams(const StarInfo &S, StarKParams &P)
 {
     memset(&P, 0, sizeof(P));
@@ -1156,8 +1293,45 @@ static int ensure_smem(edgpu_ctx *ctx, const void *kern, size_t smem)
     return 0;
 }
 
+// 2-D tensor map over a [rows][ld] fp64 tile for the strip loads of the down pass: boxes of 4 columns x BR rows
+static int encode_strip_map(edgpu_ctx *ctx, CUtensorMap *tm, const double *base, int64_t ld, int64_t rows, int BR)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return edgpu_fail(ctx, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeFn>(p);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {4, (cuuint32_t)BR};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return edgpu_fail(ctx, "cuTensorMapEncodeTiled failed (%d) for ld=%lld rows=%lld box=4x%d", (int)r, (long long)ld, (long long)rows, BR);
+    return 0;
+}
+
+using Dw3Kernel = void (*)(const CUtensorMap, StarKParams, int64_t, int64_t, int, int, int, const StarBlock *, const int16_t *, const uint8_t *,
+                           const double *, double *, int);
+template <int NORB>
+static Dw3Kernel pick_dw3(int NH)
+{
+    switch (NH) {
+        case 4: return k_star_dw3<NORB, 4>;
+        case 5: return k_star_dw3<NORB, 5>;
+        case 6: return k_star_dw3<NORB, 6>;
+        default: return k_star_dw3<NORB, 8>;
+    }
+}
+
 using DwKernel = void (*)(StarKParams, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
-                          const double *, double *, int);
+                          const double *, double *, int, int);
 using UpKernel = void (*)(StarKParams, SlabMap, int64_t, int64_t, int, int, int, int, const StarBlock *, const int16_t *, const uint8_t *,
                           const double *, const double *, const double *, const uint32_t *, const double *, const double *, double *, int);
 
@@ -1224,9 +1398,33 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
         // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
         int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
         SP = std::max<int64_t>(1, std::min<int64_t>(SP, ((ncols + 3) / 4) / (4 * (int64_t)ctx->sm_count)));
-        const int NH = (SP == 1 && !force_generic) ? round_nh(B.nh) : 0;
         int bD = 1;                                                            // table stride: largest star of THIS block
         for (int a = 0; a < NORB; a++) bD = std::max(bD, Dn.D[B.n[a]]);
+        if (!force_generic && !(ctx->par.reserved[0] & 8) && B.size >= ((ctx->par.reserved[0] & 16) ? 4 : kBulkMin) && round_nh(B.nh) &&
+            B.size % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && ld % 2 == 0) {
+            // tensor-map pipeline
+            int BR = 0;
+            for (int d = 4; d <= 256 && d <= B.size; d += 4)
+                if (B.size % d == 0) BR = d;
+            const int NH3 = round_nh(B.nh);
+            const size_t tileb = ((size_t)B.size * 32 + 127) & ~(size_t)127;
+            const size_t tabs = lean_tabs_bytes(NORB, bD, NH3) + 64;
+            const int nstage = (2 * tileb + tabs <= 227 * 1024) ? 2 : 1;
+            const size_t smem = nstage * tileb + tabs;
+            if (BR >= 16 && smem <= 227 * 1024) {
+                CUtensorMap tm;
+                if (int rc = encode_strip_map(ctx, &tm, x, ld, s->dim_dw, BR)) return rc;
+                auto kern = pick_dw3<NORB>(NH3);
+                if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
+                const int64_t ntiles = (ncols + 3) / 4;
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
+                const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+                kern<<<nctas, kNT3, smem, ctx->stream>>>(tm, PD, ncols, ld, (int)bi, BR, nstage, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, y, bD);
+                CUDA_TRY(ctx, cudaGetLastError());
+                continue;
+            }
+        }
+        const int NH = (SP == 1 && !force_generic) ? round_nh(B.nh) : 0;
         const size_t tab = NH ? lean_tabs_bytes(NORB, bD, NH) : tabs_bytes(NORB, bD, Dn.H);
         const int W = (!force_narrow && sizeof(double) * (size_t)B.size * 4 * SP + tab <= 227 * 1024) ? 4 : 2;
         const int64_t nstrips = (ncols + W - 1) / W;
@@ -1235,7 +1433,8 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
         auto kern = pick_dw<NORB>(W, NH);
         if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
         const unsigned nctas = (unsigned)((nstrips + SP - 1) / SP);
-        kern<<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, x, y, bD);
+        kern<<<nctas, kNT, smem, ctx->stream>>>(PD, ncols, ld, (int)bi, (int)SP, Dn.d_blocks, Dn.d_hopd, Dn.d_hopc, Dn.d_hopv, x, y, bD,
+                                                 ctx->sm_count * (smem * 2 + 2048 <= 227 * 1024 ? 2 : 1));
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return 0;
