@@ -31,6 +31,7 @@ static constexpr int kMaxStarCfg = 1024;      // 2^(Nbath+1), Nbath <= 9
 static constexpr int kMaxH = 9;               // hops per star configuration <= Nbath
 static constexpr int kMaxBlocks = 4096;
 static constexpr int kBigBlock = 2048;        // up-blocks at least this large use the pipelined kernel
+static constexpr int kBulkMin = 256;          // blocks at least this large use the copy-engine (TMA) kernels; smaller ones the fringe kernels
 
 struct StarBlock {             // one occupation tuple of one spin
     int off;                   // first internal index
@@ -61,9 +62,12 @@ struct StarInfo {
     int ngroups = 0, max_small = 0;
     std::vector<int> big_blocks;                 // blocks handled by the persistent pipelined up kernel
     int max_block = 0;
+    // "fringe": the configurations of all blocks smaller than kBulkMin, handled by one thread-per-element launch
+    int nfringe = 0;
+    int *d_fringe = nullptr;                     // [nfringe] internal indices
     ~StarInfo()
     {
-        cudaFree(d_blocks); cudaFree(d_hopj); cudaFree(d_hopd); cudaFree(d_hopc); cudaFree(d_hopv); cudaFree(d_estar); cudaFree(d_upgroups); cudaFree(d_uplist);
+        cudaFree(d_blocks); cudaFree(d_hopj); cudaFree(d_hopd); cudaFree(d_hopc); cudaFree(d_hopv); cudaFree(d_estar); cudaFree(d_upgroups); cudaFree(d_uplist); cudaFree(d_fringe);
     }
 };
 
@@ -256,6 +260,17 @@ int build_star_layout(edgpu_ctx *ctx, SpinBasis *b, const std::vector<HopPair> &
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_estar, estar.data(), sizeof(double) * estar.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_upgroups, groups.data(), sizeof(int) * groups.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(S->d_uplist, uplist.data(), sizeof(int) * uplist.size(), cudaMemcpyHostToDevice, st));
+    {
+        std::vector<int> fr;
+        for (const StarBlock &B : S->blocks)
+            if (B.size < kBulkMin)
+                for (int e = 0; e < B.size; e++) fr.push_back(B.off + e);
+        S->nfringe = (int)fr.size();
+        if (S->nfringe) {
+            CUDA_TRY(ctx, cudaMalloc(&S->d_fringe, sizeof(int) * fr.size()));
+            CUDA_TRY(ctx, cudaMemcpyAsync(S->d_fringe, fr.data(), sizeof(int) * fr.size(), cudaMemcpyHostToDevice, st));
+        }
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     cudaFree(d_srank); cudaFree(d_D); cudaFree(d_blockoff);
     b->star = S;
@@ -1269,6 +1284,63 @@ k_star_dw3(const __grid_constant__ CUtensorMap tmx, StarKParams P, int64_t dim_u
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Fringe kernels: the blocks smaller than kBulkMin hold ~1 % of a large sector but would cost one launch each
+// (~20 us apiece for no work); all of them go through ONE thread-per-element launch per pass that reads the ELL hop
+// tables of the generic kernel (hxv_generic.cu) straight from global memory / L2.
+//   k_fringe_dw: y[rd][c]  = sum_j ampD_j x[tgtD_j(rd)][c]                       rd in the fringe rows, all columns
+//   k_fringe_up: y[r][ru] (+)= diag x[r][ru] + sum_j ampU_j x[r][tgtU_j(ru)]      ru in the fringe columns, all rows
+__global__ void __launch_bounds__(256)
+k_fringe_dw(int nfr, const int *__restrict__ fringe, int64_t ncols, int64_t ld, int64_t dim_dw,
+            const uint32_t *__restrict__ hop_dw, const uint8_t *__restrict__ nhop_dw, const double *__restrict__ amp_dw,
+            const double *__restrict__ x, double *__restrict__ y)
+{
+    __shared__ double s_amp[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_amp[i] = amp_dw[i];
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    for (int q = blockIdx.y; q < nfr; q += gridDim.y) {
+        const int64_t rd = fringe[q];
+        const int nd = nhop_dw[rd];
+        double acc = 0.0;
+        for (int j = 0; j < nd; j++) {
+            const uint32_t h = hop_dw[(int64_t)j * dim_dw + rd];
+            acc += s_amp[h & 255u] * x[(int64_t)(h >> 8) * ld + c];
+        }
+        y[rd * ld + c] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, int64_t dim_up, int norb, int accumulate,
+            const uint32_t *__restrict__ cfg_up, const uint32_t *__restrict__ cfg_dw,
+            const double *__restrict__ e_up, const double *__restrict__ e_dw, const double *__restrict__ xtab,
+            const uint32_t *__restrict__ hop_up, const uint8_t *__restrict__ nhop_up, const double *__restrict__ amp_up,
+            const double *__restrict__ x, double *__restrict__ y)
+{
+    __shared__ double s_amp[256], s_x[32 * 32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_amp[i] = amp_up[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_x[i] = xtab[i];
+    __syncthreads();
+    const uint32_t impmask = (1u << norb) - 1u;
+    const int64_t total = nrows * nfr;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / nfr;
+        const int q = (int)(idx - r * nfr);
+        const int64_t ru = fringe[q];
+        const double *xr = x + r * ld;
+        double acc = (e_up[ru] + e_dw[r] + s_x[(cfg_dw[r] & impmask) * 32u + (cfg_up[ru] & impmask)]) * xr[ru];
+        if (accumulate) acc += y[r * ld + ru];
+        const int nu = nhop_up[ru];
+        for (int j = 0; j < nu; j++) {
+            const uint32_t h = hop_up[(int64_t)j * dim_up + ru];
+            acc += s_amp[h & 255u] * xr[h >> 8];
+        }
+        y[r * ld + ru] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 static void fill_kparams(const StarInfo &S, StarKParams &P)
 {
     memset(&P, 0, sizeof(P));
@@ -1276,7 +1348,6 @@ static void fill_kparams(const StarInfo &S, StarKParams &P)
     for (int m = 0; m < 16; m++) { P.D[m] = S.D[m]; P.A0[m] = S.A0[m]; P.coff[m] = S.coff[m]; }
 }
 
-static constexpr int kBulkMin = 256;         // up-blocks at least this large use the bulk-copy (TMA) up kernel
 static constexpr int kStageElems = 4900;     // elements (x 16 B) per pipeline stage of the up pass / per tile of the down pass
 
 // hop lists of the lean kernels are padded to one of these lengths (0: no lean kernel, generic tile_pass)
@@ -1393,8 +1464,15 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
     if (maxD > kNT) return edgpu_fail(ctx, "star kernels: star dimension %d exceeds %d threads", maxD, kNT);
     const bool force_narrow = (ctx->par.reserved[0] & 1) != 0;                 // test hook: exercise the 2-column path
     const bool force_generic = (ctx->par.reserved[0] & 4) != 0;                // test hook: generic tile_pass everywhere
+    const bool fringe = !(ctx->par.reserved[0] & (4 | 8 | 16)) && Dn.nfringe > 0;
+    if (fringe) {
+        dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)std::min(Dn.nfringe, 4096));
+        k_fringe_dw<<<grid, 256, 0, ctx->stream>>>(Dn.nfringe, Dn.d_fringe, ncols, ld, s->dim_dw, s->dw->hop, s->dw->nhop, s->dw->amp, x, y);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     for (size_t bi = 0; bi < Dn.blocks.size(); bi++) {                         // one launch per down-block
         const StarBlock &B = Dn.blocks[bi];
+        if (fringe && B.size < kBulkMin) continue;
         // strips per tile: up to kStageElems rows (x 32 B) of shared memory, but keep >= 4 CTAs per SM worth of tiles
         int64_t SP = std::max<int64_t>(1, kStageElems / B.size);
         SP = std::max<int64_t>(1, std::min<int64_t>(SP, ((ncols + 3) / 4) / (4 * (int64_t)ctx->sm_count)));
@@ -1458,8 +1536,17 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
     memset(&M, 0, sizeof(M));
     if (slabs) M = *slabs; else { M.n = 1; M.ldc0 = (int)ld; M.magic = 0; M.ldc[0] = (int)ld; }
     const int64_t npairs = (nrows + 1) / 2;
+    const bool fringe = !slabs && !(ctx->par.reserved[0] & (4 | 8 | 16)) && U.nfringe > 0;
+    if (fringe) {
+        const int64_t total = nrows * U.nfringe;
+        const unsigned nb = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
+        k_fringe_up<<<nb, 256, 0, ctx->stream>>>(U.nfringe, U.d_fringe, nrows, ld, s->dim_up, NORB, accumulate, s->up->cfg, s->dw->cfg + row0,
+                                                 s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     for (size_t bi = 0; bi < U.blocks.size(); bi++) {                          // persistent kernel, one launch per up-block
         const StarBlock &B = U.blocks[bi];
+        if (fringe && B.size < kBulkMin) continue;
         int64_t RP = std::max<int64_t>(1, kStageElems / B.size);
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
         int bD = 1;
@@ -1563,5 +1650,11 @@ int hxv_star(edgpu_sector *s, const double *x, double *y)
 
 int hxv_star_launches(const edgpu_sector *s)
 {
-    return (int)s->up->star->blocks.size() + (int)s->dw->star->blocks.size();
+    int n = 0;
+    for (const StarInfo *S : {s->up->star.get(), s->dw->star.get()}) {
+        const bool fringe = !(s->ctx->par.reserved[0] & (4 | 8 | 16)) && S->nfringe > 0;
+        for (const StarBlock &B : S->blocks) n += (fringe && B.size < kBulkMin) ? 0 : 1;
+        n += fringe ? 1 : 0;
+    }
+    return n;
 }

@@ -153,7 +153,8 @@ def test_shard_entry_points_equal_full_product(oracle, edb):
             for q in range(world):
                 n = plan.nrows[r] * plan.ldc[q]
                 blk = ys[off:off + n].view(plan.nrows[r], plan.ldc[q]).cpu().numpy()
-                assert np.array_equal(blk, yr.cpu().numpy()[:, plan.col0[q]:plan.col0[q] + plan.ldc[q]])
+                ref_blk = yr.cpu().numpy()[:, plan.col0[q]:plan.col0[q] + plan.ldc[q]]
+                assert np.abs(blk - ref_blk).max() <= 1e-13 * max(1.0, np.abs(ref_blk).max())   # other kernels, other summation order
                 off += n
         assert np.abs(Y - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
     x.free(); y.free(); s.free(); ctx.close()
