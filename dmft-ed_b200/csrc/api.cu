@@ -71,6 +71,7 @@ extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu
     h.hloc.assign((size_t)h.nspin * h.norb * h.norb, 0.0);
     const size_t nscal = 8 + 2 * 4096;
     if (cudaMalloc(&ctx->d_partials, sizeof(double) * kRedBlocks * 4) != cudaSuccess ||
+        cudaMalloc(&ctx->d_dotpart, sizeof(double) * 16384) != cudaSuccess ||
         cudaMalloc(&ctx->d_scal, sizeof(double) * nscal) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scal, sizeof(double) * 64) != cudaSuccess) {
         delete ctx;
@@ -87,7 +88,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->bases.clear();
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
     delete ctx;
     return 0;
 }
@@ -331,6 +332,8 @@ static bool use_star(const edgpu_sector *s)
     if (s->up->layout != 2 || s->dw->layout != 2 || ctx->par.hxv_kernel == 1 || ctx->ham.jhflag) return false;
     return ctx->par.hxv_kernel == 2 || s->dim >= (1ll << 21);
 }
+
+bool hxv_uses_star(const edgpu_sector *s) { return !s->csr && use_star(s); }
 
 int hxv_dispatch(edgpu_sector *s, const double *x, double *y)
 {

@@ -87,7 +87,8 @@ struct edgpu_ctx {
     std::string err;
     std::map<std::pair<int, int>, std::shared_ptr<SpinBasis>> bases;   // (pspin, n) -> tables
     // reduction scratch
-    double *d_partials = nullptr;      // [kMaxPartials * kMaxScal]
+    double *d_partials = nullptr;      // [kRedBlocks * 4]
+    double *d_dotpart = nullptr;       // [16384] per-CTA partials of the dot product fused into the star up pass
     double *d_scal = nullptr;          // device scalars
     double *h_scal = nullptr;          // pinned host mirror
     void *d_flush = nullptr;           // L2 flush scratch
@@ -116,6 +117,8 @@ struct edgpu_vec {
 int build_spin_basis(edgpu_ctx *ctx, int pspin, int n, std::shared_ptr<SpinBasis> &out);
 int hxv_generic(edgpu_sector *s, const double *x, double *y);
 int hxv_star(edgpu_sector *s, const double *x, double *y);
+int hxv_star_dot(edgpu_sector *s, const double *x, double *y, double *dot, int *ndot);
+bool hxv_uses_star(const edgpu_sector *s);
 int hxv_csr(edgpu_sector *s, const double *x, double *y);
 int hxv_dispatch(edgpu_sector *s, const double *x, double *y);
 int upload_xtab(edgpu_ctx *ctx);

@@ -31,6 +31,7 @@ static constexpr int kMaxStarCfg = 1024;      // 2^(Nbath+1), Nbath <= 9
 static constexpr int kMaxH = 9;               // hops per star configuration <= Nbath
 static constexpr int kMaxBlocks = 4096;
 static constexpr int kBigBlock = 2048;        // up-blocks at least this large use the pipelined kernel
+static constexpr int kDotSlots = 16384;       // capacity of ctx->d_dotpart (per-CTA partial sums of the fused <x, H x>)
 static constexpr int kBulkMin = 256;          // blocks at least this large use the copy-engine (TMA) kernels; smaller ones the fringe kernels
 
 struct StarBlock {             // one occupation tuple of one spin
@@ -926,9 +927,11 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
            const StarBlock *__restrict__ blocks,
            const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
            const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
-           const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD)
+           const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD,
+           double *__restrict__ dot_out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_dot[kNT / 32];
     const StarBlock B = blocks[block_index];
     const int size = B.size, tid = threadIdx.x;
     const int lead = B.off & 1;                                                // copy starts one element early when the block starts odd
@@ -1017,6 +1020,7 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
     L.init(B, D, A0, LT);
     const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
     const int estep = NY * D0;
+    double dsum = 0.0;                                                        // partial <x, H x> (fused Lanczos alpha)
     int i = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
         const int st = i & 1, k = i >> 1;
@@ -1038,7 +1042,10 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
                     double acc[1], es;
                     uint32_t dgo;
                     lean_element<NORB, NH, 1>(L, LT, A0, maxD, a0, 0u, i1, i2, init, acc, es, dgo);
-                    sts64(ya, fma(es + lds64(dgs + dgo), lds64(a0), acc[0]));
+                    const double own = lds64(a0);
+                    const double res = fma(es + lds64(dgs + dgo), own, acc[0]);
+                    sts64(ya, res);
+                    dsum = fma(own, res, dsum);
                     a0 += (uint32_t)estep * 8u;
                     ya += (uint32_t)estep * 8u;
                     i1 += NY;
@@ -1049,6 +1056,18 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // results visible to the copy engine
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(bar0 + 16 + 8 * st);
+    }
+    if (dot_out) {
+        // fixed-order reduction over the 16 consumer warps (named barrier: the producer warp is not part of it)
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+        if ((tid & 31) == 0) s_dot[tid >> 5] = dsum;
+        asm volatile("bar.sync 1, %0;" ::"n"(kNT) : "memory");
+        if (tid == 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kNT / 32; w++) v += s_dot[w];
+            dot_out[blockIdx.x] = v;
+        }
     }
 }
 
@@ -1316,14 +1335,15 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
             const uint32_t *__restrict__ cfg_up, const uint32_t *__restrict__ cfg_dw,
             const double *__restrict__ e_up, const double *__restrict__ e_dw, const double *__restrict__ xtab,
             const uint32_t *__restrict__ hop_up, const uint8_t *__restrict__ nhop_up, const double *__restrict__ amp_up,
-            const double *__restrict__ x, double *__restrict__ y)
+            const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dot_out)
 {
-    __shared__ double s_amp[256], s_x[32 * 32];
+    __shared__ double s_amp[256], s_x[32 * 32], s_red[8];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_amp[i] = amp_up[i];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_x[i] = xtab[i];
     __syncthreads();
     const uint32_t impmask = (1u << norb) - 1u;
     const int64_t total = nrows * nfr;
+    double dsum = 0.0;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / nfr;
         const int q = (int)(idx - r * nfr);
@@ -1337,6 +1357,17 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
             acc += s_amp[h & 255u] * xr[h >> 8];
         }
         y[r * ld + ru] = acc;
+        dsum = fma(xr[ru], acc, dsum);
+    }
+    if (dot_out) {
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int w = 0; w < 8; w++) v += s_red[w];
+            dot_out[blockIdx.x] = v;
+        }
     }
 }
 
@@ -1426,7 +1457,7 @@ static DwKernel pick_dw(int W, int NH)
 }
 
 using Up3Kernel = void (*)(StarKParams, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
-                           const double *, const double *, const uint32_t *, const double *, const double *, double *, int);
+                           const double *, const double *, const uint32_t *, const double *, const double *, double *, int, double *);
 template <int NORB>
 static Up3Kernel pick_up3(int NH)
 {
@@ -1521,9 +1552,13 @@ static int launch_star_dw(edgpu_sector *s, const double *x, double *y, int64_t n
 // Up pass on a row range: x, y point at a [nrows][ld] tile holding ALL up-spin columns of down-spin rows
 // [row0, row0+nrows) (the whole vector, or the row shard of one rank after the transpose).
 template <int NORB>
+// dot != nullptr: the kernels also leave per-CTA partial sums of <x, y_final> in dot[0 .. *ndot); *ndot = -1 when a block
+// went through a kernel without that epilogue (the caller then computes the dot product separately)
 static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate,
-                          const SlabMap *slabs = nullptr)
+                          const SlabMap *slabs = nullptr, double *dot = nullptr, int *ndot = nullptr)
 {
+    int slots = 0;
+    bool dot_ok = dot != nullptr;
     edgpu_ctx *ctx = s->ctx;
     const StarInfo &U = *s->up->star;
     StarKParams PU;
@@ -1540,9 +1575,12 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
     if (fringe) {
         const int64_t total = nrows * U.nfringe;
         const unsigned nb = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
+        const bool d = dot_ok && slots + (int)nb <= kDotSlots;
         k_fringe_up<<<nb, 256, 0, ctx->stream>>>(U.nfringe, U.d_fringe, nrows, ld, s->dim_up, NORB, accumulate, s->up->cfg, s->dw->cfg + row0,
-                                                 s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y);
+                                                 s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y,
+                                                 d ? dot + slots : nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
+        if (d) slots += (int)nb; else dot_ok = false;
     }
     for (size_t bi = 0; bi < U.blocks.size(); bi++) {                          // persistent kernel, one launch per up-block
         const StarBlock &B = U.blocks[bi];
@@ -1565,9 +1603,11 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
                 if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
                 const int64_t ntiles = (nrows + G - 1) / G;
                 const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
+                const bool d = dot_ok && slots + (int)nctas <= kDotSlots;
                 kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)G, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
-                                                          s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD);
+                                                          s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD, d ? dot + slots : nullptr);
                 CUDA_TRY(ctx, cudaGetLastError());
+                if (d) slots += (int)nctas; else dot_ok = false;
                 continue;
             }
         }
@@ -1586,7 +1626,9 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         kern<<<nctas, kNT, smem, ctx->stream>>>(PU, M, nrows, ld, (int)bi, (int)RP, accumulate, nstage, U.d_blocks, U.d_hopd, U.d_hopc,
                                                           U.d_hopv, U.d_estar, s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD);
         CUDA_TRY(ctx, cudaGetLastError());
+        dot_ok = false;
     }
+    if (ndot) *ndot = dot_ok ? slots : -1;
     return 0;
 }
 
@@ -1646,6 +1688,19 @@ int hxv_star(edgpu_sector *s, const double *x, double *y)
 {
     if (int rc = hxv_star_dw(s, x, y, s->dim_up, s->ld)) return rc;
     return hxv_star_up(s, x, y, 0, s->dim_dw, s->ld, 1);
+}
+
+// y = H x and, fused into the up pass, per-CTA partial sums of <x, y> in dot[0 .. *ndot) (Lanczos alpha);
+// *ndot = -1: not produced (some block used a kernel without the epilogue)
+int hxv_star_dot(edgpu_sector *s, const double *x, double *y, double *dot, int *ndot)
+{
+    if (int rc = hxv_star_dw(s, x, y, s->dim_up, s->ld)) return rc;
+    switch (s->ctx->ham.norb) {
+    case 1: return launch_star_up<1>(s, x, y, 0, s->dim_dw, s->ld, 1, nullptr, dot, ndot);
+    case 2: return launch_star_up<2>(s, x, y, 0, s->dim_dw, s->ld, 1, nullptr, dot, ndot);
+    case 3: return launch_star_up<3>(s, x, y, 0, s->dim_dw, s->ld, 1, nullptr, dot, ndot);
+    default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
+    }
 }
 
 int hxv_star_launches(const edgpu_sector *s)

@@ -5,6 +5,10 @@
 // ED_GF_NORMAL.f90:187-192,240-245 (in-tree ancestor .repo/PLAIN_LANCZOS.f90:87-118,154-180,286-385).
 // Recurrence (no re-orthogonalisation, like the reference):
 //   tmp = H vin - b vout ; a = <vin,tmp> ; tmp -= a vin ; b = |tmp| ; vout = vin ; vin = tmp/b
+// evaluated on UNNORMALISED vectors w_k = b_k v_k so that no pass is spent on scaling (lanczos_step below):
+//   u = H w_k ; a_k = <w_k,u>/b_k^2 ; w_{k+1} = u/b_k - (b_k/b_{k-1}) w_{k-1} - (a_k/b_k) w_k ; b_{k+1} = |w_{k+1}|
+// (<v_k, v_{k-1}> = 0 to rounding, so a_k equals the reference's <v_k, H v_k - b_k v_{k-1}> to ~1e-16), and with
+// <w_k,u> accumulated inside the H*v kernels of the star path: 4 vector passes per step instead of 9.
 // All Lanczos scalars live in device memory so that the GF tridiagonalisation runs without host round trips;
 // dot products use a fixed launch shape + fixed-order second stage => bit-reproducible run to run.
 #include "edgpu_internal.h"
@@ -55,36 +59,6 @@ __global__ void __launch_bounds__(kRedThreads) k_dot(const double *__restrict__ 
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         acc += a[i] * b[i];
-    block_store_partial(acc, partials + blockIdx.x);
-}
-
-// tmp -= b*vout ; partial <vin,tmp>          (b read from device memory)
-__global__ void __launch_bounds__(kRedThreads) k_lanc_a(double *__restrict__ tmp, const double *__restrict__ vout,
-                                                        const double *__restrict__ vin, const double *__restrict__ bptr,
-                                                        int64_t n, double *__restrict__ partials)
-{
-    const double b = *bptr;
-    double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double t = tmp[i] - b * vout[i];
-        tmp[i] = t;
-        acc += vin[i] * t;
-    }
-    block_store_partial(acc, partials + blockIdx.x);
-}
-
-// tmp -= a*vin ; partial <tmp,tmp>
-__global__ void __launch_bounds__(kRedThreads) k_lanc_b(double *__restrict__ tmp, const double *__restrict__ vin,
-                                                        const double *__restrict__ aptr, int64_t n,
-                                                        double *__restrict__ partials)
-{
-    const double a = *aptr;
-    double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double t = tmp[i] - a * vin[i];
-        tmp[i] = t;
-        acc += t * t;
-    }
     block_store_partial(acc, partials + blockIdx.x);
 }
 
@@ -151,20 +125,74 @@ int sector_work(edgpu_sector *s, int i, double **p)
 // Device scalar slots (ctx->d_scal): [0] norm / b , [1] a , [2] zero constant, [8 + k] alanc[k], [8 + NMAX + k] blanc[k]
 static constexpr int kScalB = 0, kScalArr = 8, kLancMax = 4096;
 
-// One Lanczos step on device pointers. b_in: device pointer to the b of the previous step; a_out/b_out: where
-// to leave this step's a and b.  On return the roles rotate: (vin, vout, tmp) -> (tmp, vin, vout).
-static int lanczos_step(edgpu_sector *s, double *vin, double *vout, double *tmp,
-                        const double *b_in, double *a_out, double *b_out)
+// a = (sum of the partials) / nrm^2
+__global__ void k_lanc_alpha(const double *__restrict__ partials, int n, const double *__restrict__ nrm, double *__restrict__ out)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    __shared__ double sh[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) { const double d = *nrm; *out = v / (d * d); }
+    }
+}
+
+// w_new = u/nc - (bp/no) w_old - (a/nc) w_cur, written over w_old ; partial |w_new|^2
+__global__ void __launch_bounds__(kRedThreads) k_lanc_c(double *__restrict__ old, const double *__restrict__ u,
+                                                        const double *__restrict__ cur, const double *__restrict__ p_bprev,
+                                                        const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
+                                                        const double *__restrict__ p_a, int64_t n, double *__restrict__ partials)
+{
+    const double nc = *p_ncur, c_old = *p_bprev / *p_nold, c_cur = *p_a / nc;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = u[i] / nc - c_old * old[i] - c_cur * cur[i];
+        old[i] = t;
+        acc += t * t;
+    }
+    block_store_partial(acc, partials + blockIdx.x);
+}
+
+__global__ void k_set_one(double *p) { *p = 1.0; }
+
+// Device scalar slots: [0] norm, [3] the constant 1, [kScalArr + k] alanc[k], [kScalArr + kLancMax + k] blanc[k]
+static int reset_scalars(edgpu_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    k_set_one<<<1, 1, 0, ctx->stream>>>(ctx->d_scal + 3);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// One Lanczos step (iteration `iter`, 1-based) on unnormalised vectors: cur = w_iter (norm b_iter, 1 for iter 1),
+// old = w_{iter-1}, u = scratch.  d_b[k] holds blanc(k+1) (d_b[0] = 0), d_a[k] alanc(k+1).  On return w_{iter+1} lies in
+// `old`: the caller rotates (cur, old) -> (old, cur).
+static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, int iter, double *d_a, double *d_b)
 {
     edgpu_ctx *ctx = s->ctx;
     const int64_t n = s->nalloc;
     const int nb = red_blocks(n);
-    if (int rc = hxv_dispatch(s, vin, tmp)) return rc;
-    k_lanc_a<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, vout, vin, b_in, n, ctx->d_partials);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, a_out, 0);
-    k_lanc_b<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, vin, a_out, n, ctx->d_partials);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, b_out, 1);
-    k_div<<<nb, kRedThreads, 0, ctx->stream>>>(tmp, b_out, n);
+    const double *one = ctx->d_scal + 3;
+    const double *p_bprev = d_b + (iter - 1);
+    const double *p_ncur = iter == 1 ? one : d_b + (iter - 1);
+    const double *p_nold = iter <= 2 ? one : d_b + (iter - 2);
+    int ndot = -1;
+    if (hxv_uses_star(s)) {
+        if (int rc = hxv_star_dot(s, cur, u, ctx->d_dotpart, &ndot)) return rc;
+    } else if (int rc = hxv_dispatch(s, cur, u)) return rc;
+    if (ndot >= 0) {
+        k_lanc_alpha<<<1, 256, 0, ctx->stream>>>(ctx->d_dotpart, ndot, p_ncur, d_a + (iter - 1));
+    } else {
+        k_dot<<<nb, kRedThreads, 0, ctx->stream>>>(cur, u, n, ctx->d_partials);
+        k_lanc_alpha<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, p_ncur, d_a + (iter - 1));
+    }
+    k_lanc_c<<<nb, kRedThreads, 0, ctx->stream>>>(old, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials);
+    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, d_b + iter, 1);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -190,18 +218,18 @@ extern "C" int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlan
     if (!s || !v || v->s != s) return s ? edgpu_fail(s->ctx, "edgpu_lanczos_tridiag: bad vector/sector") : 1;
     edgpu_ctx *ctx = s->ctx;
     if (nlanc < 1 || nlanc > kLancMax) return edgpu_fail(ctx, "edgpu_lanczos_tridiag: nlanc=%d out of range", nlanc);
-    double *vin = v->d, *vout, *tmp;
-    if (int rc = sector_work(s, 0, &vout)) return rc;
-    if (int rc = sector_work(s, 1, &tmp)) return rc;
+    double *cur = v->d, *old, *u;
+    if (int rc = sector_work(s, 0, &old)) return rc;
+    if (int rc = sector_work(s, 1, &u)) return rc;
     const int64_t n = s->nalloc;
-    CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
-    if (int rc = normalise(s, vin)) return rc;                 // iter==1: vin=vin/norm ; b=0   (:94-99)
+    CUDA_TRY(ctx, cudaMemsetAsync(old, 0, sizeof(double) * (size_t)n, ctx->stream));
+    if (int rc = reset_scalars(ctx)) return rc;
+    if (int rc = normalise(s, cur)) return rc;                 // iter==1: vin=vin/norm ; b=0   (:94-99)
     double *d_a = ctx->d_scal + kScalArr, *d_b = ctx->d_scal + kScalArr + kLancMax;
     // d_b[k] holds Fortran blanc(k+1): d_b[0] = 0 (b entering iteration 1)
     for (int iter = 1; iter <= nlanc; iter++) {
-        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
-        double *t = vout; vout = vin; vin = tmp; tmp = t;       // vout = vin ; vin = tmp/b
+        if (int rc = lanczos_step(s, cur, old, u, iter, d_a, d_b)) return rc;
+        double *t = cur; cur = old; old = t;                    // vout = vin ; vin = tmp/b  (unnormalised)
     }
     std::vector<double> ha(nlanc), hb(nlanc + 1);
     CUDA_TRY(ctx, cudaMemcpyAsync(ha.data(), d_a, sizeof(double) * nlanc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -242,14 +270,14 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
     double *vin = w0, *vout = w1, *tmp = w2;
     CUDA_TRY(ctx, cudaMemcpyAsync(vin, v0->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    if (int rc = reset_scalars(ctx)) return rc;
     if (int rc = normalise(s, vin)) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal + kScalB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_scal[0] == 0.0) return edgpu_fail(ctx, "lanczos_plain_iteration: norm =0!!");
     for (int iter = 1; iter <= nitermax; iter++) {
-        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
-        { double *t = vout; vout = vin; vin = tmp; tmp = t; }
+        if (int rc = lanczos_step(s, vin, vout, tmp, iter, d_a, d_b)) return rc;     // (cur, old, scratch)
+        { double *t = vin; vin = vout; vout = t; }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, d_a + (iter - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + 1, d_b + iter, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -283,13 +311,16 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
     CUDA_TRY(ctx, cudaMemcpyAsync(vin, v0->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(v0->d, 0, sizeof(double) * (size_t)n, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    if (int rc = reset_scalars(ctx)) return rc;
     if (int rc = normalise(s, vin)) return rc;
     for (int iter = 1; iter <= nlanc; iter++) {
-        if (int rc = vec_axpy(ctx, v0->d, vin, Z[iter - 1], n)) return rc;      // Z(iter,1)
+        // vin holds the unnormalised w_iter = b_iter v_iter (b_1 = 1); the kernels are deterministic, so the b of this
+        // pass are bit-identical to the blanc of pass 1
+        const double nrm = iter == 1 ? 1.0 : blanc[iter - 1];
+        if (int rc = vec_axpy(ctx, v0->d, vin, Z[iter - 1] / nrm, n)) return rc;     // Z(iter,1)
         if (iter == nlanc) break;
-        if (int rc = lanczos_step(s, vin, vout, tmp, d_b + (iter - 1), d_a + (iter - 1), d_b + iter)) return rc;
-        { double *t = vout; vout = vin; vin = tmp; tmp = t; }
+        if (int rc = lanczos_step(s, vin, vout, tmp, iter, d_a, d_b)) return rc;
+        { double *t = vin; vin = vout; vout = t; }
     }
     if (int rc = normalise(s, v0->d)) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
