@@ -923,7 +923,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
 
 template <int NORB, int NH>
 __global__ void __launch_bounds__(kNT3)
-k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
+k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t ld, int block_index, int G,
            const StarBlock *__restrict__ blocks,
            const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
            const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
@@ -932,6 +932,9 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_dot[kNT / 32];
+    __shared__ SlabMap s_M;
+    if (threadIdx.x == 0) s_M = Mpar;                                          // visible after the barrier below
+    const SlabMap &M = s_M;
     const StarBlock B = blocks[block_index];
     const int size = B.size, tid = threadIdx.x;
     const int lead = B.off & 1;                                                // copy starts one element early when the block starts odd
@@ -963,12 +966,26 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
         // ---------------- producer warp ----------------
         const int lane = tid - kNT;
         int64_t t = blockIdx.x;
+        // the row segment [colb, colb + ncopy) as pieces of the vector: one piece, or one per slab of a row shard that
+        // arrived by all-to-all (slab boundaries are multiples of 4 columns, so every piece stays 16-byte aligned)
+        auto for_segments = [&](int64_t row, auto &&fn) {                      // fn(element offset, column - colb, count)
+            if (M.n <= 1) { fn(row * ld + colb, 0, ncopy); return; }
+            const int64_t cend = colb + ncopy;
+            for (int p = 0; p < M.n; p++) {
+                const int64_t lo = colb > M.col0[p] ? colb : (int64_t)M.col0[p];
+                const int64_t he = (int64_t)M.col0[p] + M.ldc[p], hi = cend < he ? cend : he;
+                if (lo < hi) fn(M.base[p] + row * M.ldc[p] + (lo - M.col0[p]), (int)(lo - colb), (int)(hi - lo));
+            }
+        };
+        auto elem_off = [&](int64_t row, int64_t c) -> int64_t { return M.n <= 1 ? row * ld + c : slab_off(M, row, (int)c); };
         auto store_tile = [&](int64_t tt, int st) {
             if (lane == 0) {
                 const int64_t r0 = tt * G;
                 const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
-                for (int g = 0; g < gc; g++)
-                    bulk_s2g(y + (r0 + g) * ld + colb, ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb, (uint32_t)ncopy * 8u);
+                for (int g = 0; g < gc; g++) {
+                    const uint32_t src = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
+                    for_segments(r0 + g, [&](int64_t off, int rel, int cnt) { bulk_s2g(y + off, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         };
@@ -996,10 +1013,20 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
             __syncwarp();
             if (lane == 0) {
                 const uint32_t fb = bar0 + 8 * st;
-                mbar_expect_tx(fb, (uint32_t)gc * 2u * (uint32_t)ncopy * 8u);
+                // accumulate == 0 (the result overwrites y): only the first and last 16 bytes of the y segment are loaded --
+                // they may hold an element of the neighbouring block, which the store must put back unchanged
+                const uint32_t ybytes = accumulate ? (uint32_t)ncopy * 8u : (ncopy > 2 ? 32u : 16u);
+                mbar_expect_tx(fb, (uint32_t)gc * ((uint32_t)ncopy * 8u + ybytes));
                 for (int g = 0; g < gc; g++) {
-                    bulk_g2s(xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb, x + (r0 + g) * ld + colb, (uint32_t)ncopy * 8u, fb);
-                    bulk_g2s(ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb, y + (r0 + g) * ld + colb, (uint32_t)ncopy * 8u, fb);
+                    const uint32_t xd = xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb, yd = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
+                    for_segments(r0 + g, [&](int64_t off, int rel, int cnt) {
+                        bulk_g2s(xd + (uint32_t)rel * 8u, x + off, (uint32_t)cnt * 8u, fb);
+                        if (accumulate) bulk_g2s(yd + (uint32_t)rel * 8u, y + off, (uint32_t)cnt * 8u, fb);
+                    });
+                    if (!accumulate) {
+                        bulk_g2s(yd, y + elem_off(r0 + g, colb), 16u, fb);
+                        if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y + elem_off(r0 + g, colb + ncopy - 2), 16u, fb);
+                    }
                 }
             }
         }
@@ -1038,7 +1065,7 @@ k_star_up3(StarKParams P, int64_t dim_dw, int64_t ld, int block_index, int G,
                 uint32_t a0 = xs + eb, ya = ys + eb;
 #pragma unroll 2
                 for (int o = L.ty; o < O; o += NY) {
-                    const double init[1] = {lds64(ya)};
+                    const double init[1] = {accumulate ? lds64(ya) : 0.0};
                     double acc[1], es;
                     uint32_t dgo;
                     lean_element<NORB, NH, 1>(L, LT, A0, maxD, a0, 0u, i1, i2, init, acc, es, dgo);
@@ -1456,7 +1483,7 @@ static DwKernel pick_dw(int W, int NH)
     }
 }
 
-using Up3Kernel = void (*)(StarKParams, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
+using Up3Kernel = void (*)(StarKParams, SlabMap, int, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
                            const double *, const double *, const uint32_t *, const double *, const double *, double *, int, double *);
 template <int NORB>
 static Up3Kernel pick_up3(int NH)
@@ -1589,7 +1616,7 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
         int bD = 1;
         for (int a = 0; a < NORB; a++) bD = std::max(bD, U.D[B.n[a]]);
-        if (!slabs && accumulate && !force_generic && !(ctx->par.reserved[0] & 8) && B.size >= ((ctx->par.reserved[0] & 16) ? 1 : kBulkMin) && round_nh(B.nh) &&
+        if (!force_generic && !(ctx->par.reserved[0] & 8) && B.size >= ((ctx->par.reserved[0] & 16) ? 1 : kBulkMin) && round_nh(B.nh) &&
             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
             // bulk-copy pipeline: G rows per tile
             const int NH3 = round_nh(B.nh);
@@ -1604,7 +1631,7 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
                 const int64_t ntiles = (nrows + G - 1) / G;
                 const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
                 const bool d = dot_ok && slots + (int)nctas <= kDotSlots;
-                kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, nrows, ld, (int)bi, (int)G, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
+                kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, M, accumulate, nrows, ld, (int)bi, (int)G, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
                                                           s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD, d ? dot + slots : nullptr);
                 CUDA_TRY(ctx, cudaGetLastError());
                 if (d) slots += (int)nctas; else dot_ok = false;

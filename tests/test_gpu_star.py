@@ -101,7 +101,8 @@ def test_star_equals_generic_at_cfg3_size(oracle, edb):
     assert np.abs(out["star"] - out["generic"]).max() < HXV_TOL * np.abs(out["generic"]).max()
 
 
-def test_shard_entry_points_equal_full_product(oracle, edb):
+@pytest.mark.parametrize("flags", [0, 16])           # 16: the copy-engine kernels (slab-addressed, accumulate = 0) for every block size
+def test_shard_entry_points_equal_full_product(oracle, edb, flags):
     """edgpu_shard_hxv_dw on column shards + edgpu_shard_hxv_up on row shards (world=2 and 3, emulated on one GPU)
     reproduce the single-GPU product; the exchange logic itself is covered by tests/test_sharded_cpu.py (gloo)."""
     import ctypes as C
@@ -109,7 +110,7 @@ def test_shard_entry_points_equal_full_product(oracle, edb):
     import torch
     sharded = importlib.import_module("dmft-ed_b200.sharded")
     case = dict(Norb=2, Nbath=4, uloc=(2.0, 2.0), ust=0.7, jh=0.1)
-    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2)
+    p, model, ctx, rng = make(oracle, edb, case, layout=2, hxv_kernel=2, debug_flags=flags)
     s = ctx.sector(5, 4)
     du, dd = s.dim_up, s.dim_dw
     r2iu = np.zeros(du, dtype=np.uint32)
