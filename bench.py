@@ -198,7 +198,7 @@ def run_sharded(args, edb, world, rank, local):
     edb.lib().ed_finalize_solver(tmp)
     ctx.set_hamiltonian(bath, [2.0] * Norb)
     s = ctx.sector(nup, ndw)
-    sh = sharded.make_gpu_shard(edb, s, rank, world)
+    sh = sharded.make_gpu_shard(edb, s, rank, world, nchunks=args.chunks)
     plan = sh.plan
     g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
     x = sh.zeros()
@@ -244,7 +244,7 @@ def run_sharded(args, edb, world, rank, local):
                        "vector": "N(0,1) per rank", "dim": dim,
                        "l2": f"inputs exceed L2: {alg_bytes / world / 1e9:.3f} GB touched per rank and step",
                        "parallelism": f"sector vector sharded by up-spin column blocks over {world} ranks; down term local, "
-                                      "up term via 2 NCCL all-to-all transposes per H*v"},
+                                      f"up term via 2 NCCL all-to-all transposes per H*v, pipelined in {plan.nchunks} row groups"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
                          "nvlink_bytes_sent_per_rank_per_hxv": nvl,
@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "shard", "chains"],
                     help="N>1: 'shard' = one sector vector sharded by up-spin column blocks with all-to-all transposes "
                          "(strong scaling); 'chains' = independent H*v streams per rank (weak scaling)")
+    ap.add_argument("--chunks", type=int, default=4, help="row groups of the pipelined all-to-all exchange (sharded mode)")
     ap.add_argument("--layout", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
     args = ap.parse_args()

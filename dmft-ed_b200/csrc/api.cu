@@ -16,6 +16,8 @@ int csr_build(edgpu_sector *s);
 int hxv_star_launches(const edgpu_sector *s);
 int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld);
 int hxv_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate);
+int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *yp, int64_t row0, int64_t nrows, int nslab,
+                      const int64_t *col0, const int64_t *ldc, int accumulate);
 int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int nslab,
                       const int64_t *col0, const int64_t *ldc, int accumulate);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
@@ -491,6 +493,61 @@ extern "C" int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t n
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: bad row shard");
     if (nrows == 0) return 0;
     return hxv_star_up_slabs(s, (const double *)x_dev, (double *)y_dev, row0, nrows, nslab, col0, ldc, accumulate);
+}
+
+extern "C" int edgpu_shard_hxv_up_peers(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nranks, const int64_t *col0,
+                                        const int64_t *ldc, const void *const *x_shards, void *const *y_shards, int32_t accumulate)
+{
+    if (!s || !x_shards || !y_shards || !col0 || !ldc) return 1;
+    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: needs the star-product layout");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: bad row shard");
+    if (nrows == 0) return 0;
+    return hxv_star_up_peers(s, (const double *const *)x_shards, (double *const *)y_shards, row0, nrows, nranks, col0, ldc, accumulate);
+}
+
+// ---- device buffers that other processes of the node can map (CUDA IPC) -----------------------------------------
+extern "C" int edgpu_dev_alloc(edgpu_ctx *ctx, int64_t bytes, void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || bytes <= 0) return 1;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc(dev_ptr, (size_t)bytes));             // a separate allocation: IPC handles map whole allocations
+    CUDA_TRY(ctx, cudaMemsetAsync(*dev_ptr, 0, (size_t)bytes, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int edgpu_dev_free(edgpu_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return 1;
+    CUDA_TRY(ctx, cudaFree(dev_ptr));
+    return 0;
+}
+
+extern "C" int edgpu_ipc_export(edgpu_ctx *ctx, void *dev_ptr, unsigned char handle[64])
+{
+    if (!ctx || !dev_ptr || !handle) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+extern "C" int edgpu_ipc_open(edgpu_ctx *ctx, const unsigned char handle[64], void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || !handle) return 1;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int edgpu_ipc_close(edgpu_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return 1;
+    CUDA_TRY(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
 }
 
 extern "C" int edgpu_shard_perm(const edgpu_sector *s, uint32_t *r2i_up, uint32_t *r2i_dw)

@@ -656,16 +656,27 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Row shard of a multi-GPU run: after the all-to-all the rows of this rank arrive as one slab per source rank
 // ([nrows][ldc_p] each, source rank p owns columns [col0_p, col0_p + ldc_p)); the up pass reads and writes the slabs
 // in place instead of paying an unpack and a pack pass.  n == 1 (single GPU / contiguous rows) is the plain layout.
+// peer == 1 ("peer mode", one process per GPU): slab p is not a piece of a received buffer but the column shard of rank p
+// itself, [dim_dw][ldc_p] in THAT GPU's memory (CUDA IPC mapping over NVLink): xp[p] / yp[p] are its base pointers and
+// base[p] = row0 * ldc[p] selects this rank's rows.  The copy engine then reads x from, and writes the result to, the
+// owners directly -- the two all-to-all transposes of the exchange are fused into the up-pass kernel.
 struct SlabMap {
     int n, ldc0;
     unsigned magic;                 // ceil(2^32 / ldc0): column / ldc0 by multiplication
     int col0[8], ldc[8];
     long long base[8];              // element offset of slab p
+    int peer;
+    const double *xp[8];
+    double *yp[8];
 };
+__device__ __forceinline__ int slab_of(const SlabMap &M, int c)
+{
+    const int p = (int)__umulhi((unsigned)c, M.magic);
+    return p < M.n - 1 ? p : M.n - 1;
+}
 __device__ __forceinline__ int64_t slab_off(const SlabMap &M, int64_t row, int c)
 {
-    int p = (int)__umulhi((unsigned)c, M.magic);
-    p = p < M.n - 1 ? p : M.n - 1;
+    const int p = slab_of(M, c);
     return M.base[p] + row * M.ldc[p] + (c - M.col0[p]);
 }
 
@@ -968,23 +979,30 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
         int64_t t = blockIdx.x;
         // the row segment [colb, colb + ncopy) as pieces of the vector: one piece, or one per slab of a row shard that
         // arrived by all-to-all (slab boundaries are multiples of 4 columns, so every piece stays 16-byte aligned)
-        auto for_segments = [&](int64_t row, auto &&fn) {                      // fn(element offset, column - colb, count)
-            if (M.n <= 1) { fn(row * ld + colb, 0, ncopy); return; }
+        auto for_segments = [&](int64_t row, auto &&fn) {                      // fn(x pointer, y pointer, column - colb, count)
+            if (M.n <= 1 && !M.peer) { fn(x + row * ld + colb, y + row * ld + colb, 0, ncopy); return; }
             const int64_t cend = colb + ncopy;
             for (int p = 0; p < M.n; p++) {
                 const int64_t lo = colb > M.col0[p] ? colb : (int64_t)M.col0[p];
                 const int64_t he = (int64_t)M.col0[p] + M.ldc[p], hi = cend < he ? cend : he;
-                if (lo < hi) fn(M.base[p] + row * M.ldc[p] + (lo - M.col0[p]), (int)(lo - colb), (int)(hi - lo));
+                if (lo < hi) {
+                    const int64_t off = M.base[p] + row * M.ldc[p] + (lo - M.col0[p]);
+                    fn((M.peer ? M.xp[p] : x) + off, (M.peer ? M.yp[p] : y) + off, (int)(lo - colb), (int)(hi - lo));
+                }
             }
         };
-        auto elem_off = [&](int64_t row, int64_t c) -> int64_t { return M.n <= 1 ? row * ld + c : slab_off(M, row, (int)c); };
+        auto y_elem = [&](int64_t row, int64_t c) -> double * {
+            if (M.n <= 1 && !M.peer) return y + row * ld + c;
+            const int p = slab_of(M, (int)c);
+            return (M.peer ? M.yp[p] : y) + M.base[p] + row * M.ldc[p] + (c - M.col0[p]);
+        };
         auto store_tile = [&](int64_t tt, int st) {
             if (lane == 0) {
                 const int64_t r0 = tt * G;
                 const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
                 for (int g = 0; g < gc; g++) {
                     const uint32_t src = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
-                    for_segments(r0 + g, [&](int64_t off, int rel, int cnt) { bulk_s2g(y + off, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
+                    for_segments(r0 + g, [&](const double *, double *yd, int rel, int cnt) { bulk_s2g(yd, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -1019,13 +1037,13 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
                 mbar_expect_tx(fb, (uint32_t)gc * ((uint32_t)ncopy * 8u + ybytes));
                 for (int g = 0; g < gc; g++) {
                     const uint32_t xd = xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb, yd = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
-                    for_segments(r0 + g, [&](int64_t off, int rel, int cnt) {
-                        bulk_g2s(xd + (uint32_t)rel * 8u, x + off, (uint32_t)cnt * 8u, fb);
-                        if (accumulate) bulk_g2s(yd + (uint32_t)rel * 8u, y + off, (uint32_t)cnt * 8u, fb);
+                    for_segments(r0 + g, [&](const double *xs, double *ys, int rel, int cnt) {
+                        bulk_g2s(xd + (uint32_t)rel * 8u, xs, (uint32_t)cnt * 8u, fb);
+                        if (accumulate) bulk_g2s(yd + (uint32_t)rel * 8u, ys, (uint32_t)cnt * 8u, fb);
                     });
                     if (!accumulate) {
-                        bulk_g2s(yd, y + elem_off(r0 + g, colb), 16u, fb);
-                        if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y + elem_off(r0 + g, colb + ncopy - 2), 16u, fb);
+                        bulk_g2s(yd, y_elem(r0 + g, colb), 16u, fb);
+                        if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y_elem(r0 + g, colb + ncopy - 2), 16u, fb);
                     }
                 }
             }
@@ -1362,9 +1380,11 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
             const uint32_t *__restrict__ cfg_up, const uint32_t *__restrict__ cfg_dw,
             const double *__restrict__ e_up, const double *__restrict__ e_dw, const double *__restrict__ xtab,
             const uint32_t *__restrict__ hop_up, const uint8_t *__restrict__ nhop_up, const double *__restrict__ amp_up,
-            const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dot_out)
+            const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dot_out, SlabMap Mpar, int slabbed)
 {
     __shared__ double s_amp[256], s_x[32 * 32], s_red[8];
+    __shared__ SlabMap M;
+    if (threadIdx.x == 0) M = Mpar;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_amp[i] = amp_up[i];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_x[i] = xtab[i];
     __syncthreads();
@@ -1375,16 +1395,25 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
         const int64_t r = idx / nfr;
         const int q = (int)(idx - r * nfr);
         const int64_t ru = fringe[q];
-        const double *xr = x + r * ld;
-        double acc = (e_up[ru] + e_dw[r] + s_x[(cfg_dw[r] & impmask) * 32u + (cfg_up[ru] & impmask)]) * xr[ru];
-        if (accumulate) acc += y[r * ld + ru];
+        // element (r, c) of the row shard: plain [nrows][ld] tile, or slab / peer addressing (see SlabMap)
+        auto xat = [&](int64_t c) -> const double * {
+            if (!slabbed) return x + r * ld + c;
+            const int p = slab_of(M, (int)c);
+            return (M.peer ? M.xp[p] : x) + M.base[p] + r * M.ldc[p] + (c - M.col0[p]);
+        };
+        const double xo = *xat(ru);
+        double acc = (e_up[ru] + e_dw[r] + s_x[(cfg_dw[r] & impmask) * 32u + (cfg_up[ru] & impmask)]) * xo;
+        double *yo;
+        if (!slabbed) yo = y + r * ld + ru;
+        else { const int p = slab_of(M, (int)ru); yo = (M.peer ? M.yp[p] : y) + M.base[p] + r * M.ldc[p] + (ru - M.col0[p]); }
+        if (accumulate) acc += *yo;
         const int nu = nhop_up[ru];
         for (int j = 0; j < nu; j++) {
             const uint32_t h = hop_up[(int64_t)j * dim_up + ru];
-            acc += s_amp[h & 255u] * xr[h >> 8];
+            acc += s_amp[h & 255u] * *xat(h >> 8);
         }
-        y[r * ld + ru] = acc;
-        dsum = fma(xr[ru], acc, dsum);
+        *yo = acc;
+        dsum = fma(xo, acc, dsum);
     }
     if (dot_out) {
         for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
@@ -1598,14 +1627,14 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
     memset(&M, 0, sizeof(M));
     if (slabs) M = *slabs; else { M.n = 1; M.ldc0 = (int)ld; M.magic = 0; M.ldc[0] = (int)ld; }
     const int64_t npairs = (nrows + 1) / 2;
-    const bool fringe = !slabs && !(ctx->par.reserved[0] & (4 | 8 | 16)) && U.nfringe > 0;
+    const bool fringe = !(ctx->par.reserved[0] & (4 | 8 | 16)) && U.nfringe > 0;
     if (fringe) {
         const int64_t total = nrows * U.nfringe;
         const unsigned nb = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
         const bool d = dot_ok && slots + (int)nb <= kDotSlots;
         k_fringe_up<<<nb, 256, 0, ctx->stream>>>(U.nfringe, U.d_fringe, nrows, ld, s->dim_up, NORB, accumulate, s->up->cfg, s->dw->cfg + row0,
                                                  s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y,
-                                                 d ? dot + slots : nullptr);
+                                                 d ? dot + slots : nullptr, M, slabs ? 1 : 0);
         CUDA_TRY(ctx, cudaGetLastError());
         if (d) slots += (int)nb; else dot_ok = false;
     }
@@ -1616,7 +1645,8 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         RP = std::max<int64_t>(1, std::min<int64_t>(RP, npairs / (2 * (int64_t)ctx->sm_count)));
         int bD = 1;
         for (int a = 0; a < NORB; a++) bD = std::max(bD, U.D[B.n[a]]);
-        if (!force_generic && !(ctx->par.reserved[0] & 8) && B.size >= ((ctx->par.reserved[0] & 16) ? 1 : kBulkMin) && round_nh(B.nh) &&
+        if (!force_generic && !(ctx->par.reserved[0] & 8) && round_nh(B.nh) &&
+            (B.size >= ((ctx->par.reserved[0] & 16) ? 1 : kBulkMin) || (slabs && slabs->peer)) &&
             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
             // bulk-copy pipeline: G rows per tile
             const int NH3 = round_nh(B.nh);
@@ -1638,6 +1668,8 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
                 continue;
             }
         }
+        if (slabs && slabs->peer)
+            return edgpu_fail(ctx, "star up pass (peer mode): no copy-engine kernel for the block of %d configurations", B.size);
         const int NH = (RP == 1 && !force_generic) ? round_nh(B.nh) : 0;
         const size_t tab = NH ? lean_tabs_bytes(NORB, bD, NH) : tabs_bytes(NORB, bD, U.H);
         const size_t smem1 = sizeof(double) * ((size_t)2 * B.size * RP + (size_t)16 * RP) + tab;
@@ -1695,6 +1727,36 @@ int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0,
     case 1: return launch_star_up<1>(s, x, y, row0, nrows, s->ld, accumulate, &M);
     case 2: return launch_star_up<2>(s, x, y, row0, nrows, s->ld, accumulate, &M);
     case 3: return launch_star_up<3>(s, x, y, row0, nrows, s->ld, accumulate, &M);
+    default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
+    }
+}
+
+// Up pass in peer mode: this rank's rows [row0, row0+nrows) of ALL columns, where the columns [col0[p], col0[p]+ldc[p]) live in
+// the column shard of rank p ([dim_dw][ldc[p]], base pointers xp[p] / yp[p] valid on this device, e.g. CUDA IPC mappings).
+int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *yp, int64_t row0, int64_t nrows, int nslab,
+                      const int64_t *col0, const int64_t *ldc, int accumulate)
+{
+    if (!s->up->star || !s->dw->star) return edgpu_fail(s->ctx, "hxv_star: sector is not in the star-product layout");
+    if (nslab < 1 || nslab > 8) return edgpu_fail(s->ctx, "hxv_star_up_peers: 1..8 ranks supported (got %d)", nslab);
+    SlabMap M;
+    memset(&M, 0, sizeof(M));
+    M.n = nslab;
+    M.peer = 1;
+    M.ldc0 = (int)ldc[0];
+    if (M.ldc0 <= 1) return edgpu_fail(s->ctx, "hxv_star_up_peers: column shards must be wider than 1");
+    M.magic = (unsigned)(((1ull << 32) + (uint64_t)M.ldc0 - 1) / (uint64_t)M.ldc0);
+    for (int p = 0; p < nslab; p++) {
+        if (p < nslab - 1 && ldc[p] != ldc[0]) return edgpu_fail(s->ctx, "hxv_star_up_peers: all but the last shard must have equal width");
+        if (col0[p] != (int64_t)p * ldc[0] || ldc[p] % 4) return edgpu_fail(s->ctx, "hxv_star_up_peers: shards must tile the columns in strips of 4");
+        if ((reinterpret_cast<uintptr_t>(xp[p]) | reinterpret_cast<uintptr_t>(yp[p])) & 15)
+            return edgpu_fail(s->ctx, "hxv_star_up_peers: shard pointers must be 16-byte aligned");
+        M.col0[p] = (int)col0[p]; M.ldc[p] = (int)ldc[p]; M.base[p] = (long long)row0 * ldc[p];
+        M.xp[p] = xp[p]; M.yp[p] = yp[p];
+    }
+    switch (s->ctx->ham.norb) {
+    case 1: return launch_star_up<1>(s, nullptr, nullptr, row0, nrows, s->ld, accumulate, &M);
+    case 2: return launch_star_up<2>(s, nullptr, nullptr, row0, nrows, s->ld, accumulate, &M);
+    case 3: return launch_star_up<3>(s, nullptr, nullptr, row0, nrows, s->ld, accumulate, &M);
     default: return edgpu_fail(s->ctx, "star kernels: Norb=%d unsupported", s->ctx->ham.norb);
     }
 }

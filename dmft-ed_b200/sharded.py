@@ -21,11 +21,16 @@ import torch.distributed as dist
 @dataclass
 class ShardPlan:
     """Partition of the tile.  Columns are dealt in strips of 4 (32-byte aligned rows of the column shard); rows and
-    strips follow the reference's rule Q = N/P with the remainder on the last rank (ED_HAMILTONIAN.f90:56-62)."""
+    strips follow the reference's rule Q = N/P with the remainder on the last rank (ED_HAMILTONIAN.f90:56-62).
+
+    nchunks > 1 pipelines the exchange: the rows are cut into `nchunks` groups and every group is dealt over the ranks
+    by the same rule, so that the rows of one group are contiguous on the sender (one all_to_all_single per group,
+    nothing packed) and the up-spin term of group j overlaps the transposes of groups j+1 (forth) and j-1 (back)."""
     dim_up: int
     dim_dw: int
     ld: int            # leading dimension of a full row (dim_up rounded up to 4)
     world: int
+    nchunks: int = 1
 
     def __post_init__(self):
         nstrips = (self.dim_up + 3) // 4
@@ -39,16 +44,27 @@ class ShardPlan:
             self.col0.append(c0)
             self.ldc.append(ns * 4)
             self.ncols.append(max(0, min(self.dim_up, c0 + ns * 4) - c0))
-        qr = self.dim_dw // self.world
-        self.row0 = [p * qr for p in range(self.world)]
-        self.nrows = [qr if p < self.world - 1 else self.dim_dw - p * qr for p in range(self.world)]
+        K = max(1, min(self.nchunks, max(1, self.dim_dw // max(1, self.world))))
+        self.nchunks = K
+        gq = self.dim_dw // K
+        self.chunks = []                         # (first row of the group, rows in the group, row0 per rank, nrows per rank)
+        for j in range(K):
+            g0 = j * gq
+            gl = gq if j < K - 1 else self.dim_dw - g0
+            qr = gl // self.world
+            r0 = [g0 + p * qr for p in range(self.world)]
+            nr = [qr if p < self.world - 1 else gl - p * qr for p in range(self.world)]
+            self.chunks.append((g0, gl, r0, nr))
+        self.row0 = list(self.chunks[0][2])      # (meaningful as "the" row range of a rank only when nchunks == 1)
+        self.nrows = [sum(c[3][p] for c in self.chunks) for p in range(self.world)]
 
 
 class ShardedHxv:
     """y_loc = (H x)_loc on the column shard of this rank.
 
-    ops.dw(x_cols, y_cols)               y_cols = H_dw x_cols           on [dim_dw, ldc_me]
-    ops.up(row0, nrows, x_rows, y_rows)  y_rows = (D + H_up) x_rows     on [nrows_me, ld]
+    ops.dw(x_cols, y_cols)                                y_cols = H_dw x_cols           on [dim_dw, ldc_me]
+    ops.up(row0, nrows, x_rows, y_rows)                   y_rows = (D + H_up) x_rows     on [nrows, ld]
+    ops.up_slabs(row0, nrows, col0, ldc, x_slabs, y_slabs)   the same on the slabs an all-to-all delivers (optional)
     """
 
     def __init__(self, plan: ShardPlan, rank: int, ops, group=None, device="cpu"):
@@ -58,14 +74,10 @@ class ShardedHxv:
         self.ldc = P.ldc[me]
         self.nrows = P.nrows[me]
         f64 = torch.float64
-        # exchange buffers (reused by every product)
-        self.recv_cols = torch.zeros(sum(self.nrows * P.ldc[p] for p in range(P.world)), dtype=f64, device=device)
-        self.x_rows = torch.zeros(self.nrows, P.ld, dtype=f64, device=device)
-        self.y_rows = torch.zeros(self.nrows, P.ld, dtype=f64, device=device)
-        self.send_rows = torch.zeros(sum(self.nrows * P.ldc[p] for p in range(P.world)), dtype=f64, device=device)
+        # exchange buffers (reused by every product): per row group, the slabs [nrows_j][ldc_p] of all source ranks p
+        self.recv = [torch.zeros(c[3][me] * P.ld, dtype=f64, device=device) for c in P.chunks]
+        self.send = [torch.zeros(c[3][me] * P.ld, dtype=f64, device=device) for c in P.chunks]
         self.tmp_cols = torch.zeros(P.dim_dw, self.ldc, dtype=f64, device=device)
-        self.in_split = [P.nrows[p] * self.ldc for p in range(P.world)]          # my columns, rows of rank p
-        self.out_split = [self.nrows * P.ldc[p] for p in range(P.world)]         # my rows, columns of rank p
         self.bytes_alltoall = 0
 
     def zeros(self):
@@ -79,38 +91,51 @@ class ShardedHxv:
         return dist.all_to_all_single(out, inp, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group,
                                       async_op=async_op)
 
-    def apply(self, x_cols: torch.Tensor, y_cols: torch.Tensor):
-        P = self.plan
+    def _up_chunk(self, j):
+        P, me = self.plan, self.rank
+        _, _, r0, nr = P.chunks[j]
+        if nr[me] == 0:
+            return
         if hasattr(self.ops, "up_slabs"):
-            # transpose #1 runs on NCCL's stream WHILE the down-spin term (local: down hops keep the column) runs on
-            # the compute stream; the up-spin term then works directly on the received slabs and writes the slabs
-            # that transpose #2 sends back -- no pack/unpack passes.
-            work = self._all_to_all(self.recv_cols, x_cols.reshape(-1), self.out_split, self.in_split, async_op=True)
-            self.ops.dw(x_cols, y_cols)
-            if work is not None:
-                work.wait()
-            self.ops.up_slabs(P.row0[self.rank], self.nrows, P.col0, P.ldc, self.recv_cols, self.send_rows)
-            self._all_to_all(self.tmp_cols.reshape(-1), self.send_rows, self.in_split, self.out_split)
-            y_cols += self.tmp_cols
-            return y_cols
-        # 1. down-spin term on the column shard (local: down hops keep the column)
+            # the up-spin term works directly on the received slabs and writes the slabs that go back: no pack/unpack
+            self.ops.up_slabs(r0[me], nr[me], P.col0, P.ldc, self.recv[j], self.send[j])
+            return
+        x_rows = torch.zeros(nr[me], P.ld, dtype=torch.float64, device=self.device)
+        y_rows = torch.zeros_like(x_rows)
+        off = 0
+        for p in range(P.world):
+            n = nr[me] * P.ldc[p]
+            x_rows[:, P.col0[p]:P.col0[p] + P.ldc[p]] = self.recv[j][off:off + n].view(nr[me], P.ldc[p])
+            off += n
+        self.ops.up(r0[me], nr[me], x_rows, y_rows)
+        off = 0
+        for p in range(P.world):
+            n = nr[me] * P.ldc[p]
+            self.send[j][off:off + n].view(nr[me], P.ldc[p]).copy_(y_rows[:, P.col0[p]:P.col0[p] + P.ldc[p]])
+            off += n
+
+    def apply(self, x_cols: torch.Tensor, y_cols: torch.Tensor):
+        P, me = self.plan, self.rank
+        # transpose #1 of every row group is posted first and runs on the collective stream WHILE the down-spin term
+        # (local: down hops keep the column) runs on the compute stream
+        splits, works1 = [], []
+        for j, (g0, gl, r0, nr) in enumerate(P.chunks):
+            in_split = [nr[p] * self.ldc for p in range(P.world)]            # my columns, rows of rank p in group j
+            out_split = [nr[me] * P.ldc[p] for p in range(P.world)]          # my rows of group j, columns of rank p
+            splits.append((in_split, out_split))
+            works1.append(self._all_to_all(self.recv[j], x_cols[g0:g0 + gl].reshape(-1), out_split, in_split, async_op=True))
         self.ops.dw(x_cols, y_cols)
-        # 2. transpose #1: slab of rows [row0[p], row0[p]+nrows[p]) of my columns -> rank p (slabs are contiguous)
-        self._all_to_all(self.recv_cols, x_cols.reshape(-1), self.out_split, self.in_split)
-        off = 0
-        for p in range(P.world):
-            n = self.nrows * P.ldc[p]
-            self.x_rows[:, P.col0[p]:P.col0[p] + P.ldc[p]] = self.recv_cols[off:off + n].view(self.nrows, P.ldc[p])
-            off += n
-        # 3. diagonal + up-spin term on whole rows
-        self.ops.up(P.row0[self.rank], self.nrows, self.x_rows, self.y_rows)
-        # 4. transpose #2 back to column shards and accumulate
-        off = 0
-        for p in range(P.world):
-            n = self.nrows * P.ldc[p]
-            self.send_rows[off:off + n].view(self.nrows, P.ldc[p]).copy_(self.y_rows[:, P.col0[p]:P.col0[p] + P.ldc[p]])
-            off += n
-        self._all_to_all(self.tmp_cols.reshape(-1), self.send_rows, self.in_split, self.out_split)
+        # diagonal + up-spin term group by group; transpose #2 of group j overlaps the kernels of group j+1
+        works2 = []
+        for j, (g0, gl, r0, nr) in enumerate(P.chunks):
+            if works1[j] is not None:
+                works1[j].wait()
+            self._up_chunk(j)
+            in_split, out_split = splits[j]
+            works2.append(self._all_to_all(self.tmp_cols[g0:g0 + gl].reshape(-1), self.send[j], in_split, out_split, async_op=True))
+        for w in works2:
+            if w is not None:
+                w.wait()
         y_cols += self.tmp_cols
         return y_cols
 
@@ -163,12 +188,108 @@ class GpuOps:
         self.s.ctx.check(self.edb.lib().edgpu_shard_hxv_up_slabs(self.s.h, row0, nrows, n, c0, lc, x_slabs.data_ptr(), y_slabs.data_ptr(), 0))
 
 
-def make_gpu_shard(edb, sector, rank, world, group=None):
+def make_gpu_shard(edb, sector, rank, world, group=None, nchunks=1):
     """ShardedHxv over the CUDA library for `sector` (star-product layout) on the current device."""
     import ctypes as C
     ld = C.c_int64()
     sector.ctx.check(edb.lib().edgpu_shard_ld(sector.h, C.byref(ld)))
-    plan = ShardPlan(sector.dim_up, sector.dim_dw, ld.value, world)
+    plan = ShardPlan(sector.dim_up, sector.dim_dw, ld.value, world, nchunks)
     ops = GpuOps(edb, sector)
     ops.ncols_valid = plan.ncols[rank]
     return ShardedHxv(plan, rank, ops, group=group, device=torch.device("cuda", torch.cuda.current_device()))
+
+
+class _DevBuf:
+    """A cudaMalloc'ed buffer of the CUDA library seen as a torch tensor (__cuda_array_interface__), mappable by the other
+    processes of the node through its CUDA IPC handle."""
+
+    def __init__(self, edb, ctx, rows, cols):
+        import ctypes as C
+        self.edb, self.ctx, self.shape = edb, ctx, (rows, cols)
+        p = C.c_void_p()
+        ctx.check(edb.lib().edgpu_dev_alloc(ctx.h, max(16, rows * cols * 8), C.byref(p)))
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f8", "data": (self.ptr, False), "version": 3,
+                                         "strides": None}
+        self.t = torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def handle(self):
+        import ctypes as C
+        h = C.create_string_buffer(64)
+        self.ctx.check(self.edb.lib().edgpu_ipc_export(self.ctx.h, self.ptr, h))
+        return h.raw
+
+
+class PeerShardedHxv:
+    """Sharded H*v with the exchange FUSED into the up-pass kernel (one process per GPU, NVLink/NVSwitch peer memory).
+
+    Every rank keeps its column shards (the Lanczos vectors `vec(i)` and one scratch shard) in buffers that all ranks of
+    the node map through CUDA IPC.  Per product:
+        y_i   = H_dw x_i                         local (tensor-map down kernel on the column shard)
+        barrier                                  (1-element NCCL all-reduce on the compute stream)
+        tmp_p[my rows] = (D + H_up) x[my rows]   copy-engine up kernel: bulk loads of the x row segments straight from the
+                                                 owners' shards, bulk stores of the result into the owners' scratch shards
+        barrier
+        y_i  += tmp                              local
+    No transpose buffers, no NCCL data traffic: NVLink carries (P-1)/P * Dim/P * 8 B in and out per rank and product,
+    overlapped with the gathers tile by tile by the kernel's own pipeline.  Replaces the full-vector MPI_Allgatherv of
+    directMatVec_MPI_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:163-166)."""
+
+    def __init__(self, edb, sector, rank, world, nvec=2, group=None):
+        import ctypes as C
+        self.edb, self.s, self.rank, self.world, self.group = edb, sector, rank, world, group
+        ld = C.c_int64()
+        sector.ctx.check(edb.lib().edgpu_shard_ld(sector.h, C.byref(ld)))
+        self.plan = P = ShardPlan(sector.dim_up, sector.dim_dw, ld.value, world)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.ldc = P.ldc[rank]
+        self.bufs = [_DevBuf(edb, sector.ctx, P.dim_dw, self.ldc) for _ in range(nvec + 1)]      # vectors + scratch (last)
+        handles = [b.handle() for b in self.bufs]
+        allh = [None] * world
+        if world > 1:
+            dist.all_gather_object(allh, handles, group=group)
+        else:
+            allh[0] = handles
+        # ptrs[i][p] = address of buffer i of rank p in THIS process
+        self.ptrs = []
+        for i in range(nvec + 1):
+            row = []
+            for p in range(world):
+                if p == rank:
+                    row.append(self.bufs[i].ptr)
+                else:
+                    q = C.c_void_p()
+                    sector.ctx.check(edb.lib().edgpu_ipc_open(sector.ctx.h, allh[p][i], C.byref(q)))
+                    row.append(q.value)
+            self.ptrs.append(row)
+        self._flag = torch.zeros(1, device=self.device)
+        self._col0 = (C.c_int64 * world)(*P.col0)
+        self._ldc = (C.c_int64 * world)(*P.ldc)
+        self._parr = [(C.c_void_p * world)(*row) for row in self.ptrs]
+        self.bytes_nvlink = 0
+
+    def vec(self, i):
+        return self.bufs[i].t
+
+    def barrier(self):
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def apply(self, ix, iy):
+        """vec(iy) = H vec(ix) on the column shards."""
+        P, me, L, s = self.plan, self.rank, self.edb.lib(), self.s
+        x, y, tmp = self.bufs[ix].t, self.bufs[iy].t, self.bufs[-1].t
+        s.ctx.check(L.edgpu_shard_hxv_dw(s.h, P.ncols[me], self.ldc, x.data_ptr(), y.data_ptr()))
+        self.barrier()                       # every rank's x is final, every rank is done with its scratch shard
+        s.ctx.check(L.edgpu_shard_hxv_up_peers(s.h, P.row0[me], P.nrows[me], self.world, self._col0, self._ldc,
+                                               self._parr[ix], self._parr[-1], 0))
+        self.barrier()                       # all rows of my scratch shard have arrived
+        y += tmp
+        self.bytes_nvlink += 8 * P.nrows[me] * (P.ld - self.ldc)
+        return y
+
+    def dot(self, a, b):
+        v = torch.dot(a.reshape(-1), b.reshape(-1)).reshape(1)
+        if self.world > 1:
+            dist.all_reduce(v, group=self.group)
+        return v

@@ -131,6 +131,20 @@ int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, const void 
  * unpack/pack passes around the up-spin term. */
 int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nslab, const int64_t *col0,
                              const int64_t *ldc, const void *x_dev, void *y_dev, int32_t accumulate);
+/* Peer mode of the sharded product (one process per GPU, NVLink/NVSwitch): the up-spin term of rows [row0,row0+nrows) reads
+ * x from, and writes its result to, the column shards of ALL ranks directly (x_shards[p] / y_shards[p]: base pointers of rank
+ * p's [DimDw][ldc[p]] shard, valid on this device -- own memory for p == this rank, CUDA IPC mappings otherwise).  The two
+ * MPI exchanges of directMatVec_MPI_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:163-166) are thereby fused into the kernel.
+ * accumulate = 0: y = (D + H_up) x ; 1: y += ... .  The caller orders the ranks (a barrier before and after). */
+int edgpu_shard_hxv_up_peers(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nranks, const int64_t *col0,
+                             const int64_t *ldc, const void *const *x_shards, void *const *y_shards, int32_t accumulate);
+/* Device buffers for peer mode: separate cudaMalloc allocations (zero-filled) whose CUDA IPC handle (64 bytes) another
+ * process on the node opens with edgpu_ipc_open (peer access is enabled lazily). */
+int edgpu_dev_alloc(edgpu_ctx *ctx, int64_t bytes, void **dev_ptr);
+int edgpu_dev_free(edgpu_ctx *ctx, void *dev_ptr);
+int edgpu_ipc_export(edgpu_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+int edgpu_ipc_open(edgpu_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int edgpu_ipc_close(edgpu_ctx *ctx, void *dev_ptr);
 /* ref2int_up[DimUp], ref2int_dw[DimDw]: reference (colex) rank -> device index (host arrays, uint32) */
 int edgpu_shard_perm(const edgpu_sector *s, uint32_t *ref2int_up, uint32_t *ref2int_dw);
 

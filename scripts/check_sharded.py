@@ -26,7 +26,7 @@ edb.lib().ed_init_solver(C.byref(inp), local, None, bath.ctypes.data_as(edb.dp),
 edb.lib().ed_finalize_solver(tmp)
 ctx.set_hamiltonian(bath, [2.0] * Norb, ust=0.5 if Norb > 1 else 0.0, jh=0.1 if Norb > 1 else 0.0)
 s = ctx.sector(nup, ndw)
-sh = sharded.make_gpu_shard(edb, s, rank, world)
+sh = sharded.make_gpu_shard(edb, s, rank, world, nchunks=int(os.environ.get('CHUNKS', '3')))
 plan = sh.plan
 # full product on every rank (reference for the check)
 x, y = s.vec().fill_normal(20240607), s.vec()

@@ -158,4 +158,18 @@ def test_shard_entry_points_equal_full_product(oracle, edb, flags):
                 assert np.abs(blk - ref_blk).max() <= 1e-13 * max(1.0, np.abs(ref_blk).max())   # other kernels, other summation order
                 off += n
         assert np.abs(Y - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
+        # peer mode: the up-spin term reads x from, and writes into, the column shards of all "ranks" directly
+        xs = [torch.tensor(np.ascontiguousarray(Xint[:, plan.col0[q]:plan.col0[q] + plan.ldc[q]]), device=dev) for q in range(world)]
+        ts = [torch.full_like(t, 7.0) for t in xs]                  # accumulate = 0 must overwrite every element
+        ys = [torch.zeros_like(t) for t in xs]
+        xp = (C.c_void_p * world)(*[t.data_ptr() for t in xs])
+        tp = (C.c_void_p * world)(*[t.data_ptr() for t in ts])
+        c0 = (C.c_int64 * world)(*plan.col0)
+        lc = (C.c_int64 * world)(*plan.ldc)
+        for r in range(world):
+            ctx.check(edb.lib().edgpu_shard_hxv_dw(s.h, plan.ncols[r], plan.ldc[r], xs[r].data_ptr(), ys[r].data_ptr()))
+            ctx.check(edb.lib().edgpu_shard_hxv_up_peers(s.h, plan.row0[r], plan.nrows[r], world, c0, lc, xp, tp, 0))
+        ctx.sync()
+        Yp = np.concatenate([(ys[q] + ts[q]).cpu().numpy() for q in range(world)], axis=1)
+        assert np.abs(Yp - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
     x.free(); y.free(); s.free(); ctx.close()

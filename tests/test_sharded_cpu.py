@@ -38,7 +38,7 @@ def free_port():
     return p
 
 
-def worker(rank, world, port, dim_up, dim_dw, q):
+def worker(rank, world, port, dim_up, dim_dw, q, nchunks=1):
     sys.path.insert(0, ROOT)
     sharded = importlib.import_module("dmft-ed_b200.sharded")
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -52,7 +52,7 @@ def worker(rank, world, port, dim_up, dim_dw, q):
     D = torch.randn(dim_dw, dim_up, dtype=torch.float64, generator=g)
     X = torch.randn(dim_dw, dim_up, dtype=torch.float64, generator=g)
     ld = (dim_up + 3) // 4 * 4
-    plan = sharded.ShardPlan(dim_up, dim_dw, ld, world)
+    plan = sharded.ShardPlan(dim_up, dim_dw, ld, world, nchunks)
     ops = DenseOps(Hdw, Hup, D, plan.col0[rank], plan.ncols[rank])
     sh = sharded.ShardedHxv(plan, rank, ops)
     x_loc = sh.zeros()
@@ -69,12 +69,12 @@ def worker(rank, world, port, dim_up, dim_dw, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim_up,dim_dw", [(10, 10), (35, 21), (126, 5), (7, 64)])
-def test_sharded_exchange_world2(dim_up, dim_dw):
+@pytest.mark.parametrize("dim_up,dim_dw,nchunks", [(10, 10, 1), (35, 21, 1), (126, 5, 1), (7, 64, 1), (35, 21, 3), (7, 64, 4), (126, 5, 4)])
+def test_sharded_exchange_world2(dim_up, dim_dw, nchunks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, dim_up, dim_dw, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, dim_up, dim_dw, q, nchunks)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -96,3 +96,11 @@ def test_shard_plan_follows_reference_split():
     assert p.nrows[:7] == [12870 // 8] * 7 and p.nrows[7] == 12870 // 8 + 12870 % 8      # ED_HAMILTONIAN.f90:56-62
     assert all(c % 4 == 0 for c in p.col0) and all(l % 4 == 0 for l in p.ldc)
     assert p.col0[-1] + p.ldc[-1] == p.ld
+    # pipelined exchange: every row group is dealt by the same rule and the groups tile the rows
+    p4 = sharded.ShardPlan(12870, 12870, 12872, 8, 4)
+    assert sum(p4.nrows) == 12870 and len(p4.chunks) == 4
+    nxt = 0
+    for g0, gl, r0, nr in p4.chunks:
+        assert g0 == nxt and sum(nr) == gl and r0 == [g0 + i * (gl // 8) for i in range(8)]
+        nxt = g0 + gl
+    assert nxt == 12870
