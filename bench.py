@@ -198,12 +198,24 @@ def run_sharded(args, edb, world, rank, local):
     edb.lib().ed_finalize_solver(tmp)
     ctx.set_hamiltonian(bath, [2.0] * Norb)
     s = ctx.sector(nup, ndw)
-    sh = sharded.make_gpu_shard(edb, s, rank, world, nchunks=args.chunks)
-    plan = sh.plan
     g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
-    x = sh.zeros()
-    x[:, :plan.ncols[rank]] = torch.randn(plan.dim_dw, plan.ncols[rank], dtype=torch.float64, device="cuda", generator=g)
-    y = sh.zeros()
+    if args.exchange == "auto":
+        args.exchange = "peer" if world <= 2 else "nccl"
+    if args.exchange == "peer":
+        sh = sharded.PeerShardedHxv(edb, s, rank, world)
+        plan = sh.plan
+        sh.vec(0)[:, :plan.ncols[rank]] = torch.randn(plan.dim_dw, plan.ncols[rank], dtype=torch.float64, device="cuda", generator=g)
+        apply = lambda: sh.apply(0, 1)
+        how = ("up term by a copy-engine kernel that reads x from and writes into the owners' shards over NVLink "
+               "(CUDA IPC peer memory), 2 one-element all-reduce barriers per H*v")
+    else:
+        sh = sharded.make_gpu_shard(edb, s, rank, world, nchunks=args.chunks)
+        plan = sh.plan
+        x = sh.zeros()
+        x[:, :plan.ncols[rank]] = torch.randn(plan.dim_dw, plan.ncols[rank], dtype=torch.float64, device="cuda", generator=g)
+        y = sh.zeros()
+        apply = lambda: sh.apply(x, y)
+        how = f"up term via 2 NCCL all-to-all transposes per H*v, pipelined in {plan.nchunks} row groups"
 
     def barrier():
         torch.cuda.synchronize()
@@ -211,17 +223,17 @@ def run_sharded(args, edb, world, rank, local):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        sh.apply(x, y)
+        apply()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sh.bytes_alltoall = 0
+    sh.bytes_alltoall = sh.bytes_nvlink = 0
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        sh.apply(x, y)
+        apply()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -234,7 +246,7 @@ def run_sharded(args, edb, world, rank, local):
     alg_bytes = 2.0 * dim * 8.0
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    nvl = sh.bytes_alltoall / args.steps
+    nvl = (sh.bytes_nvlink if args.exchange == "peer" else sh.bytes_alltoall) / args.steps
     if rank == 0:
         line = {
             "metric": "hxv_matvecs_per_s", "value": 1e3 / ms_step, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
@@ -243,8 +255,7 @@ def run_sharded(args, edb, world, rank, local):
             "config": {"workload": f"{args.workload}: {desc}", "bath": "init_dmft_bath noise=0 hwband=2", "uloc": 2.0,
                        "vector": "N(0,1) per rank", "dim": dim,
                        "l2": f"inputs exceed L2: {alg_bytes / world / 1e9:.3f} GB touched per rank and step",
-                       "parallelism": f"sector vector sharded by up-spin column blocks over {world} ranks; down term local, "
-                                      f"up term via 2 NCCL all-to-all transposes per H*v, pipelined in {plan.nchunks} row groups"},
+                       "parallelism": f"sector vector sharded by up-spin column blocks over {world} ranks; down term local, " + how},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
                          "nvlink_bytes_sent_per_rank_per_hxv": nvl,
@@ -275,7 +286,10 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "shard", "chains"],
                     help="N>1: 'shard' = one sector vector sharded by up-spin column blocks with all-to-all transposes "
                          "(strong scaling); 'chains' = independent H*v streams per rank (weak scaling)")
-    ap.add_argument("--chunks", type=int, default=4, help="row groups of the pipelined all-to-all exchange (sharded mode)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="sharded mode: exchange fused into the up kernel over peer memory (CUDA IPC), or NCCL all-to-all "
+                         "transposes; auto = what measured faster on B200 x8 (peer at 2 ranks, nccl beyond)")
+    ap.add_argument("--chunks", type=int, default=1, help="row groups of the pipelined all-to-all exchange (sharded mode)")
     ap.add_argument("--layout", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
     args = ap.parse_args()

@@ -56,7 +56,7 @@ EDGPU_SYMBOLS = [
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
     "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_observables",
     "edgpu_shard_ld", "edgpu_shard_hxv_dw", "edgpu_shard_hxv_up", "edgpu_shard_hxv_up_slabs", "edgpu_shard_perm",
-    "edgpu_shard_hxv_up_peers", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_ipc_export", "edgpu_ipc_open", "edgpu_ipc_close",
+    "edgpu_shard_hxv_up_peers", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_ipc_export", "edgpu_ipc_open", "edgpu_ipc_close", "edgpu_copy_async",
     "edgpu_bench_hxv", "edgpu_device_info", "edgpu_sync",
 ]
 ED_SYMBOLS = [
@@ -126,7 +126,8 @@ def lib():
     L.edgpu_shard_hxv_up.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, C.c_int32]
     L.edgpu_shard_hxv_up_slabs.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, i64p, i64p, vp, vp, C.c_int32]
     L.edgpu_shard_perm.argtypes = [vp, vp, vp]
-    L.edgpu_shard_hxv_up_peers.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, i64p, i64p, C.POINTER(vp), C.POINTER(vp), C.c_int32]
+    L.edgpu_shard_hxv_up_peers.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, i64p, i64p, C.POINTER(vp), i64p, C.POINTER(vp), C.c_int32]
+    L.edgpu_copy_async.argtypes = [vp, vp, vp, C.c_int64, vp]
     L.edgpu_dev_alloc.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     L.edgpu_dev_free.argtypes = [vp, vp]
     L.edgpu_ipc_export.argtypes = [vp, vp, C.c_char_p]

@@ -17,7 +17,7 @@ int hxv_star_launches(const edgpu_sector *s);
 int hxv_star_dw(edgpu_sector *s, const double *x, double *y, int64_t ncols, int64_t ld);
 int hxv_star_up(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int64_t ld, int accumulate);
 int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *yp, int64_t row0, int64_t nrows, int nslab,
-                      const int64_t *col0, const int64_t *ldc, int accumulate);
+                      const int64_t *col0, const int64_t *ldc, int accumulate, const int64_t *x_row0);
 int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int nslab,
                       const int64_t *col0, const int64_t *ldc, int accumulate);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
@@ -496,13 +496,14 @@ extern "C" int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t n
 }
 
 extern "C" int edgpu_shard_hxv_up_peers(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nranks, const int64_t *col0,
-                                        const int64_t *ldc, const void *const *x_shards, void *const *y_shards, int32_t accumulate)
+                                        const int64_t *ldc, const void *const *x_shards, const int64_t *x_row0, void *const *y_shards,
+                                        int32_t accumulate)
 {
     if (!s || !x_shards || !y_shards || !col0 || !ldc) return 1;
     if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: needs the star-product layout");
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: bad row shard");
     if (nrows == 0) return 0;
-    return hxv_star_up_peers(s, (const double *const *)x_shards, (double *const *)y_shards, row0, nrows, nranks, col0, ldc, accumulate);
+    return hxv_star_up_peers(s, (const double *const *)x_shards, (double *const *)y_shards, row0, nrows, nranks, col0, ldc, accumulate, x_row0);
 }
 
 // ---- device buffers that other processes of the node can map (CUDA IPC) -----------------------------------------
@@ -540,6 +541,14 @@ extern "C" int edgpu_ipc_open(edgpu_ctx *ctx, const unsigned char handle[64], vo
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     CUDA_TRY(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+// dst <- src (any pair of device pointers valid in this process, e.g. a peer mapping): copy-engine DMA on `stream`
+extern "C" int edgpu_copy_async(edgpu_ctx *ctx, void *dst, const void *src, int64_t bytes, void *stream)
+{
+    if (!ctx || !dst || !src || bytes < 0) return 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }
 

@@ -664,10 +664,11 @@ struct SlabMap {
     int n, ldc0;
     unsigned magic;                 // ceil(2^32 / ldc0): column / ldc0 by multiplication
     int col0[8], ldc[8];
-    long long base[8];              // element offset of slab p
+    long long base[8];              // element offset of slab p (y, and x unless peer)
     int peer;
     const double *xp[8];
     double *yp[8];
+    long long xbase[8];             // peer mode: element offset of this rank's first row inside xp[p]
 };
 __device__ __forceinline__ int slab_of(const SlabMap &M, int c)
 {
@@ -932,18 +933,26 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
+static constexpr int kMaxXS = 6;                         // x stages of the up pipeline (y stages: 1 or 2)
+
 template <int NORB, int NH>
 __global__ void __launch_bounds__(kNT3)
-k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t ld, int block_index, int G,
+k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t ld, int block_index, int G, int nxs, int nys,
            const StarBlock *__restrict__ blocks,
            const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
            const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
            const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD,
            double *__restrict__ dot_out)
 {
+    // Stages: tile i (i-th tile of this CTA) uses x stage i % nxs and y stage i % nys.  The x images are loaded nxs - nys
+    // tiles further ahead than the y images (remote x segments of the peer mode have NVLink latency to hide; a y image is
+    // also the output buffer, it frees only after its store has been read by the copy engine).
+    //   fullx[sx], fully[sy]: bytes landed (one expect_tx arrival by the producer)
+    //   done[sx]            : one arrival per consumer warp after tile i
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_dot[kNT / 32];
     __shared__ SlabMap s_M;
+    __shared__ uint64_t s_bar[2 * kMaxXS + 2];
     if (threadIdx.x == 0) s_M = Mpar;                                          // visible after the barrier below
     const SlabMap &M = s_M;
     const StarBlock B = blocks[block_index];
@@ -952,33 +961,35 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
     const int ncopy = (lead + size + 1) & ~1;                                  // elements per row segment moved (even)
     const uint32_t rowb = (uint32_t)(ncopy + 2) * 8u;                          // bytes per row slot (16-byte multiple)
     const uint32_t stageb = rowb * (uint32_t)G;
-    double *s_dg = reinterpret_cast<double *>(smem_raw + (size_t)4 * stageb);  // [2 stages][G][8]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_dg + (size_t)16 * G);     // full[2], done[2]
-    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_bar + 4);
+    double *s_dg = reinterpret_cast<double *>(smem_raw + (size_t)(nxs + nys) * stageb);   // [nxs][G][8]
+    unsigned char *tab_base = reinterpret_cast<unsigned char *>(s_dg + (size_t)8 * G * nxs);
     int D[3] = {1, 1, 1}, A0[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < NORB; a++) { D[a] = P.D[B.n[a]]; A0[a] = P.A0[B.n[a]]; }
     const LeanTabs LT = load_lean_tabs<NORB, NH>(P, B, D, A0, hopd, hopc, hopv, estar, tab_base, maxD, 8);
-    const uint32_t xbuf = (uint32_t)__cvta_generic_to_shared(smem_raw);        // [2][G][rowb]
-    const uint32_t ybuf = xbuf + 2u * stageb;
+    const uint32_t xbuf = (uint32_t)__cvta_generic_to_shared(smem_raw);        // [nxs][G][rowb]
+    const uint32_t ybuf = xbuf + (uint32_t)nxs * stageb;                       // [nys][G][rowb]
     const uint32_t dg_addr = (uint32_t)__cvta_generic_to_shared(s_dg);
-    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const uint32_t bfx = (uint32_t)__cvta_generic_to_shared(s_bar);            // fullx[kMaxXS]
+    const uint32_t bdn = bfx + 8u * kMaxXS;                                    // done[kMaxXS]
+    const uint32_t bfy = bdn + 8u * kMaxXS;                                    // fully[2]
     if (tid == 0) {
-        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);                            // full[s]: the producer's expect_tx arrival
-        mbar_init(bar0 + 16, kNT / 32); mbar_init(bar0 + 24, kNT / 32);        // done[s]: one arrival per consumer warp
+        for (int k = 0; k < kMaxXS; k++) { mbar_init(bfx + 8 * k, 1); mbar_init(bdn + 8 * k, kNT / 32); }
+        mbar_init(bfy, 1); mbar_init(bfy + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();                                                           // tables + barriers ready
     const uint32_t impmask = (1u << NORB) - 1u;
     const int64_t ntiles = (dim_dw + G - 1) / G;
     const int64_t colb = (int64_t)B.off - lead;                                // first column moved (even)
+    const int ntot = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;   // tiles of this CTA
+    auto tile_of = [&](int i) -> int64_t { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
 
     if (tid >= kNT) {
         // ---------------- producer warp ----------------
         const int lane = tid - kNT;
-        int64_t t = blockIdx.x;
         // the row segment [colb, colb + ncopy) as pieces of the vector: one piece, or one per slab of a row shard that
-        // arrived by all-to-all (slab boundaries are multiples of 4 columns, so every piece stays 16-byte aligned)
+        // arrived by all-to-all / per column shard of a peer (boundaries are multiples of 4 columns: 16-byte aligned)
         auto for_segments = [&](int64_t row, auto &&fn) {                      // fn(x pointer, y pointer, column - colb, count)
             if (M.n <= 1 && !M.peer) { fn(x + row * ld + colb, y + row * ld + colb, 0, ncopy); return; }
             const int64_t cend = colb + ncopy;
@@ -986,8 +997,8 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
                 const int64_t lo = colb > M.col0[p] ? colb : (int64_t)M.col0[p];
                 const int64_t he = (int64_t)M.col0[p] + M.ldc[p], hi = cend < he ? cend : he;
                 if (lo < hi) {
-                    const int64_t off = M.base[p] + row * M.ldc[p] + (lo - M.col0[p]);
-                    fn((M.peer ? M.xp[p] : x) + off, (M.peer ? M.yp[p] : y) + off, (int)(lo - colb), (int)(hi - lo));
+                    const int64_t off = row * M.ldc[p] + (lo - M.col0[p]);
+                    fn(M.peer ? M.xp[p] + M.xbase[p] + off : x + M.base[p] + off, (M.peer ? M.yp[p] : y) + M.base[p] + off, (int)(lo - colb), (int)(hi - lo));
                 }
             }
         };
@@ -996,65 +1007,78 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
             const int p = slab_of(M, (int)c);
             return (M.peer ? M.yp[p] : y) + M.base[p] + row * M.ldc[p] + (c - M.col0[p]);
         };
-        auto store_tile = [&](int64_t tt, int st) {
-            if (lane == 0) {
-                const int64_t r0 = tt * G;
-                const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
-                for (int g = 0; g < gc; g++) {
-                    const uint32_t src = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
-                    for_segments(r0 + g, [&](const double *, double *yd, int rel, int cnt) { bulk_s2g(yd, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+        auto rows_of = [&](int i, int64_t &r0) -> int {
+            r0 = tile_of(i) * G;
+            return (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
         };
-        int i = 0;
-        for (; t < ntiles; t += gridDim.x, i++) {
-            const int st = i & 1, k = i >> 1;
-            if (i >= 2) {
-                // the stage still holds tile i-2: wait for the consumers, write its result back, wait until the
-                // copy engine has read the buffer, then refill it
-                if (lane == 0) mbar_wait(bar0 + 16 + 8 * st, (uint32_t)(k - 1) & 1u);
-                __syncwarp();
-                store_tile(t - 2 * (int64_t)gridDim.x, st);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            }
-            const int64_t r0 = t * G;
-            const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
+        auto load_x = [&](int i) {                                             // x image + diagonal terms of tile i
+            const int sx = i % nxs;
+            int64_t r0;
+            const int gc = rows_of(i, r0);
             for (int j = lane; j < 8 * gc; j += 32) {
                 // s_dg[stage][g][ui] = E_dw[row] + X[imp_dw(row)][ui] + (Ust-Jh) * C(nimp(ui), 2)
                 const int g = j >> 3, ui = j & 7;
                 const int64_t r = r0 + g;
                 const int nimp = __popc(ui);
-                s_dg[(size_t)st * 8 * G + j] = e_dw[r] + xtab[(cfg_dw[r] & impmask) * 32u + ui] + P.pair_e * (double)(nimp * (nimp - 1) / 2);
+                s_dg[(size_t)sx * 8 * G + j] = e_dw[r] + xtab[(cfg_dw[r] & impmask) * 32u + ui] + P.pair_e * (double)(nimp * (nimp - 1) / 2);
             }
             __syncwarp();
             if (lane == 0) {
-                const uint32_t fb = bar0 + 8 * st;
-                // accumulate == 0 (the result overwrites y): only the first and last 16 bytes of the y segment are loaded --
-                // they may hold an element of the neighbouring block, which the store must put back unchanged
-                const uint32_t ybytes = accumulate ? (uint32_t)ncopy * 8u : (ncopy > 2 ? 32u : 16u);
-                mbar_expect_tx(fb, (uint32_t)gc * ((uint32_t)ncopy * 8u + ybytes));
+                const uint32_t fb = bfx + 8 * sx;
+                mbar_expect_tx(fb, (uint32_t)gc * (uint32_t)ncopy * 8u);
                 for (int g = 0; g < gc; g++) {
-                    const uint32_t xd = xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb, yd = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb;
-                    for_segments(r0 + g, [&](const double *xs, double *ys, int rel, int cnt) {
-                        bulk_g2s(xd + (uint32_t)rel * 8u, xs, (uint32_t)cnt * 8u, fb);
-                        if (accumulate) bulk_g2s(yd + (uint32_t)rel * 8u, ys, (uint32_t)cnt * 8u, fb);
-                    });
-                    if (!accumulate) {
-                        bulk_g2s(yd, y_elem(r0 + g, colb), 16u, fb);
-                        if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y_elem(r0 + g, colb + ncopy - 2), 16u, fb);
-                    }
+                    const uint32_t xd = xbuf + (uint32_t)sx * stageb + (uint32_t)g * rowb;
+                    for_segments(r0 + g, [&](const double *xs, double *, int rel, int cnt) { bulk_g2s(xd + (uint32_t)rel * 8u, xs, (uint32_t)cnt * 8u, fb); });
                 }
             }
-        }
-        // drain: the last (up to two) tiles are still in their stages
-        const int ntot = i;
-        for (int j = (ntot >= 2 ? ntot - 2 : 0); j < ntot; j++) {
-            const int st = j & 1, k = j >> 1;
-            if (lane == 0) mbar_wait(bar0 + 16 + 8 * st, (uint32_t)k & 1u);
+        };
+        auto load_y = [&](int i) {
+            if (lane != 0) return;
+            const int sy = i % nys;
+            int64_t r0;
+            const int gc = rows_of(i, r0);
+            const uint32_t fb = bfy + 8 * sy;
+            // accumulate == 0 (the result overwrites y): only the first and last 16 bytes of the y segment are loaded --
+            // they may hold an element of the neighbouring block, which the store must put back unchanged
+            const uint32_t ybytes = accumulate ? (uint32_t)ncopy * 8u : (ncopy > 2 ? 32u : 16u);
+            mbar_expect_tx(fb, (uint32_t)gc * ybytes);
+            for (int g = 0; g < gc; g++) {
+                const uint32_t yd = ybuf + (uint32_t)sy * stageb + (uint32_t)g * rowb;
+                if (accumulate) {
+                    for_segments(r0 + g, [&](const double *, double *ys, int rel, int cnt) { bulk_g2s(yd + (uint32_t)rel * 8u, ys, (uint32_t)cnt * 8u, fb); });
+                } else {
+                    bulk_g2s(yd, y_elem(r0 + g, colb), 16u, fb);
+                    if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y_elem(r0 + g, colb + ncopy - 2), 16u, fb);
+                }
+            }
+        };
+        auto store_tile = [&](int i) {
+            if (lane != 0) return;
+            int64_t r0;
+            const int gc = rows_of(i, r0);
+            for (int g = 0; g < gc; g++) {
+                const uint32_t src = ybuf + (uint32_t)(i % nys) * stageb + (uint32_t)g * rowb;
+                for_segments(r0 + g, [&](const double *, double *yd, int rel, int cnt) { bulk_s2g(yd, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        };
+        auto wait_done = [&](int i) {                                          // consumers have finished tile i
+            if (lane == 0) mbar_wait(bdn + 8 * (i % nxs), (uint32_t)(i / nxs) & 1u);
             __syncwarp();
-            store_tile((int64_t)blockIdx.x + (int64_t)j * gridDim.x, st);
+        };
+        // prologue
+        for (int i = 0; i < nxs && i < ntot; i++) load_x(i);
+        for (int i = 0; i < nys && i < ntot; i++) load_y(i);
+        // steady state: tile i - nys done -> store it, free its y stage for tile i and its x stage for tile i - nys + nxs
+        for (int i = nys; i < ntot + nys; i++) {
+            wait_done(i - nys);
+            store_tile(i - nys);
+            if (i < ntot) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                load_y(i);
+            }
+            if (i - nys + nxs < ntot) load_x(i - nys + nxs);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         return;
@@ -1066,17 +1090,17 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
     const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
     const int estep = NY * D0;
     double dsum = 0.0;                                                        // partial <x, H x> (fused Lanczos alpha)
-    int i = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
-        const int st = i & 1, k = i >> 1;
-        mbar_wait(bar0 + 8 * st, (uint32_t)k & 1u);
-        const int64_t r0 = t * G;
+    for (int i = 0; i < ntot; i++) {
+        const int sx = i % nxs, sy = i % nys;
+        mbar_wait(bfx + 8 * sx, (uint32_t)(i / nxs) & 1u);
+        mbar_wait(bfy + 8 * sy, (uint32_t)(i / nys) & 1u);
+        const int64_t r0 = tile_of(i) * G;
         const int gc = (int)((dim_dw - r0) < G ? (dim_dw - r0) : G);
         if (L.active) {
             for (int g = 0; g < gc; g++) {
-                const uint32_t xs = xbuf + (uint32_t)st * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
-                const uint32_t ys = ybuf + (uint32_t)st * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
-                const uint32_t dgs = dg_addr + (uint32_t)(st * G + g) * 64u;
+                const uint32_t xs = xbuf + (uint32_t)sx * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
+                const uint32_t ys = ybuf + (uint32_t)sy * stageb + (uint32_t)g * rowb + (uint32_t)lead * 8u;
+                const uint32_t dgs = dg_addr + (uint32_t)(sx * G + g) * 64u;
                 int i1 = L.ty, i2 = 0;
                 if (NORB >= 3) while (i1 >= D1) { i1 -= D1; i2++; }
                 const uint32_t eb = (uint32_t)(L.ty * D0 + L.i0) * 8u;
@@ -1100,7 +1124,7 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // results visible to the copy engine
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bar0 + 16 + 8 * st);
+        if ((tid & 31) == 0) mbar_arrive(bdn + 8 * sx);
     }
     if (dot_out) {
         // fixed-order reduction over the 16 consumer warps (named barrier: the producer warp is not part of it)
@@ -1399,7 +1423,7 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
         auto xat = [&](int64_t c) -> const double * {
             if (!slabbed) return x + r * ld + c;
             const int p = slab_of(M, (int)c);
-            return (M.peer ? M.xp[p] : x) + M.base[p] + r * M.ldc[p] + (c - M.col0[p]);
+            return (M.peer ? M.xp[p] + M.xbase[p] : x + M.base[p]) + r * M.ldc[p] + (c - M.col0[p]);
         };
         const double xo = *xat(ru);
         double acc = (e_up[ru] + e_dw[r] + s_x[(cfg_dw[r] & impmask) * 32u + (cfg_up[ru] & impmask)]) * xo;
@@ -1512,7 +1536,7 @@ static DwKernel pick_dw(int W, int NH)
     }
 }
 
-using Up3Kernel = void (*)(StarKParams, SlabMap, int, int64_t, int64_t, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
+using Up3Kernel = void (*)(StarKParams, SlabMap, int, int64_t, int64_t, int, int, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
                            const double *, const double *, const uint32_t *, const double *, const double *, double *, int, double *);
 template <int NORB>
 static Up3Kernel pick_up3(int NH)
@@ -1654,14 +1678,21 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
             G = std::max<int64_t>(1, std::min<int64_t>(G, nrows / (2 * (int64_t)ctx->sm_count)));
             const int lead = B.off & 1, ncopy = (lead + B.size + 1) & ~1;
             const size_t rowb = (size_t)(ncopy + 2) * 8;
-            const size_t smem = 4 * rowb * G + sizeof(double) * 16 * G + 32 + lean_tabs_bytes(NORB, bD, NH3);
-            if (smem <= 227 * 1024) {
+            const size_t tabs = lean_tabs_bytes(NORB, bD, NH3) + 64;
+            // stages: 2 y images when they fit; x images as far ahead as shared memory allows when x comes over NVLink
+            const size_t avail = 227 * 1024 - 1024 - tabs;
+            const size_t per = rowb * G + 64 * G;                                  // one stage (+ its diagonal terms)
+            const int nst = (int)std::min<size_t>(avail / per, (size_t)kMaxXS + 2);
+            const int nys = nst >= 4 ? 2 : 1;
+            const int nxs = std::max(1, std::min(nst - nys, (slabs && slabs->peer) ? kMaxXS : 2));
+            const size_t smem = (size_t)(nxs + nys) * rowb * G + sizeof(double) * 8 * G * nxs + tabs;
+            if (nst >= 2 && smem <= 227 * 1024) {
                 auto kern = pick_up3<NORB>(NH3);
                 if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
                 const int64_t ntiles = (nrows + G - 1) / G;
                 const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
                 const bool d = dot_ok && slots + (int)nctas <= kDotSlots;
-                kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, M, accumulate, nrows, ld, (int)bi, (int)G, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
+                kern<<<nctas, kNT3, smem, ctx->stream>>>(PU, M, accumulate, nrows, ld, (int)bi, (int)G, nxs, nys, U.d_blocks, U.d_hopd, U.d_hopc, U.d_hopv, U.d_estar,
                                                           s->dw->ediag + row0, s->dw->cfg + row0, ctx->d_xtab, x, y, bD, d ? dot + slots : nullptr);
                 CUDA_TRY(ctx, cudaGetLastError());
                 if (d) slots += (int)nctas; else dot_ok = false;
@@ -1734,7 +1765,7 @@ int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0,
 // Up pass in peer mode: this rank's rows [row0, row0+nrows) of ALL columns, where the columns [col0[p], col0[p]+ldc[p]) live in
 // the column shard of rank p ([dim_dw][ldc[p]], base pointers xp[p] / yp[p] valid on this device, e.g. CUDA IPC mappings).
 int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *yp, int64_t row0, int64_t nrows, int nslab,
-                      const int64_t *col0, const int64_t *ldc, int accumulate)
+                      const int64_t *col0, const int64_t *ldc, int accumulate, const int64_t *x_row0)
 {
     if (!s->up->star || !s->dw->star) return edgpu_fail(s->ctx, "hxv_star: sector is not in the star-product layout");
     if (nslab < 1 || nslab > 8) return edgpu_fail(s->ctx, "hxv_star_up_peers: 1..8 ranks supported (got %d)", nslab);
@@ -1751,6 +1782,7 @@ int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *y
         if ((reinterpret_cast<uintptr_t>(xp[p]) | reinterpret_cast<uintptr_t>(yp[p])) & 15)
             return edgpu_fail(s->ctx, "hxv_star_up_peers: shard pointers must be 16-byte aligned");
         M.col0[p] = (int)col0[p]; M.ldc[p] = (int)ldc[p]; M.base[p] = (long long)row0 * ldc[p];
+        M.xbase[p] = (long long)(row0 - (x_row0 ? x_row0[p] : 0)) * ldc[p];
         M.xp[p] = xp[p]; M.yp[p] = yp[p];
     }
     switch (s->ctx->ham.norb) {

@@ -225,17 +225,18 @@ class PeerShardedHxv:
 
     Every rank keeps its column shards (the Lanczos vectors `vec(i)` and one scratch shard) in buffers that all ranks of
     the node map through CUDA IPC.  Per product:
-        y_i   = H_dw x_i                         local (tensor-map down kernel on the column shard)
         barrier                                  (1-element NCCL all-reduce on the compute stream)
-        tmp_p[my rows] = (D + H_up) x[my rows]   copy-engine up kernel: bulk loads of the x row segments straight from the
-                                                 owners' shards, bulk stores of the result into the owners' scratch shards
+        y_i   = H_dw x_i                         local (tensor-map down kernel on the column shard), WHILE the copy engines
+                                                 pull this rank's rows of the other shards over NVLink (DMA, no SMs)
+        tmp_p[my rows] = (D + H_up) x[my rows]   copy-engine up kernel: bulk stores of the result straight into the owners'
+                                                 scratch shards (prefetch=False: also bulk loads of x from the owners)
         barrier
         y_i  += tmp                              local
     No transpose buffers, no NCCL data traffic: NVLink carries (P-1)/P * Dim/P * 8 B in and out per rank and product,
     overlapped with the gathers tile by tile by the kernel's own pipeline.  Replaces the full-vector MPI_Allgatherv of
     directMatVec_MPI_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:163-166)."""
 
-    def __init__(self, edb, sector, rank, world, nvec=2, group=None):
+    def __init__(self, edb, sector, rank, world, nvec=2, group=None, prefetch=True):
         import ctypes as C
         self.edb, self.s, self.rank, self.world, self.group = edb, sector, rank, world, group
         ld = C.c_int64()
@@ -267,6 +268,15 @@ class PeerShardedHxv:
         self._ldc = (C.c_int64 * world)(*P.ldc)
         self._parr = [(C.c_void_p * world)(*row) for row in self.ptrs]
         self.bytes_nvlink = 0
+        # DMA prefetch of the remote x rows (see apply): local copies [nrows_me][ldc_p] of the other ranks' shards
+        self.prefetch = prefetch
+        self.side = torch.cuda.Stream()
+        self.ev = torch.cuda.Event()
+        self.recv = [None if p == rank else torch.zeros(max(1, P.nrows[rank] * P.ldc[p]), dtype=torch.float64, device=self.device)
+                     for p in range(world)]
+        self._xloc = [(C.c_void_p * world)(*[self.ptrs[i][p] if p == rank else self.recv[p].data_ptr() for p in range(world)])
+                      for i in range(nvec + 1)]
+        self._xrow0 = (C.c_int64 * world)(*[0 if p == rank else P.row0[rank] for p in range(world)])
 
     def vec(self, i):
         return self.bufs[i].t
@@ -277,12 +287,28 @@ class PeerShardedHxv:
 
     def apply(self, ix, iy):
         """vec(iy) = H vec(ix) on the column shards."""
+        import ctypes as C
         P, me, L, s = self.plan, self.rank, self.edb.lib(), self.s
         x, y, tmp = self.bufs[ix].t, self.bufs[iy].t, self.bufs[-1].t
-        s.ctx.check(L.edgpu_shard_hxv_dw(s.h, P.ncols[me], self.ldc, x.data_ptr(), y.data_ptr()))
+        cur = torch.cuda.current_stream()
         self.barrier()                       # every rank's x is final, every rank is done with its scratch shard
+        if self.prefetch and self.world > 1:
+            # copy-engine DMA of this rank's rows of the other shards WHILE the down pass runs: the up kernel then reads
+            # local memory and NVLink carries its stores only
+            self.side.wait_stream(cur)
+            for p in range(self.world):
+                if p != me:
+                    s.ctx.check(L.edgpu_copy_async(s.ctx.h, self.recv[p].data_ptr(), self.ptrs[ix][p] + 8 * P.row0[me] * P.ldc[p],
+                                                   8 * P.nrows[me] * P.ldc[p], C.c_void_p(self.side.cuda_stream)))
+            self.ev.record(self.side)
+            xarr, xrow0 = self._xloc[ix], self._xrow0
+        else:
+            xarr, xrow0 = self._parr[ix], None
+        s.ctx.check(L.edgpu_shard_hxv_dw(s.h, P.ncols[me], self.ldc, x.data_ptr(), y.data_ptr()))
+        if self.prefetch and self.world > 1:
+            cur.wait_event(self.ev)
         s.ctx.check(L.edgpu_shard_hxv_up_peers(s.h, P.row0[me], P.nrows[me], self.world, self._col0, self._ldc,
-                                               self._parr[ix], self._parr[-1], 0))
+                                               xarr, xrow0, self._parr[-1], 0))
         self.barrier()                       # all rows of my scratch shard have arrived
         y += tmp
         self.bytes_nvlink += 8 * P.nrows[me] * (P.ld - self.ldc)

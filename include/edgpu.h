@@ -135,9 +135,13 @@ int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t nrows, int32
  * x from, and writes its result to, the column shards of ALL ranks directly (x_shards[p] / y_shards[p]: base pointers of rank
  * p's [DimDw][ldc[p]] shard, valid on this device -- own memory for p == this rank, CUDA IPC mappings otherwise).  The two
  * MPI exchanges of directMatVec_MPI_cc (ED_HAMILTONIAN_DIRECT_HxV.f90:163-166) are thereby fused into the kernel.
- * accumulate = 0: y = (D + H_up) x ; 1: y += ... .  The caller orders the ranks (a barrier before and after). */
+ * accumulate = 0: y = (D + H_up) x ; 1: y += ... .  The caller orders the ranks (a barrier before and after).
+ * x_row0[p] (NULL = all 0): global index of the first row held by x_shards[p] -- 0 for a whole shard, row0 for a local
+ * copy of just this rank's rows (prefetched by copy-engine DMA while the down pass runs, edgpu_copy_async). */
 int edgpu_shard_hxv_up_peers(edgpu_sector *s, int64_t row0, int64_t nrows, int32_t nranks, const int64_t *col0,
-                             const int64_t *ldc, const void *const *x_shards, void *const *y_shards, int32_t accumulate);
+                             const int64_t *ldc, const void *const *x_shards, const int64_t *x_row0, void *const *y_shards,
+                             int32_t accumulate);
+int edgpu_copy_async(edgpu_ctx *ctx, void *dst, const void *src, int64_t bytes, void *stream);
 /* Device buffers for peer mode: separate cudaMalloc allocations (zero-filled) whose CUDA IPC handle (64 bytes) another
  * process on the node opens with edgpu_ipc_open (peer access is enabled lazily). */
 int edgpu_dev_alloc(edgpu_ctx *ctx, int64_t bytes, void **dev_ptr);

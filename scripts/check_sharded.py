@@ -50,4 +50,17 @@ dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"sharded H*v world={world} sector ({nup},{ndw}) dim={s.dim}: max rel err vs single GPU = {t.item():.3e}")
     assert t.item() < 1e-12
+# peer mode: the exchange fused into the up-pass kernel (CUDA IPC mappings of the other ranks' shards)
+ps = sharded.PeerShardedHxv(edb, s, rank, world)
+ps.vec(0).copy_(x_loc)
+for _ in range(2):                      # twice: the scratch shards are reused
+    ps.apply(0, 1)
+torch.cuda.synchronize()
+err = np.abs(ps.vec(1)[:, :nc].cpu().numpy() - Yref[np.ix_(idw, iu[c0:c0 + nc])]).max() / np.abs(Yref).max()
+t = torch.tensor([err], device="cuda", dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"peer-mode H*v world={world}: max rel err vs single GPU = {t.item():.3e}")
+    assert t.item() < 1e-12
+dist.barrier()
 dist.destroy_process_group()

@@ -168,8 +168,20 @@ def test_shard_entry_points_equal_full_product(oracle, edb, flags):
         lc = (C.c_int64 * world)(*plan.ldc)
         for r in range(world):
             ctx.check(edb.lib().edgpu_shard_hxv_dw(s.h, plan.ncols[r], plan.ldc[r], xs[r].data_ptr(), ys[r].data_ptr()))
-            ctx.check(edb.lib().edgpu_shard_hxv_up_peers(s.h, plan.row0[r], plan.nrows[r], world, c0, lc, xp, tp, 0))
+            ctx.check(edb.lib().edgpu_shard_hxv_up_peers(s.h, plan.row0[r], plan.nrows[r], world, c0, lc, xp, None, tp, 0))
         ctx.sync()
         Yp = np.concatenate([(ys[q] + ts[q]).cpu().numpy() for q in range(world)], axis=1)
         assert np.abs(Yp - Yint_ref).max() < HXV_TOL * np.abs(Yint_ref).max()
+        # the same with local copies of just this rank's rows of the other shards (what the DMA prefetch delivers)
+        t2 = [torch.full_like(t, -3.0) for t in xs]
+        tp2 = (C.c_void_p * world)(*[t.data_ptr() for t in t2])
+        for r in range(world):
+            rows = slice(plan.row0[r], plan.row0[r] + plan.nrows[r])
+            loc = [xs[q] if q == r else xs[q][rows].contiguous() for q in range(world)]
+            xl = (C.c_void_p * world)(*[t.data_ptr() for t in loc])
+            xr0 = (C.c_int64 * world)(*[0 if q == r else plan.row0[r] for q in range(world)])
+            ctx.check(edb.lib().edgpu_shard_hxv_up_peers(s.h, plan.row0[r], plan.nrows[r], world, c0, lc, xl, xr0, tp2, 0))
+            ctx.sync()
+        for q in range(world):
+            assert torch.equal(t2[q], ts[q])
     x.free(); y.free(); s.free(); ctx.close()
