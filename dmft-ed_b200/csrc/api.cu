@@ -1,5 +1,6 @@
 // api.cu -- the C-ABI of libedgpu (include/edgpu.h): context, Hamiltonian, sectors, vectors, H*v entry points.
 #include "edgpu_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -10,6 +11,7 @@ uint64_t edgpu_binom(int n, int k);
 int sector_map_kernel(edgpu_sector *s, int64_t first, int64_t count, uint64_t *d_out);
 int sector_map_check_kernel(edgpu_sector *s, unsigned long long *d_sum, unsigned long long *d_viol);
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst);
+int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st);
 int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst);
 int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 int csr_build(edgpu_sector *s);
@@ -90,6 +92,8 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->bases.clear();
+    for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
     delete ctx;
     return 0;
@@ -257,13 +261,41 @@ extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cpl
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return 0;
     }
-    double *stage = nullptr;
-    if (int rc = stage_alloc(ctx, bytes, &stage)) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = vec_convert(s, is_cplx ? 1 : 0, stage, v->d);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
-    return rc;
+    // chunks of reference rows through two persistent staging buffers: the host-to-device copy of chunk k+1 (copy stream)
+    // overlaps the layout conversion of chunk k (compute stream)
+    const size_t rowb = sizeof(double) * (size_t)s->dim_up * (is_cplx ? 2 : 1);
+    const size_t kChunk = (size_t)64 << 20;
+    const int64_t crow = (int64_t)std::max<size_t>(1, kChunk / rowb);
+    const size_t cbytes = rowb * (size_t)crow;
+    if (ctx->stage_bytes < cbytes) {
+        for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); ctx->d_stage[b] = nullptr; }
+        for (int b = 0; b < 2; b++) CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage[b], cbytes));
+        ctx->stage_bytes = cbytes;
+    }
+    if (!ctx->copy_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)s->nalloc, ctx->stream));        // pad columns stay zero
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[0], ctx->stream));                                    // order after earlier work
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+    int k = 0;
+    for (int64_t r0 = 0; r0 < s->dim_dw; r0 += crow, k++) {
+        const int b = k & 1;
+        const int64_t r1 = std::min<int64_t>(s->dim_dw, r0 + crow);
+        if (k >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], reinterpret_cast<const char *>(host) + rowb * (size_t)r0, rowb * (size_t)(r1 - r0),
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        if (int rc = vec_convert_rows(s, is_cplx ? 1 : 0, r0, r1, ctx->d_stage[b], v->d, ctx->stream)) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[b], ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_cplx)

@@ -94,6 +94,11 @@ struct edgpu_ctx {
     void *d_flush = nullptr;           // L2 flush scratch
     size_t flush_bytes = 0;
     double *d_xtab = nullptr;          // [32*32] cross-spin interaction table X(u_imp,d_imp) + constant
+    // chunked host<->device vector transfers (edgpu_vec_upload): two staging buffers, copy stream, hand-over events
+    double *d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
 };
 
 struct edgpu_sector {

@@ -935,9 +935,9 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
 
 static constexpr int kMaxXS = 6;                         // x stages of the up pipeline (y stages: 1 or 2)
 
-template <int NORB, int NH>
+template <int NORB, int NH, bool GEN>                     // GEN = false: nxs = nys = 2 known at compile time (single GPU)
 __global__ void __launch_bounds__(kNT3)
-k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t ld, int block_index, int G, int nxs, int nys,
+k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t ld, int block_index, int G, int nxs_arg, int nys_arg,
            const StarBlock *__restrict__ blocks,
            const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
            const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
@@ -953,6 +953,7 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
     __shared__ double s_dot[kNT / 32];
     __shared__ SlabMap s_M;
     __shared__ uint64_t s_bar[2 * kMaxXS + 2];
+    const int nxs = GEN ? nxs_arg : 2, nys = GEN ? nys_arg : 2;
     if (threadIdx.x == 0) s_M = Mpar;                                          // visible after the barrier below
     const SlabMap &M = s_M;
     const StarBlock B = blocks[block_index];
@@ -1539,13 +1540,19 @@ static DwKernel pick_dw(int W, int NH)
 using Up3Kernel = void (*)(StarKParams, SlabMap, int, int64_t, int64_t, int, int, int, int, const StarBlock *, const int16_t *, const uint8_t *, const double *,
                            const double *, const double *, const uint32_t *, const double *, const double *, double *, int, double *);
 template <int NORB>
-static Up3Kernel pick_up3(int NH)
+static Up3Kernel pick_up3(int NH, bool gen)
 {
+    if (gen) switch (NH) {
+        case 4: return k_star_up3<NORB, 4, true>;
+        case 5: return k_star_up3<NORB, 5, true>;
+        case 6: return k_star_up3<NORB, 6, true>;
+        default: return k_star_up3<NORB, 8, true>;
+    }
     switch (NH) {
-        case 4: return k_star_up3<NORB, 4>;
-        case 5: return k_star_up3<NORB, 5>;
-        case 6: return k_star_up3<NORB, 6>;
-        default: return k_star_up3<NORB, 8>;
+        case 4: return k_star_up3<NORB, 4, false>;
+        case 5: return k_star_up3<NORB, 5, false>;
+        case 6: return k_star_up3<NORB, 6, false>;
+        default: return k_star_up3<NORB, 8, false>;
     }
 }
 
@@ -1687,7 +1694,7 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
             const int nxs = std::max(1, std::min(nst - nys, (slabs && slabs->peer) ? kMaxXS : 2));
             const size_t smem = (size_t)(nxs + nys) * rowb * G + sizeof(double) * 8 * G * nxs + tabs;
             if (nst >= 2 && smem <= 227 * 1024) {
-                auto kern = pick_up3<NORB>(NH3);
+                auto kern = pick_up3<NORB>(NH3, !(nxs == 2 && nys == 2));
                 if (int rc = ensure_smem(ctx, (const void *)kern, smem)) return rc;
                 const int64_t ntiles = (nrows + G - 1) / G;
                 const unsigned nctas = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);

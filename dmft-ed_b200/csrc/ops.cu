@@ -3,6 +3,7 @@
 // apply_c replaces the seed loops of lanc_build_gf_normal_c (ED_GF_NORMAL.f90:159-174 for c^+, :212-227 for c);
 // observables replaces the normal-mode core of observables_impurity (ED_OBSERVABLES.f90:127-158).
 #include "edgpu_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -13,16 +14,17 @@ int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 // mode 2: ref (real) <- internal        ; 3: interleaved complex (imag=0) <- internal
 // mode 4: internal <- imag part of complex source ; 5: complex.imag <- internal (real part untouched)
 __global__ void __launch_bounds__(256)
-k_convert(int mode, int64_t dim_up, int64_t dim_dw, int64_t ld,
+k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, int64_t ld,
           const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw,
           const double *__restrict__ src, double *__restrict__ dst)
 {
+    // reference rows [rd_begin, rd_end); the reference-side array starts at row rd_begin (chunked transfers)
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ru >= dim_up) return;
     const int64_t iu = r2i_up ? (int64_t)r2i_up[ru] : ru;
-    for (int64_t rd = blockIdx.y; rd < dim_dw; rd += gridDim.y) {
+    for (int64_t rd = rd_begin + blockIdx.y; rd < rd_end; rd += gridDim.y) {
         const int64_t id = r2i_dw ? (int64_t)r2i_dw[rd] : rd;
-        const int64_t iref = rd * dim_up + ru, iint = id * ld + iu;
+        const int64_t iref = (rd - rd_begin) * dim_up + ru, iint = id * ld + iu;
         switch (mode) {
         case 0: dst[iint] = src[iref]; break;
         case 1: dst[iint] = src[2 * iref]; break;
@@ -40,7 +42,17 @@ static dim3 grid2d(const edgpu_sector *s) {
 
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst)
 {
-    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, src, dst);
+    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, 0, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, src, dst);
+    CUDA_TRY(s->ctx, cudaGetLastError());
+    return 0;
+}
+
+// the same for reference rows [rd0, rd1) only; the reference-side array is the chunk holding just those rows
+int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st)
+{
+    if (rd1 <= rd0) return 0;
+    dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)std::min<int64_t>(rd1 - rd0, 32768));
+    k_convert<<<grid, 256, 0, st>>>(mode, s->dim_up, rd0, rd1, s->ld, s->up->ref2int, s->dw->ref2int, src, dst);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
