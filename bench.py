@@ -290,6 +290,7 @@ def main():
                     help="sharded mode: exchange fused into the up kernel over peer memory (CUDA IPC), or NCCL all-to-all "
                          "transposes; auto = what measured faster on B200 x8 (peer at 2 ranks, nccl beyond)")
     ap.add_argument("--chunks", type=int, default=1, help="row groups of the pipelined all-to-all exchange (sharded mode)")
+    ap.add_argument("--flags", type=int, default=0, help="edgpu_params.reserved[0] test hooks (A/B runs of kernel variants)")
     ap.add_argument("--layout", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
     args = ap.parse_args()
@@ -321,7 +322,8 @@ def main():
         return run_sharded(args, edb, world, rank, local)
     Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
     stream = torch.cuda.current_stream().cuda_stream
-    ctx = edb.Context(Norb, Nbath, 1, True, device=local, stream=stream, layout=args.layout, hxv_kernel=args.kernel)
+    ctx = edb.Context(Norb, Nbath, 1, True, device=local, stream=stream, layout=args.layout, hxv_kernel=args.kernel,
+                      debug_flags=args.flags)
     # synthetic inputs: deterministic bath of init_dmft_bath, Uloc=2, Ust=Jh=0, xmu=0, HFMODE=T
     inp = edb.default_input(Norb=Norb, Nbath=Nbath, uloc=[2.0] * Norb)
     sol_bath = np.zeros(edb.lib().ed_get_bath_dimension(inp))
