@@ -1090,11 +1090,11 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
     }
 
     // ---------------- consumer warps ----------------
+    double dsum = 0.0;                                                        // partial <x, H x> (fused Lanczos alpha)
     LeanThread<NH> L;
     L.init(B, D, A0, LT);
     const int D0 = D[0], D1 = D[1], NY = L.NY, O = L.O;
     const int estep = NY * D0;
-    double dsum = 0.0;                                                        // partial <x, H x> (fused Lanczos alpha)
     for (int i = 0; i < ntot; i++) {
         const int sx = i % nxs, sy = i % nys;
         mbar_wait(bfx + 8 * sx, (uint32_t)(i / nxs) & 1u);
@@ -1711,7 +1711,8 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
             // stages: 2 y images when they fit; x images as far ahead as shared memory allows when x comes over NVLink
             const size_t avail = 227 * 1024 - 1024 - tabs;
             const size_t per = rowb * G + 64 * G;                                  // one stage (+ its diagonal terms)
-            const int nst = (int)std::min<size_t>(avail / per, (size_t)kMaxXS + 2);
+            int nst = (int)std::min<size_t>(avail / per, (size_t)kMaxXS + 2);
+            if (ctx->par.reserved[0] & 64) nst = std::min(nst, (ctx->par.reserved[0] & 128) ? 3 : 2);   // test hooks: few stages
             const int nys = nst >= 4 ? 2 : 1;
             const int nxs = std::max(1, std::min(nst - nys, (slabs && slabs->peer) ? kMaxXS : 2));
             const size_t smem = (size_t)(nxs + nys) * rowb * G + sizeof(double) * 8 * G * nxs + tabs;
