@@ -175,9 +175,12 @@ def run_reference_arm(args):
 
 
 def star_blocks(norb, nbath, n):
-    """number of star-occupation blocks (= kernel launches of one spin pass) for n particles"""
+    """kernel launches of one spin pass for n particles: one per star-occupation block of >= 256 configurations plus one
+    fringe launch for all smaller blocks (hxv_star.cu)"""
     import itertools
-    return sum(1 for t in itertools.product(range(nbath + 2), repeat=norb) if sum(t) == n)
+    import math
+    sizes = [math.prod(math.comb(nbath + 1, m) for m in t) for t in itertools.product(range(nbath + 2), repeat=norb) if sum(t) == n]
+    return sum(1 for z in sizes if z >= 256) + (1 if any(z < 256 for z in sizes) else 0)
 
 
 def run_sharded(args, edb, world, rank, local):
@@ -200,7 +203,7 @@ def run_sharded(args, edb, world, rank, local):
     s = ctx.sector(nup, ndw)
     g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
     if args.exchange == "auto":
-        args.exchange = "peer" if world <= 2 else "nccl"
+        args.exchange = "peer" if world <= 4 else "nccl"
     if args.exchange == "peer":
         sh = sharded.PeerShardedHxv(edb, s, rank, world)
         plan = sh.plan
@@ -247,6 +250,27 @@ def run_sharded(args, edb, world, rank, local):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     nvl = (sh.bytes_nvlink if args.exchange == "peer" else sh.bytes_alltoall) / args.steps
+    # the other level of parallelism of the north star, for comparison in the same run: independent Lanczos chains, one
+    # whole sector vector per GPU, no data-path collective -> aggregate H*v per second over all ranks
+    chains = None
+    try:
+        xf, yf = s.vec(), s.vec()
+        xf.fill_normal(20240607 + rank)
+        for _ in range(args.warmup):
+            s.hxv(xf, yf)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            s.hxv(xf, yf)
+        ev1.record()
+        barrier()
+        tc = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        chains = {"value": world * args.steps / (float(tc.item()) * 1e-3), "unit": "matvec/s", "scaling": "weak",
+                  "what": "independent chains: one whole sector vector per GPU, no collective (bench.py --mode chains)"}
+        xf.free(); yf.free()
+    except Exception as e:                   # e.g. the whole vector does not fit next to the shards
+        chains = {"error": str(e)[:200]}
     if rank == 0:
         line = {
             "metric": "hxv_matvecs_per_s", "value": 1e3 / ms_step, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
@@ -260,7 +284,7 @@ def run_sharded(args, edb, world, rank, local):
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
                          "nvlink_bytes_sent_per_rank_per_hxv": nvl,
                          "nvlink_floor_ms": nvl / 770e9 * 1e3, "nvlink_peak_source": "770 GB/s per direction (B200_PROFILING.md peer copy)"},
-            "e2e": None, "cpu_baseline": None,
+            "e2e": None, "cpu_baseline": None, "independent_chains": chains,
             "gpu_launches": int(args.steps * (star_blocks(Norb, Nbath, nup) + star_blocks(Norb, Nbath, ndw))), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -288,7 +312,7 @@ def main():
                          "(strong scaling); 'chains' = independent H*v streams per rank (weak scaling)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="sharded mode: exchange fused into the up kernel over peer memory (CUDA IPC), or NCCL all-to-all "
-                         "transposes; auto = what measured faster on B200 x8 (peer at 2 ranks, nccl beyond)")
+                         "transposes; auto = what measured faster on B200 x8 (peer up to 4 ranks, nccl at 8)")
     ap.add_argument("--chunks", type=int, default=1, help="row groups of the pipelined all-to-all exchange (sharded mode)")
     ap.add_argument("--flags", type=int, default=0, help="edgpu_params.reserved[0] test hooks (A/B runs of kernel variants)")
     ap.add_argument("--layout", type=int, default=0)
