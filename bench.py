@@ -205,7 +205,7 @@ def run_sharded(args, edb, world, rank, local):
     if args.exchange == "auto":
         args.exchange = "peer" if world <= 4 else "nccl"
     if args.exchange == "peer":
-        sh = sharded.PeerShardedHxv(edb, s, rank, world)
+        sh = sharded.PeerShardedHxv(edb, s, rank, world, nvec=3)
         plan = sh.plan
         sh.vec(0)[:, :plan.ncols[rank]] = torch.randn(plan.dim_dw, plan.ncols[rank], dtype=torch.float64, device="cuda", generator=g)
         apply = lambda: sh.apply(0, 1)
@@ -250,6 +250,34 @@ def run_sharded(args, edb, world, rank, local):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     nvl = (sh.bytes_nvlink if args.exchange == "peer" else sh.bytes_alltoall) / args.steps
+    # end to end: the column shard of the start vector comes from pinned host memory, nlanc sharded Lanczos steps
+    # (H*v + all-reduced scalars + vector updates), alpha/beta go back to the host
+    e2e = None
+    if not args.no_e2e:
+        nlanc = min(args.nlanc, 50)
+        hostv = torch.empty(plan.dim_dw, plan.ldc[rank], dtype=torch.float64).pin_memory()
+        hostv.zero_()
+        hostv[:, :plan.ncols[rank]] = 1.0 / np.sqrt(dim)
+        times = []
+        for i in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            if args.exchange == "peer":
+                sh.vec(0).copy_(hostv, non_blocking=True)
+                al, be = sh.lanczos_tridiag(nlanc)
+            else:
+                x.copy_(hostv, non_blocking=True)
+                al, be = sh.lanczos_tridiag(x, nlanc)
+            barrier()
+            times.append(time.perf_counter() - t0)
+        te = torch.tensor([times[-1]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = float(te.item())
+        e2e = {"value": nlanc / te, "unit": "matvec/s", "h2d_bytes_per_step": int(world * hostv.numel() * 8),
+               "d2h_bytes_per_step": int(2 * nlanc * 8),
+               "call": f"pinned host column shards -> device, {nlanc} steps of the sharded Lanczos recurrence "
+                       "(dmft-ed_b200/sharded.py: sharded_lanczos), alpha/beta -> host", "s_per_call": te,
+               "alpha0": float(al[0])}
     # the other level of parallelism of the north star, for comparison in the same run: independent Lanczos chains, one
     # whole sector vector per GPU, no data-path collective -> aggregate H*v per second over all ranks
     chains = None
@@ -284,7 +312,7 @@ def run_sharded(args, edb, world, rank, local):
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
                          "nvlink_bytes_sent_per_rank_per_hxv": nvl,
                          "nvlink_floor_ms": nvl / 770e9 * 1e3, "nvlink_peak_source": "770 GB/s per direction (B200_PROFILING.md peer copy)"},
-            "e2e": None, "cpu_baseline": None, "independent_chains": chains,
+            "e2e": e2e, "cpu_baseline": None, "independent_chains": chains,
             "gpu_launches": int(args.steps * (star_blocks(Norb, Nbath, nup) + star_blocks(Norb, Nbath, ndw))), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -148,21 +148,33 @@ class ShardedHxv:
 
     def lanczos_tridiag(self, v_cols: torch.Tensor, nlanc: int):
         """sp_lanc_tridiag recurrence (.repo/PLAIN_LANCZOS.f90:87-118,154-180) on the sharded vector."""
-        vin = v_cols / torch.sqrt(self.dot(v_cols, v_cols))
-        vout = torch.zeros_like(vin)
-        tmp = torch.zeros_like(vin)
-        alfa, beta = [], [0.0]
-        b = torch.zeros(1, dtype=torch.float64, device=self.device)
-        for _ in range(nlanc):
-            self.apply(vin, tmp)
-            tmp -= b * vout
-            a = self.dot(vin, tmp)
-            tmp -= a * vin
-            b = torch.sqrt(self.dot(tmp, tmp))
-            vout, vin, tmp = vin, tmp / b, vout
-            alfa.append(a)
-            beta.append(b)
-        return torch.cat(alfa).cpu().numpy(), torch.cat([torch.zeros(1, dtype=torch.float64, device=self.device)] + beta[1:]).cpu().numpy()[:nlanc]
+        cur = v_cols.clone()
+        return sharded_lanczos(lambda a, b: self.apply(a, b), self.dot, cur, torch.zeros_like(cur), torch.zeros_like(cur), nlanc)
+
+
+def sharded_lanczos(apply, dot, cur, old, u, nlanc):
+    """Lanczos tridiagonalisation of a sharded vector on unnormalised vectors (the recurrence of lanczos.cu):
+        u = H w_k ; a_k = <w_k,u>/b_k^2 ; w_{k+1} = u/b_k - (b_k/b_{k-1}) w_{k-1} - (a_k/b_k) w_k ; b_{k+1} = |w_{k+1}|
+    apply(x, y): y = H x on the shards; dot(a, b): all-reduced scalar (1-element tensor).  cur holds the start vector, old
+    and u are scratch shards; every coefficient stays a device tensor (no host synchronisation inside the loop).
+    Returns (alfa[nlanc], beta[nlanc]) with beta[0] = 0 like the reference's blanc."""
+    one = torch.ones(1, dtype=torch.float64, device=cur.device)
+    cur.div_(torch.sqrt(dot(cur, cur)))
+    old.zero_()
+    ncur, nold, bprev = one, one, torch.zeros_like(one)
+    alfa, beta = [], [torch.zeros_like(one)]
+    for _ in range(nlanc):
+        apply(cur, u)
+        a = dot(cur, u) / (ncur * ncur)
+        old.mul_(-(bprev / nold))
+        old.addcmul_(u, 1.0 / ncur)
+        old.addcmul_(cur, -(a / ncur))
+        b = torch.sqrt(dot(old, old))
+        alfa.append(a)
+        beta.append(b)
+        cur, old = old, cur
+        nold, ncur, bprev = ncur, b, b
+    return torch.cat(alfa).cpu().numpy(), torch.cat(beta).cpu().numpy()[:nlanc]
 
 
 class GpuOps:
@@ -319,3 +331,10 @@ class PeerShardedHxv:
         if self.world > 1:
             dist.all_reduce(v, group=self.group)
         return v
+
+    def lanczos_tridiag(self, nlanc):
+        """Lanczos chain started from vec(0) (destroyed); needs nvec >= 3."""
+        assert len(self.bufs) >= 4, "PeerShardedHxv(nvec=3) is needed for the Lanczos recurrence"
+        idx = {self.bufs[i].t.data_ptr(): i for i in range(len(self.bufs) - 1)}
+        return sharded_lanczos(lambda a, b: self.apply(idx[a.data_ptr()], idx[b.data_ptr()]), self.dot,
+                               self.vec(0), self.vec(1), self.vec(2), nlanc)
