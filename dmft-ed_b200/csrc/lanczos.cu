@@ -12,6 +12,7 @@
 // All Lanczos scalars live in device memory so that the GF tridiagonalisation runs without host round trips;
 // dot products use a fixed launch shape + fixed-order second stage => bit-reproducible run to run.
 #include "edgpu_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -33,6 +34,39 @@ __device__ __forceinline__ void block_store_partial(double v, double *out)
         v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
         v = warp_sum(v);
         if (lane == 0) *out = v;
+    }
+}
+
+// Second stage folded into the producing kernel (saves a launch per reduction -- the many small sectors of an ed_solve
+// scan are launch-bound): the block that takes the last ticket sums the partials in index order, so the result does not
+// depend on which block that is.  mode 0: sum ; 1: sqrt(sum) ; 2: sum / (*nrm)^2.  Call with all threads of the block,
+// after block_store_partial.
+__device__ __forceinline__ void finalize_by_last_block(const double *__restrict__ partials, int nblocks, int mode,
+                                                       const double *__restrict__ nrm, double *__restrict__ out,
+                                                       unsigned int *__restrict__ ticket)
+{
+    __shared__ bool s_last;
+    __shared__ double sh2[32];
+    __threadfence();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += __ldcg(partials + i);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh2[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh2[lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) {
+            if (mode == 1) v = sqrt(v);
+            else if (mode == 2) { const double d = *nrm; v = v / (d * d); }
+            *out = v;
+            *ticket = 0u;
+        }
     }
 }
 
@@ -158,6 +192,36 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c(double *__restrict__ old
     block_store_partial(acc, partials + blockIdx.x);
 }
 
+// a = <a_vec, b_vec> / (*nrm)^2 in one launch
+__global__ void __launch_bounds__(kRedThreads) k_dot_alpha(const double *__restrict__ a, const double *__restrict__ b, int64_t n,
+                                                           double *__restrict__ partials, const double *__restrict__ nrm,
+                                                           double *__restrict__ out, unsigned int *__restrict__ ticket)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i] * b[i];
+    block_store_partial(acc, partials + blockIdx.x);
+    finalize_by_last_block(partials, gridDim.x, 2, nrm, out, ticket);
+}
+
+// k_lanc_c + the final sqrt(sum) in one launch
+__global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict__ old, const double *__restrict__ u,
+                                                             const double *__restrict__ cur, const double *__restrict__ p_bprev,
+                                                             const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
+                                                             const double *__restrict__ p_a, int64_t n, double *__restrict__ partials,
+                                                             double *__restrict__ b_out, unsigned int *__restrict__ ticket)
+{
+    const double nc = *p_ncur, c_old = *p_bprev / *p_nold, c_cur = *p_a / nc;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = u[i] / nc - c_old * old[i] - c_cur * cur[i];
+        old[i] = t;
+        acc += t * t;
+    }
+    block_store_partial(acc, partials + blockIdx.x);
+    finalize_by_last_block(partials, gridDim.x, 1, nullptr, b_out, ticket);
+}
+
 __global__ void k_set_one(double *p) { *p = 1.0; }
 
 // Device scalar slots: [0] norm, [3] the constant 1, [kScalArr + k] alanc[k], [kScalArr + kLancMax + k] blanc[k]
@@ -181,6 +245,7 @@ static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, in
     const double *p_bprev = d_b + (iter - 1);
     const double *p_ncur = iter == 1 ? one : d_b + (iter - 1);
     const double *p_nold = iter <= 2 ? one : d_b + (iter - 2);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(ctx->d_scal + 4);    // zero between launches (reset by the last block)
     int ndot = -1;
     if (hxv_uses_star(s)) {
         if (int rc = hxv_star_dot(s, cur, u, ctx->d_dotpart, &ndot)) return rc;
@@ -188,11 +253,10 @@ static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, in
     if (ndot >= 0) {
         k_lanc_alpha<<<1, 256, 0, ctx->stream>>>(ctx->d_dotpart, ndot, p_ncur, d_a + (iter - 1));
     } else {
-        k_dot<<<nb, kRedThreads, 0, ctx->stream>>>(cur, u, n, ctx->d_partials);
-        k_lanc_alpha<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, p_ncur, d_a + (iter - 1));
+        k_dot_alpha<<<nb, kRedThreads, 0, ctx->stream>>>(cur, u, n, ctx->d_partials, p_ncur, d_a + (iter - 1), ticket);
     }
-    k_lanc_c<<<nb, kRedThreads, 0, ctx->stream>>>(old, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, d_b + iter, 1);
+    k_lanc_c_norm<<<nb, kRedThreads, 0, ctx->stream>>>(old, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials,
+                                                       d_b + iter, ticket);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -209,7 +273,7 @@ static int normalise(edgpu_sector *s, double *v)
     return 0;
 }
 
-// tql2 (EISPACK, as carried in .repo/PLAIN_LANCZOS.f90:427-565): host, tiny.
+// tql2 (EISPACK, as carried in .repo/PLAIN_LANCZOS.f90:427-565): host, tiny.  z == nullptr: eigenvalues only.
 int host_tql2(int n, double *d, double *e, double *z);
 
 extern "C" int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlanc, double threshold,
@@ -275,26 +339,37 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal + kScalB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_scal[0] == 0.0) return edgpu_fail(ctx, "lanczos_plain_iteration: norm =0!!");
-    for (int iter = 1; iter <= nitermax; iter++) {
-        if (int rc = lanczos_step(s, vin, vout, tmp, iter, d_a, d_b)) return rc;     // (cur, old, scratch)
-        { double *t = vin; vin = vout; vout = t; }
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, d_a + (iter - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + 1, d_b + iter, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // The reference diagonalises the growing tridiagonal and tests |dE0| after EVERY step.  Small sectors are bound by
+    // that host round trip, so the device runs kBatch steps ahead and the host then replays the reference's rule step
+    // by step over the new (a, b) pairs: the stopping iteration is identical, at most kBatch - 1 steps are computed in
+    // vain (pass 2 regenerates exactly nlanc vectors).  Only eigenVALUES are needed here (tql2 without vectors gives
+    // bit-identical values); the vectors are computed once, after the loop.
+    const int kBatch = s->dim < (1ll << 22) ? 8 : 1;
+    bool stop = false;
+    for (int iter0 = 1; iter0 <= nitermax && !stop; iter0 += kBatch) {
+        const int nb = std::min(kBatch, nitermax - iter0 + 1);
+        for (int k = 0; k < nb; k++) {
+            if (int rc = lanczos_step(s, vin, vout, tmp, iter0 + k, d_a, d_b)) return rc;     // (cur, old, scratch)
+            double *t = vin; vin = vout; vout = t;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, d_a + (iter0 - 1), sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + 8, d_b + iter0, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const double a = ctx->h_scal[0], b = ctx->h_scal[1];
-        if (std::fabs(b) < threshold) break;                                    // :333
-        nlanc++;
-        alanc[iter - 1] = a;
-        blanc[iter] = b;
-        for (int i = 0; i < nlanc; i++) { diag[i] = alanc[i]; sub[i] = i > 0 ? blanc[i] : 0.0; }
-        Z.assign((size_t)nlanc * nlanc, 0.0);
-        for (int i = 0; i < nlanc; i++) Z[i + (size_t)nlanc * i] = 1.0;
-        host_tql2(nlanc, diag.data(), sub.data(), Z.data());
-        if (nlanc >= ncheck) {                                                  // :352-359
-            esave[nlanc - (ncheck - 1)] = diag[0];
-            if (nlanc >= ncheck + 1) {
-                double diff = esave[nlanc - (ncheck - 1)] - esave[nlanc - (ncheck - 1) - 1];
-                if (std::fabs(diff) <= threshold) break;
+        for (int k = 0; k < nb; k++) {
+            const int iter = iter0 + k;
+            const double a = ctx->h_scal[k], b = ctx->h_scal[8 + k];
+            if (std::fabs(b) < threshold) { stop = true; break; }               // :333
+            nlanc++;
+            alanc[iter - 1] = a;
+            blanc[iter] = b;
+            for (int i = 0; i < nlanc; i++) { diag[i] = alanc[i]; sub[i] = i > 0 ? blanc[i] : 0.0; }
+            host_tql2(nlanc, diag.data(), sub.data(), nullptr);
+            if (nlanc >= ncheck) {                                              // :352-359
+                esave[nlanc - (ncheck - 1)] = diag[0];
+                if (nlanc >= ncheck + 1) {
+                    double diff = esave[nlanc - (ncheck - 1)] - esave[nlanc - (ncheck - 1) - 1];
+                    if (std::fabs(diff) <= threshold) { stop = true; break; }
+                }
             }
         }
     }
@@ -389,11 +464,13 @@ int host_tql2(int n, double *d, double *e, double *z)
                     c = p / r;
                     p = c * d[i] - s * g;
                     d[i + 1] = h + s * (c * g + s * d[i]);
-                    double *zi = z + (size_t)n * i, *zi1 = z + (size_t)n * (i + 1);
-                    for (int k = 0; k < n; k++) {
-                        const double hh = zi1[k];
-                        zi1[k] = s * zi[k] + c * hh;
-                        zi[k] = c * zi[k] - s * hh;
+                    if (z) {
+                        double *zi = z + (size_t)n * i, *zi1 = z + (size_t)n * (i + 1);
+                        for (int k = 0; k < n; k++) {
+                            const double hh = zi1[k];
+                            zi1[k] = s * zi[k] + c * hh;
+                            zi[k] = c * zi[k] - s * hh;
+                        }
                     }
                 }
                 p = -s * s2 * c3 * el1 * e[l] / dl1;
@@ -410,7 +487,7 @@ int host_tql2(int n, double *d, double *e, double *z)
         for (int j = ii; j < n; j++) if (d[j] < p) { k = j; p = d[j]; }
         if (k != i) {
             d[k] = d[i]; d[i] = p;
-            for (int j = 0; j < n; j++) std::swap(z[j + (size_t)n * i], z[j + (size_t)n * k]);
+            if (z) for (int j = 0; j < n; j++) std::swap(z[j + (size_t)n * i], z[j + (size_t)n * k]);
         }
     }
     return 0;
