@@ -58,6 +58,10 @@ struct ed_solver {
     std::vector<cplx> Gmats, Greal, Smats, Sreal, G0mats, G0real;
     std::vector<double> dens, dens_up, dens_dw, docc, magz, sz2, n2;
     double s2tot = 0;
+    // spin susceptibility (ED_VARS_GLOBAL.f90:144-146, ED_SETUP.f90:342-344)
+    int Ltau = 0;
+    std::vector<double> vm, tau, spinChi_tau;
+    std::vector<cplx> spinChi_iv, spinChi_w;
     double timings[4] = {0, 0, 0, 0};
 };
 
@@ -92,6 +96,7 @@ extern "C" void ed_input_defaults(ed_input *in)
     in->gs_threshold = 1e-9; in->hwband = 2.0;
     in->lanc_method = 0; in->lanc_nstates_sector = 6; in->lanc_nstates_total = 1;
     in->lanc_niter = 512; in->lanc_ngfiter = 200; in->lanc_tolerance = 1e-12; in->lanc_dim_threshold = 256;
+    in->chispin_flag = 0; in->Ltau = 1000;
     in->ed_twin = 0; in->ed_sparse_H = 1; in->ed_verbose = 3;
 }
 
@@ -463,6 +468,79 @@ static int build_gf(ed_solver *s)
     return 0;
 }
 
+// add_to_lanczos_spinChi (ED_GF_CHISPIN.f90:247-319), T = 0 (pesoBZ = 1).  isign = +1 and -1 in one go.
+static void add_to_lanczos_spinchi(ed_solver *s, double vnorm, double Ei, const std::vector<double> &alanc,
+                                   const std::vector<double> &blanc, int iorb)
+{
+    const ed_input &in = s->in;
+    const int nlanc = (int)alanc.size(), L1 = in.Norb + 1;
+    const double beta = in.beta;
+    const double pesoF = vnorm * vnorm / s->zeta;
+    std::vector<double> w(nlanc), Z((size_t)nlanc * nlanc);
+    ed_host_eigh_tridiag(nlanc, alanc.data(), blanc.data(), w.data(), Z.data());
+    for (int isign = 1; isign >= -1; isign -= 2)
+        for (int j = 0; j < nlanc; j++) {
+            const double dE = w[j] - Ei;
+            const double peso = pesoF * Z[(size_t)nlanc * j] * Z[(size_t)nlanc * j];
+            const double ex = std::exp(-beta * dE);
+            s->spinChi_iv[iorb] += (beta * dE < 1e-1) ? peso * beta : peso * (1.0 - ex) / dE;          // :273-277, :294-298
+            for (int i = 1; i <= in.Lmats; i++)
+                s->spinChi_iv[iorb + (size_t)L1 * i] += isign == 1 ? peso * (ex - 1.0) / (cplx(0.0, s->vm[i]) - dE)
+                                                                   : peso * (1.0 - ex) / (cplx(0.0, s->vm[i]) + dE);
+            for (int i = 0; i <= s->Ltau; i++)
+                s->spinChi_tau[iorb + (size_t)L1 * i] += isign == 1 ? peso * std::exp(-s->tau[i] * dE) : peso * std::exp(-(beta - s->tau[i]) * dE);
+            for (int i = 0; i < in.Lreal; i++)
+                s->spinChi_w[iorb + (size_t)L1 * i] += isign == 1 ? peso * (ex - 1.0) / (cplx(s->wr[i], in.eps) - dE)
+                                                                  : peso * (1.0 - ex) / (cplx(s->wr[i], in.eps) + dE);
+        }
+}
+
+// build_chi_spin (ED_GF_CHISPIN.f90:22-40): one chain per kept state and orbital, seed S_z,a |gs> in the state's own sector
+// (lanc_ed_build_spinChi_c :57-141), plus S_z^tot for Norb > 1 (lanc_ed_build_spinChi_tot_c :160-237).
+static int build_chi_spin(ed_solver *s)
+{
+    const ed_input &in = s->in;
+    const int L1 = in.Norb + 1;
+    const double pi = 3.14159265358979323846;
+    s->Ltau = std::max((int)in.beta, (int)in.Ltau);                                  // ED_INPUT_VARS.f90:211
+    s->vm.resize(in.Lmats + 1);
+    s->tau.resize(s->Ltau + 1);
+    for (int i = 0; i <= in.Lmats; i++) s->vm[i] = pi / in.beta * 2.0 * (double)i;   // ED_AUX_FUNX.f90:456-458
+    for (int i = 0; i <= s->Ltau; i++) s->tau[i] = s->Ltau > 0 ? in.beta * (double)i / (double)s->Ltau : 0.0;
+    s->spinChi_iv.assign((size_t)L1 * (in.Lmats + 1), cplx(0, 0));
+    s->spinChi_tau.assign((size_t)L1 * (s->Ltau + 1), 0.0);
+    s->spinChi_w.assign((size_t)L1 * in.Lreal, cplx(0, 0));
+    if (!in.chispin_flag) return 0;
+    const int nchan = in.Norb + (in.Norb > 1 ? 1 : 0);
+    for (int ic = 0; ic < nchan; ic++) {
+        const bool tot = ic == in.Norb;
+        for (size_t istate = 0; istate < s->states.size(); istate++) {
+            EdState &st = s->states[istate];
+            int64_t idim = 0;
+            edgpu_sector_dim(st.sec, &idim, nullptr, nullptr);
+            edgpu_vec *vv = nullptr;
+            GPU_TRY(s, edgpu_vec_alloc(st.sec, &vv));
+            double nrm = 0;
+            int rc = edgpu_apply_sz(st.sec, tot ? 0 : ic + 1, st.vec, vv, 1, &nrm);
+            const int nlanc = (int)std::min<int64_t>(idim, in.lanc_ngfiter);
+            std::vector<double> alfa(nlanc, 0.0), beta(nlanc, 0.0);
+            int nused = 0;
+            if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_build_csr(st.sec);
+            if (!rc && nrm > 0.0) rc = edgpu_lanczos_tridiag(st.sec, vv, nlanc, 1e-13, alfa.data(), beta.data(), &nused);
+            if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_drop_csr(st.sec);
+            edgpu_vec_free(vv);
+            if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
+            // the single-orbital routine hands the NORM to add_to_lanczos_spinChi (:101), the total one its SQUARE (:206);
+            // both are squared again there (pesoF = vnorm**2, :263) -- reproduced as is
+            if (nrm > 0.0) add_to_lanczos_spinchi(s, tot ? nrm * nrm : nrm, st.e, alfa, beta, ic);
+        }
+    }
+    for (auto &v : s->spinChi_tau) v /= s->zeta;                                     // :36-38
+    for (auto &v : s->spinChi_w) v /= s->zeta;
+    for (auto &v : s->spinChi_iv) v /= s->zeta;
+    return 0;
+}
+
 static cplx delta_bath(const ed_solver *s, cplx x, int ispin, int iorb)
 {
     // delta_bath_mats_main, normal/normal (ED_BATH_FUNCTIONS.f90:245-256)
@@ -534,6 +612,7 @@ extern "C" int ed_solve(ed_solver *s, const double *bath, int32_t bath_len, cons
     if (int rc = build_gf(s)) return rc;                    // buildgf_impurity
     double t2 = now_s();
     build_sigma(s);
+    if (int rc = build_chi_spin(s)) return rc;              // buildchi_impurity (ED_MAIN.f90:274)
     double t3 = now_s();
     if (int rc = observables(s)) return rc;                 // observables_impurity
     double t4 = now_s();
@@ -580,6 +659,17 @@ extern "C" int ed_get_grids(const ed_solver *s, double *wm, double *wr)
     if (!s) return 1;
     if (wm) copy_d(s->wm, wm);
     if (wr) copy_d(s->wr, wr);
+    return 0;
+}
+extern "C" int ed_get_spinchi(const ed_solver *s, double *chi_iv, double *chi_tau, double *chi_w, double *vm, double *tau, int32_t *ltau)
+{
+    if (!s || s->spinChi_iv.empty()) return 1;
+    if (chi_iv) copy_c(s->spinChi_iv, chi_iv);
+    if (chi_tau) copy_d(s->spinChi_tau, chi_tau);
+    if (chi_w) copy_c(s->spinChi_w, chi_w);
+    if (vm) copy_d(s->vm, vm);
+    if (tau) copy_d(s->tau, tau);
+    if (ltau) *ltau = s->Ltau;
     return 0;
 }
 extern "C" int ed_get_state_count(const ed_solver *s, int32_t *n, double *zeta, double *egs)

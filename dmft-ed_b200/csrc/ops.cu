@@ -159,6 +159,41 @@ extern "C" int edgpu_apply_c(edgpu_sector *si, edgpu_sector *so, int32_t isite, 
     return 0;
 }
 
+// ---- diagonal seed operators of the susceptibility chains (ED_GF_CHISPIN.f90:93-100, 198-205) ----------------------
+// out = 1/2 (n_up - n_dw) in   over the impurity levels selected by `mask` (one orbital, or all of them for S_z^tot)
+__global__ void __launch_bounds__(256)
+k_apply_sz(uint32_t mask, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t *__restrict__ cfg_up,
+           const uint32_t *__restrict__ cfg_dw, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ru >= dim_up) return;
+    const int nu = __popc(cfg_up[ru] & mask);
+    for (int64_t rd = blockIdx.y; rd < dim_dw; rd += gridDim.y) {
+        const double sgn = (double)nu - (double)__popc(cfg_dw[rd] & mask);
+        out[rd * ld + ru] = 0.5 * sgn * in[rd * ld + ru];
+    }
+}
+
+extern "C" int edgpu_apply_sz(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm)
+{
+    if (!s || !in || !out || in->s != s || out->s != s) return s ? edgpu_fail(s->ctx, "edgpu_apply_sz: bad handles") : 1;
+    edgpu_ctx *ctx = s->ctx;
+    const int norb = ctx->ham.norb;
+    if (iorb < 0 || iorb > norb) return edgpu_fail(ctx, "edgpu_apply_sz: iorb=%d out of range (0 = total, 1..Norb)", iorb);
+    if (in->d == out->d) return edgpu_fail(ctx, "edgpu_apply_sz: in-place application is not allowed");
+    const uint32_t mask = iorb == 0 ? (1u << norb) - 1u : 1u << (iorb - 1);
+    dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)(s->dim_dw < 32768 ? s->dim_dw : 32768));
+    k_apply_sz<<<grid, 256, 0, ctx->stream>>>(mask, s->dim_up, s->dim_dw, s->ld, s->up->cfg, s->dw->cfg, in->d, out->d);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (int rc = vec_dot(ctx, out->d, out->d, s->nalloc, ctx->d_scal)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const double n2 = ctx->h_scal[0];
+    if (norm) *norm = std::sqrt(n2);
+    if (normalise && n2 > 0.0) return vec_scale(ctx, out->d, 1.0 / std::sqrt(n2), s->nalloc);
+    return 0;
+}
+
 // ---- observables: joint distribution of the impurity bits -------------------------------------------------
 // rowsum[rd][ui] = sum_{ru : imp(u)=ui} gs[rd][ru]^2 ; the host combines rows by imp(d) (fixed order => deterministic).
 __global__ void __launch_bounds__(256)

@@ -110,6 +110,12 @@ MODULE ED_GPU_BINDING
        integer(c_int32_t),value   :: isite,dagger,normalise
        real(c_double),intent(out) :: norm2
      end function edgpu_apply_c
+     integer(c_int) function edgpu_apply_sz(sec,iorb,vin,vout,normalise,norm) bind(C,name="edgpu_apply_sz")
+       import :: c_ptr,c_int,c_int32_t,c_double
+       type(c_ptr),value        :: sec,vin,vout
+       integer(c_int32_t),value :: iorb,normalise
+       real(c_double)           :: norm
+     end function edgpu_apply_sz
      integer(c_int) function edgpu_observables(s,gs,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot) bind(C,name="edgpu_observables")
        import :: c_int,c_ptr,c_double
        type(c_ptr),value            :: s,gs
@@ -199,6 +205,23 @@ contains
     ierr=edgpu_vec_free(vv)
     ierr=edgpu_sector_free(sec_j)
   end subroutine gpu_lanc_gf_chain
+
+  !> replaces the seed loop + sp_lanc_tridiag of lanc_ed_build_spinChi_c (ED_GF_CHISPIN.f90:89-122; iorb=0: the S_z^tot
+  !> variant, :194-227).  norm is |S_z gs| -- the caller keeps the reference's norm2 convention (:101 vs :206).
+  subroutine gpu_lanc_spinchi_chain(sec_i,vec_i,iorb,sparse_H,nlanc,norm,alfa_,beta_)
+    type(c_ptr),intent(in)  :: sec_i,vec_i
+    integer,intent(in)      :: iorb,nlanc
+    logical,intent(in)      :: sparse_H
+    real(8),intent(out)     :: norm,alfa_(nlanc),beta_(nlanc)
+    type(c_ptr)             :: vv
+    integer(c_int32_t)      :: nused
+    integer(c_int)          :: ierr
+    call gpu_check(edgpu_vec_alloc(sec_i,vv),"gpu_lanc_spinchi_chain")
+    call gpu_check(edgpu_apply_sz(sec_i,int(iorb,c_int32_t),vec_i,vv,1_c_int32_t,norm),"apply_sz")
+    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_i),"ed_buildH_c")
+    call gpu_check(edgpu_lanczos_tridiag(sec_i,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    ierr=edgpu_vec_free(vv)
+  end subroutine gpu_lanc_spinchi_chain
 
   !> replaces the i-loop of observables_impurity (ED_OBSERVABLES.f90:127-158) for one state
   subroutine gpu_observables(sec,vec,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot)

@@ -41,7 +41,9 @@ typedef struct {
     int32_t ed_verbose;
     int32_t gpu_layout;             /* edgpu_params.layout  (0 auto) */
     int32_t gpu_hxv_kernel;         /* edgpu_params.hxv_kernel (0 auto) */
-    int32_t reserved[8];
+    int32_t chispin_flag;           /* CHISPIN_FLAG (ED_INPUT_VARS.f90:156): build the spin susceptibility in ed_solve */
+    int32_t Ltau;                   /* LTAU (ED_INPUT_VARS.f90:148,211): imaginary-time points, raised to int(beta) */
+    int32_t reserved[6];
 } ed_input;
 
 void ed_input_defaults(ed_input *in);
@@ -79,6 +81,11 @@ int ed_get_mag(const ed_solver *s, double *magz);
 int ed_get_sz2_n2(const ed_solver *s, double *sz2, double *n2, double *s2tot);
 /* grids: wm(Lmats), wr(Lreal) (ED_AUX_FUNX.f90:449-461) */
 int ed_get_grids(const ed_solver *s, double *wm, double *wr);
+/* Spin susceptibility <S_z,a(tau) S_z,a(0)> (build_chi_spin, ED_GF_CHISPIN.f90:22-40; printed by ED_IO/print_impChi.f90),
+ * available after ed_solve when chispin_flag != 0.  Row Norb+1 is S_z^tot (only filled for Norb > 1, like the reference).
+ * chi_iv (Norb+1, 0:Lmats) complex, chi_tau (Norb+1, 0:Ltau) real, chi_w (Norb+1, Lreal) complex, column-major;
+ * vm(0:Lmats) bosonic Matsubara frequencies, tau(0:Ltau).  ltau returns the effective Ltau. */
+int ed_get_spinchi(const ed_solver *s, double *chi_iv, double *chi_tau, double *chi_w, double *vm, double *tau, int32_t *ltau);
 
 /* state_list after diagonalize_impurity (ED_DIAG.f90:220-236, 383-416): number of kept states, zeta_function,
  * and per state: energy, nup, ndw. */

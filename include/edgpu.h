@@ -111,6 +111,12 @@ int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlanc, double t
 int edgpu_apply_c(edgpu_sector *s_in, edgpu_sector *s_out, int32_t isite, int32_t dagger,
                   const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm2);
 
+/* Seed of the spin-susceptibility chains (ED_GF_CHISPIN.f90:93-104, 198-208): out = S_z |in> in the SAME sector, with
+ * S_z = 1/2 (n_up - n_dw) of impurity orbital iorb (1..Norb) or of all impurity orbitals (iorb = 0).
+ * norm = sqrt(<out|out>) (before normalisation); normalise != 0 scales out to unit norm.  The chain itself is
+ * edgpu_lanczos_tridiag on `out`. */
+int edgpu_apply_sz(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm);
+
 /* observables_impurity core (ED_OBSERVABLES.f90:127-158): accumulates (+=) like the reference.
  * dens,dens_up,dens_dw,docc,magz: [Norb]; sz2,n2: [Norb*Norb] column-major; s2tot scalar. */
 int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double peso,

@@ -128,6 +128,8 @@ class Params:
     lanc_dim_threshold: int = 256
     ed_twin: bool = False
     ed_sparse_H: bool = True
+    chispin_flag: bool = False
+    Ltau: int = 1000
 
     @property
     def Ns(self):
@@ -338,6 +340,12 @@ class Result:
     sz2: np.ndarray | None = None
     n2: np.ndarray | None = None
     s2tot: float = 0.0
+    vm: np.ndarray | None = None
+    tau: np.ndarray | None = None
+    spinChi_iv: np.ndarray | None = None
+    spinChi_tau: np.ndarray | None = None
+    spinChi_w: np.ndarray | None = None
+    chi_chains: list = field(default_factory=list)
 
 
 def sector_index(Ns, nup, ndw):
@@ -473,6 +481,76 @@ def build_gf(model: Model, res: Result):
     return res
 
 
+def apply_sz(Ns, Norb, iorb, smap, gs):
+    """Seed of the spin-susceptibility chain (ED_GF_CHISPIN.f90:93-100; iorb = None: S_z^tot, :198-205):
+    vvinit(m) = 1/2 (n_up - n_dw) gs(m) over the impurity level(s); returns the unnormalised vector."""
+    words = np.asarray(smap, dtype=np.uint64)
+    orbs = range(Norb) if iorb is None else [iorb]
+    sgn = np.zeros(words.size)
+    for a in orbs:
+        sgn += ((words >> np.uint64(a)) & np.uint64(1)).astype(float) - ((words >> np.uint64(a + Ns)) & np.uint64(1)).astype(float)
+    return 0.5 * sgn * gs
+
+
+def add_to_lanczos_spinchi(p: Params, res: Result, vnorm, Ei, alanc, blanc, isign, iorb):
+    """add_to_lanczos_spinChi (ED_GF_CHISPIN.f90:247-319), T = 0 (pesoBZ = 1)."""
+    beta = p.beta
+    pesoF = vnorm ** 2 / res.zeta
+    lam, Z = eigh_tridiag(alanc, blanc)
+    for j in range(len(alanc)):
+        dE = lam[j] - Ei
+        peso = pesoF * Z[0, j] * Z[0, j]
+        ex = np.exp(-beta * dE)
+        res.spinChi_iv[iorb, 0] += peso * beta if beta * dE < 1e-1 else peso * (1.0 - ex) / dE
+        if isign == 1:
+            res.spinChi_iv[iorb, 1:] += peso * (ex - 1.0) / (1j * res.vm[1:] - dE)
+            res.spinChi_tau[iorb, :] += peso * np.exp(-res.tau * dE)
+            res.spinChi_w[iorb, :] += peso * (ex - 1.0) / ((res.wr + 1j * p.eps) - dE)
+        else:
+            res.spinChi_iv[iorb, 1:] += peso * (1.0 - ex) / (1j * res.vm[1:] + dE)
+            res.spinChi_tau[iorb, :] += peso * np.exp(-(beta - res.tau) * dE)
+            res.spinChi_w[iorb, :] += peso * (1.0 - ex) / ((res.wr + 1j * p.eps) + dE)
+
+
+def build_chi_spin(model: Model, res: Result):
+    """buildChi_impurity / build_chi_spin (ED_GREENS_FUNCTIONS.f90:72-103, ED_GF_CHISPIN.f90:22-40): per kept state and
+    orbital one Lanczos chain in the state's OWN sector seeded with S_z,a |gs> (:57-141), S_z^tot for Norb > 1 (:160-237).
+    Quirk kept as is: the single-orbital routine passes the norm of the seed (:101), the total one its square (:206); both
+    are squared again in add_to_lanczos_spinChi (:263); the final division by zeta_function (:36-38) comes on top of
+    the one inside pesoF."""
+    p = model.p
+    Ns = p.Ns
+    Ltau = max(int(p.beta), p.Ltau)                                            # ED_INPUT_VARS.f90:211
+    res.vm = np.pi / p.beta * 2.0 * np.arange(0, p.Lmats + 1)                  # ED_AUX_FUNX.f90:452-458
+    res.tau = np.linspace(0.0, p.beta, Ltau + 1)
+    if res.wr is None:
+        res.wm, res.wr = grids(p)
+    res.spinChi_iv = np.zeros((p.Norb + 1, p.Lmats + 1), dtype=np.complex128)
+    res.spinChi_tau = np.zeros((p.Norb + 1, Ltau + 1))
+    res.spinChi_w = np.zeros((p.Norb + 1, p.Lreal), dtype=np.complex128)
+    if not p.chispin_flag:
+        return res
+    chans = list(range(p.Norb)) + ([None] if p.Norb > 1 else [])
+    for ic, iorb in enumerate(chans):
+        for istate, st in enumerate(res.states):
+            smap = build_sector(Ns, st.nup, st.ndw)
+            vv = apply_sz(Ns, p.Norb, iorb, smap, st.vec)
+            n2 = float(np.vdot(vv, vv).real)
+            if n2 <= 0.0:
+                continue
+            nrm = np.sqrt(n2)
+            nlanc = min(smap.size, p.lanc_ngfiter)
+            alfa, beta, nused = lanc_tridiag(model, smap, vv / nrm, nlanc)
+            res.chi_chains.append(dict(iorb=ic, istate=istate, norm=nrm, alfa=alfa, beta=beta, nused=nused))
+            vnorm = n2 if iorb is None else nrm
+            for isign in (1, -1):
+                add_to_lanczos_spinchi(p, res, vnorm, st.e, alfa, beta, isign, ic)
+    res.spinChi_tau /= res.zeta
+    res.spinChi_w /= res.zeta
+    res.spinChi_iv /= res.zeta
+    return res
+
+
 def delta_bath(model: Model, x, ispin, iorb):
     """delta_bath_mats_main, normal/normal (ED_BATH_FUNCTIONS.f90:245-256)."""
     p = model.p
@@ -528,6 +606,7 @@ def ed_solve(p: Params, bath: np.ndarray, hloc=None, sectors=None) -> Result:
     ed_diag(model, res, sectors=sectors)
     build_gf(model, res)
     build_sigma(model, res)
+    build_chi_spin(model, res)
     observables(model, res)
     res.model = model
     return res

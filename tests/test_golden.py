@@ -121,3 +121,37 @@ def test_gpu_reproduces_golden_solves(edb):
     assert np.abs(ch["alfa"][:5] - G["cfg2_chain0_alfa"][:5]).max() < 1e-9
     assert np.abs(ch["beta"][:5] - G["cfg2_chain0_beta"][:5]).max() < 1e-9
     sol.close()
+
+
+# ------------------------------------------------------------------------------------------------ spin susceptibility
+def _chi_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_chi", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                                                  "make_golden_chi.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return (("cfg1", m.CFG1), ("two", m.TWO))
+
+
+def test_oracle_reproduces_golden_chi(oracle):
+    GC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_chi.npz"))
+    for name, kw in _chi_cases():
+        p = oracle.Params(**kw)
+        r = oracle.ed_solve(p, oracle.init_bath(p))
+        assert np.abs(r.spinChi_tau - GC[name + "_chi_tau"]).max() < 1e-10
+        assert np.abs(r.spinChi_iv - GC[name + "_chi_iv"]).max() < 1e-9 * max(1.0, np.abs(GC[name + "_chi_iv"]).max())
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_chi(edb):
+    GC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_chi.npz"))
+    for name, kw in _chi_cases():
+        kw = dict(kw)
+        kw["chispin_flag"] = 1
+        inp = edb.default_input(ed_sparse_H=0, **kw)
+        sol = edb.Solver(inp)
+        sol.solve()
+        iv, ct, cw, vm, tau = sol.spinchi()
+        assert np.abs(ct - GC[name + "_chi_tau"]).max() < 1e-8
+        assert np.abs(iv - GC[name + "_chi_iv"]).max() < 1e-8 * max(1.0, np.abs(GC[name + "_chi_iv"]).max())
+        sol.close()

@@ -15,7 +15,8 @@ def run_pair(oracle, edb, sectors=None, sparse=0, **kw):
                             beta=p.beta, xmu=p.xmu, hfmode=int(p.hfmode), Lmats=p.Lmats, Lreal=p.Lreal,
                             lanc_method=p.lanc_method, lanc_nstates_sector=p.lanc_nstates_sector,
                             lanc_ngfiter=p.lanc_ngfiter, lanc_niter=p.lanc_niter, lanc_dim_threshold=p.lanc_dim_threshold,
-                            lanc_tolerance=p.lanc_tolerance, gs_threshold=p.gs_threshold, ed_sparse_H=sparse)
+                            lanc_tolerance=p.lanc_tolerance, gs_threshold=p.gs_threshold, ed_sparse_H=sparse,
+                            chispin_flag=int(p.chispin_flag), Ltau=p.Ltau)
     sol = edb.Solver(inp)
     assert np.array_equal(sol.bath, bath)                         # init_dmft_bath mirror
     if sectors is not None:
@@ -91,3 +92,40 @@ def test_ed_solve_cfg2_half_filling_window(oracle, edb):
         assert np.abs(c["alfa"][:k] - r["alfa"][:k]).max() < 1e-9
         assert np.abs(c["beta"][:k] - r["beta"][:k]).max() < 1e-9
     sol.close()
+
+
+def test_spin_susceptibility_matches_oracle(oracle, edb):
+    """build_chi_spin (ED_GF_CHISPIN.f90:22-40) through ed_solve: S_z seeds (edgpu_apply_sz) + the same GF Lanczos chains.
+    chi(tau), chi(i nu), chi(w) within the G/Sigma tolerance of the north star (1e-8)."""
+    for kw in (dict(Norb=1, Nbath=4, chispin_flag=True, Ltau=200),
+               dict(Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, lanc_dim_threshold=64, chispin_flag=True, Ltau=64)):
+        p, ref, sol = run_pair(oracle, edb, **kw)
+        compare(p, ref, sol)
+        iv, ct, cw, vm, tau = sol.spinchi()
+        assert ct.shape == ref.spinChi_tau.shape and np.array_equal(vm, ref.vm)
+        assert np.abs(tau - ref.tau).max() < 1e-12
+        assert np.abs(ct - ref.spinChi_tau).max() < 1e-8
+        assert np.abs(iv - ref.spinChi_iv).max() < 1e-8 * max(1.0, np.abs(ref.spinChi_iv).max())
+        assert np.abs(cw - ref.spinChi_w).max() < 1e-4 * max(1.0, np.abs(ref.spinChi_w).max())
+        if p.Norb == 1:
+            assert np.abs(ct[1]).max() == 0.0                       # S_z^tot row only for Norb > 1
+        sol.close()
+
+
+def test_apply_sz_seed(oracle, edb):
+    """edgpu_apply_sz against the literal seed loop (ED_GF_CHISPIN.f90:93-100, 198-205), both layouts."""
+    import ctypes as C
+    from test_gpu_parity import make, CASES as BASE_CASES
+    for layout in (1, 2):
+        p, model, ctx, rng = make(oracle, edb, BASE_CASES["2orb_hund"], layout=layout)
+        s = ctx.sector(3, 2)
+        smap = oracle.build_sector(p.Ns, 3, 2)
+        g = rng.normal(size=smap.size)
+        vin, vout = s.vec(g), s.vec()
+        for iorb in (0, 1, 2):
+            nrm = C.c_double()
+            ctx.check(edb.lib().edgpu_apply_sz(s.h, iorb, vin.h, vout.h, 0, C.byref(nrm)))
+            ref = oracle.apply_sz(p.Ns, p.Norb, None if iorb == 0 else iorb - 1, smap, g)
+            assert np.abs(vout.download() - ref).max() < 1e-14
+            assert abs(nrm.value - np.linalg.norm(ref)) < 1e-12
+        vin.free(); vout.free(); s.free(); ctx.close()

@@ -172,6 +172,32 @@ def test_ed_solve_cfg1_invariants(oracle):
     assert np.abs(r0.impGmats[0, 0, 0, 0] - g0).max() < 1e-9
 
 
+def test_spin_susceptibility_invariants(oracle):
+    """build_chi_spin restatement (ED_GF_CHISPIN.f90): chi(tau) = chi(beta - tau); the static value equals the tau integral
+    (term by term: int_0^beta [e^{-tau dE} + e^{-(beta-tau) dE}] = 2 (1 - e^{-beta dE})/dE); a unique ground state with
+    <S_z> = 0 gives chi(tau = 0) = <S_z^2> of the observables; the S_z^tot row only exists for Norb > 1."""
+    p = params(oracle, Norb=1, Nbath=3, Lmats=32, Lreal=16, beta=40.0, chispin_flag=True, Ltau=4000, lanc_dim_threshold=8)
+    r = oracle.ed_solve(p, oracle.init_bath(p))
+    ct = r.spinChi_tau[0]
+    assert r.spinChi_tau.shape == (2, 4001) and np.abs(r.spinChi_tau[1]).max() == 0.0
+    assert np.abs(ct - ct[::-1]).max() < 1e-12
+    assert ct[0] > ct[len(ct) // 2] > 0.0
+    integ = np.trapezoid(ct, r.tau)
+    assert abs(integ - r.spinChi_iv[0, 0].real) < 2e-3 * abs(integ) and abs(r.spinChi_iv[0, 0].imag) < 1e-12
+    if r.zeta == 1.0 and abs(r.magz[0]) < 1e-9:
+        assert abs(ct[0] - r.sz2[0, 0]) < 1e-6
+    # every chain is normalised: sum_j Z(1,j)^2 = 1, and its norm is |S_z gs|
+    for c in r.chi_chains:
+        lam, Z = oracle.eigh_tridiag(c["alfa"], c["beta"])
+        assert abs((Z[0] ** 2).sum() - 1.0) < 1e-10
+    # two orbitals: total row filled, chi_tot(0) from the squared-norm quirk is reproducible and positive
+    p2 = params(oracle, Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.0, jh=0.2, Lmats=16, Lreal=8, beta=30.0, chispin_flag=True, Ltau=50,
+                lanc_dim_threshold=16)
+    r2 = oracle.ed_solve(p2, oracle.init_bath(p2))
+    assert r2.spinChi_tau.shape[0] == 3 and r2.spinChi_tau[2, 0] > 0.0
+    assert np.abs(r2.spinChi_tau - r2.spinChi_tau[:, ::-1]).max() < 1e-12
+
+
 def test_ed_solve_arpack_and_lanczos_methods_agree(oracle):
     pa = oracle.Params(Norb=1, Nbath=4, Lmats=32, Lreal=32)          # reference defaults: arpack, 6 states/sector
     pl = params(oracle, Norb=1, Nbath=4, Lmats=32, Lreal=32)
