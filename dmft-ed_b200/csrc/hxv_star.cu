@@ -1043,27 +1043,34 @@ k_star_up3(StarKParams P, SlabMap Mpar, int accumulate, int64_t dim_dw, int64_t 
             int64_t r0;
             const int gc = rows_of(i, r0);
             const uint32_t fb = bfy + 8 * sy;
-            // accumulate == 0 (the result overwrites y): only the first and last 16 bytes of the y segment are loaded --
-            // they may hold an element of the neighbouring block, which the store must put back unchanged
-            const uint32_t ybytes = accumulate ? (uint32_t)ncopy * 8u : (ncopy > 2 ? 32u : 16u);
-            mbar_expect_tx(fb, (uint32_t)gc * ybytes);
+            // accumulate == 0 (the result overwrites y): nothing is loaded -- the barrier only hands the buffer over (the copy
+            // engine has finished reading the previous result, see the steady-state loop)
+            if (!accumulate) { mbar_arrive(fb); return; }
+            mbar_expect_tx(fb, (uint32_t)gc * (uint32_t)ncopy * 8u);
             for (int g = 0; g < gc; g++) {
                 const uint32_t yd = ybuf + (uint32_t)sy * stageb + (uint32_t)g * rowb;
-                if (accumulate) {
-                    for_segments(r0 + g, [&](const double *, double *ys, int rel, int cnt) { bulk_g2s(yd + (uint32_t)rel * 8u, ys, (uint32_t)cnt * 8u, fb); });
-                } else {
-                    bulk_g2s(yd, y_elem(r0 + g, colb), 16u, fb);
-                    if (ncopy > 2) bulk_g2s(yd + (uint32_t)(ncopy - 2) * 8u, y_elem(r0 + g, colb + ncopy - 2), 16u, fb);
-                }
+                for_segments(r0 + g, [&](const double *, double *ys, int rel, int cnt) { bulk_g2s(yd + (uint32_t)rel * 8u, ys, (uint32_t)cnt * 8u, fb); });
             }
         };
         auto store_tile = [&](int i) {
             if (lane != 0) return;
             int64_t r0;
             const int gc = rows_of(i, r0);
+            // accumulate != 0: the image holds the loaded neighbours, the whole (16-byte aligned) range goes back.
+            // accumulate == 0: a 16-byte pair shared with the neighbouring block (first pair when the block starts at an odd
+            // column, last pair when it ends at an even one) must not be stored as a pair: the bulk range shrinks to the
+            // interior and the block's own edge element is written with an ordinary 8-byte store.
+            const bool tail = ncopy > lead + size;
             for (int g = 0; g < gc; g++) {
                 const uint32_t src = ybuf + (uint32_t)(i % nys) * stageb + (uint32_t)g * rowb;
-                for_segments(r0 + g, [&](const double *, double *yd, int rel, int cnt) { bulk_s2g(yd, src + (uint32_t)rel * 8u, (uint32_t)cnt * 8u); });
+                for_segments(r0 + g, [&](const double *, double *yd, int rel, int cnt) {
+                    int lo = rel, hi = rel + cnt;
+                    if (!accumulate) {
+                        if (lead && lo == 0) { lo = 2 < hi ? 2 : hi; yd[1 - rel] = lds64(src + 8u); }
+                        if (tail && hi == ncopy) { hi = ncopy - 2 > lo ? ncopy - 2 : lo; yd[ncopy - 2 - rel] = lds64(src + (uint32_t)(ncopy - 2) * 8u); }
+                    }
+                    if (hi > lo) bulk_s2g(yd + (lo - rel), src + (uint32_t)lo * 8u, (uint32_t)(hi - lo) * 8u);
+                });
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         };
