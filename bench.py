@@ -13,9 +13,13 @@ workload (default: BASELINE config 4 -- Norb=2, Nbath=7, Ns=16, half-filling sec
           bandwidth (MEASURED_PEAKS.json).
 `cpu_baseline` / `--impl reference` = the CPU oracle (literal C restatement of directMatVec_cc; the Fortran
           reference cannot be built in this image) on all host cores over a bounded row sample.
-With N>1 (torchrun) the default is ONE sector vector sharded by up-spin column blocks over the ranks (down term
-local, up term through two NCCL all-to-all transposes per H*v) -> "scaling": "strong"; `--mode chains` runs
-independent H*v streams per rank instead (the GF-chain level of parallelism, no collective) -> "weak".
+With N>1 (torchrun) the default is ONE sector vector sharded by up-spin column blocks over the ranks (BASELINE config 4:
+"direct H*v sharded over 1/2/4/8 GPUs") -> "scaling": "strong".  The down term is local; the up term exchanges rows either
+inside the copy-engine up kernel over CUDA-IPC peer memory (`--exchange peer`, default up to 4 ranks) or through two NCCL
+all-to-all transposes (`--exchange nccl`, default at 8 ranks).  The same line carries `independent_chains` (the other
+level of parallelism of the north star measured in the same run: one whole vector per GPU, no collective, weak scaling;
+`--mode chains` makes it the primary value) and an `e2e` leg (pinned host shards -> device, sharded Lanczos steps,
+alpha/beta -> host).
 """
 from __future__ import annotations
 
