@@ -27,8 +27,6 @@
 
 uint64_t edgpu_binom(int n, int k);
 
-static constexpr int kMaxStarCfg = 1024;      // 2^(Nbath+1), Nbath <= 9
-static constexpr int kMaxH = 9;               // hops per star configuration <= Nbath
 static constexpr int kMaxBlocks = 4096;
 static constexpr int kBigBlock = 2048;        // up-blocks at least this large use the pipelined kernel
 static constexpr int kDotSlots = 16384;       // capacity of ctx->d_dotpart (per-CTA partial sums of the fused <x, H x>)
@@ -288,7 +286,6 @@ struct StarKParams {
 };
 
 static constexpr int kNT = 512;         // threads per CTA of the tiled kernels
-static constexpr int kVec = 4;          // outputs per thread and outer step (rows in the up pass, columns in the down pass)
 
 // Shared-memory star tables of one block (all NORB stars): per configuration i of star a
 //   s_off[a][i][h]  byte offset of the h-th source inside a [element][2] double2 plane: (j - i) * stride_a * 16
@@ -694,7 +691,7 @@ k_star_up(StarKParams P, SlabMap Mpar, int64_t dim_dw, int64_t ld, int block_ind
           const double *__restrict__ estar, const double *__restrict__ e_dw, const uint32_t *__restrict__ cfg_dw,
           const double *__restrict__ xtab, const double *__restrict__ x, double *__restrict__ y, int maxD)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SlabMap s_M;
     if (SLAB) {
         if (threadIdx.x == 0) s_M = Mpar;
@@ -1164,7 +1161,7 @@ k_star_dw(StarKParams P, int64_t dim_up, int64_t ld, int block_index, int SP,
           const int16_t *__restrict__ hopd, const uint8_t *__restrict__ hopc, const double *__restrict__ hopv,
           const double *__restrict__ x, double *__restrict__ y, int maxD, int pf_dist)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const StarBlock B = blocks[block_index];
     const int R = B.size;
     const int tile_rows = SP * R;
@@ -1530,7 +1527,7 @@ static Dw3Kernel pick_dw3(int NH)
 // griddepcontrol.wait) while the previous launch on the stream drains
 static void pdl_config(edgpu_ctx *ctx, cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, unsigned grid, unsigned block, size_t smem)
 {
-    memset(&cfg, 0, sizeof(cfg));
+    cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     // measured on cfg4 (same box, A/B): 491 matvec/s with, 511 without -- the early-resident CTAs of the next launch cost

@@ -176,22 +176,6 @@ __global__ void k_lanc_alpha(const double *__restrict__ partials, int n, const d
     }
 }
 
-// w_new = u/nc - (bp/no) w_old - (a/nc) w_cur, written over w_old ; partial |w_new|^2
-__global__ void __launch_bounds__(kRedThreads) k_lanc_c(double *__restrict__ old, const double *__restrict__ u,
-                                                        const double *__restrict__ cur, const double *__restrict__ p_bprev,
-                                                        const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
-                                                        const double *__restrict__ p_a, int64_t n, double *__restrict__ partials)
-{
-    const double nc = *p_ncur, c_old = *p_bprev / *p_nold, c_cur = *p_a / nc;
-    double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double t = u[i] / nc - c_old * old[i] - c_cur * cur[i];
-        old[i] = t;
-        acc += t * t;
-    }
-    block_store_partial(acc, partials + blockIdx.x);
-}
-
 // a = <a_vec, b_vec> / (*nrm)^2 in one launch
 __global__ void __launch_bounds__(kRedThreads) k_dot_alpha(const double *__restrict__ a, const double *__restrict__ b, int64_t n,
                                                            double *__restrict__ partials, const double *__restrict__ nrm,
@@ -204,7 +188,7 @@ __global__ void __launch_bounds__(kRedThreads) k_dot_alpha(const double *__restr
     finalize_by_last_block(partials, gridDim.x, 2, nrm, out, ticket);
 }
 
-// k_lanc_c + the final sqrt(sum) in one launch
+// w_new = u/nc - (bp/no) w_old - (a/nc) w_cur, written over w_old ; b = sqrt(sum w_new^2), one launch
 __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict__ old, const double *__restrict__ u,
                                                              const double *__restrict__ cur, const double *__restrict__ p_bprev,
                                                              const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
