@@ -44,7 +44,7 @@ class ed_input(C.Structure):
                 ("lanc_niter", C.c_int32), ("lanc_ngfiter", C.c_int32), ("lanc_tolerance", C.c_double),
                 ("lanc_dim_threshold", C.c_int32), ("ed_twin", C.c_int32), ("ed_sparse_H", C.c_int32),
                 ("ed_verbose", C.c_int32), ("gpu_layout", C.c_int32), ("gpu_hxv_kernel", C.c_int32),
-                ("chispin_flag", C.c_int32), ("Ltau", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("chispin_flag", C.c_int32), ("Ltau", C.c_int32), ("chidens_flag", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 # every symbol declared in include/edgpu.h and include/ed_b200.h (checked by tests/test_abi.py)
@@ -54,7 +54,7 @@ EDGPU_SYMBOLS = [
     "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
-    "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_apply_sz", "edgpu_observables",
+    "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_apply_sz", "edgpu_apply_n", "edgpu_observables",
     "edgpu_shard_ld", "edgpu_shard_hxv_dw", "edgpu_shard_hxv_up", "edgpu_shard_hxv_up_slabs", "edgpu_shard_perm",
     "edgpu_shard_hxv_up_peers", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_ipc_export", "edgpu_ipc_open", "edgpu_ipc_close", "edgpu_copy_async",
     "edgpu_bench_hxv", "edgpu_device_info", "edgpu_sync",
@@ -63,7 +63,7 @@ ED_SYMBOLS = [
     "ed_input_defaults", "ed_get_bath_dimension", "ed_init_solver", "ed_finalize_solver", "ed_last_error", "ed_solve",
     "ed_get_sigma_matsubara", "ed_get_sigma_real", "ed_get_gimp_matsubara", "ed_get_gimp_real",
     "ed_get_g0imp_matsubara", "ed_get_g0imp_real", "ed_get_dens", "ed_get_dens_up", "ed_get_dens_dw", "ed_get_docc",
-    "ed_get_mag", "ed_get_sz2_n2", "ed_get_grids", "ed_get_spinchi", "ed_get_state_count", "ed_get_state", "ed_get_state_vector",
+    "ed_get_mag", "ed_get_sz2_n2", "ed_get_grids", "ed_get_spinchi", "ed_get_denschi", "ed_get_state_count", "ed_get_state", "ed_get_state_vector",
     "ed_get_sector_energy", "ed_get_sector_nlanc", "ed_get_chain_count", "ed_get_chain", "ed_set_sectors_mask", "ed_get_timings",
     "ed_host_eigh", "ed_host_eigh_tridiag",
 ]
@@ -121,6 +121,7 @@ def lib():
     L.edgpu_lanczos_tridiag.argtypes = [vp, vp, C.c_int32, C.c_double, dp, dp, i32p]
     L.edgpu_apply_c.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, dp]
     L.edgpu_apply_sz.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, dp]
+    L.edgpu_apply_n.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, dp]
     L.edgpu_observables.argtypes = [vp, vp, C.c_double] + [dp] * 8
     L.edgpu_shard_ld.argtypes = [vp, i64p]
     L.edgpu_shard_hxv_dw.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
@@ -154,6 +155,7 @@ def lib():
     L.ed_get_sz2_n2.argtypes = [vp, dp, dp, dp]
     L.ed_get_grids.argtypes = [vp, dp, dp]
     L.ed_get_spinchi.argtypes = [vp, dp, dp, dp, dp, dp, i32p]
+    L.ed_get_denschi.argtypes = [vp, dp, dp, dp, dp, dp, dp]
     L.ed_get_state_count.argtypes = [vp, i32p, dp, dp]
     L.ed_get_state.argtypes = [vp, C.c_int32, dp, i32p, i32p]
     L.ed_get_state_vector.argtypes = [vp, C.c_int32, dp, C.c_int64]
@@ -464,6 +466,20 @@ class Solver:
         self.check(lib().ed_get_spinchi(self.h, C.cast(iv.ctypes.data, dp), _p(ct), C.cast(cw.ctypes.data, dp),
                                         _p(vm), _p(tau), C.byref(lt)))
         return iv, ct, cw, vm, tau
+
+    def denschi(self):
+        """(chi_iv[Norb,Norb,0:Lmats], chi_tau[Norb,Norb,0:Ltau], chi_w[Norb,Norb,Lreal], tot_iv, tot_tau, tot_w) of build_chi_dens
+        (diagonal and total channels)."""
+        lt = C.c_int32()
+        self.check(lib().ed_get_spinchi(self.h, None, None, None, None, None, C.byref(lt)))
+        n, lm, lr, ltau = self.inp.Norb, self.inp.Lmats, self.inp.Lreal, lt.value
+        iv = np.zeros((n, n, lm + 1), dtype=np.complex128, order="F")
+        ct = np.zeros((n, n, ltau + 1), order="F")
+        cw = np.zeros((n, n, lr), dtype=np.complex128, order="F")
+        tiv, tt, tw = np.zeros(lm + 1, dtype=np.complex128), np.zeros(ltau + 1), np.zeros(lr, dtype=np.complex128)
+        self.check(lib().ed_get_denschi(self.h, C.cast(iv.ctypes.data, dp), _p(ct), C.cast(cw.ctypes.data, dp),
+                                        C.cast(tiv.ctypes.data, dp), _p(tt), C.cast(tw.ctypes.data, dp)))
+        return iv, ct, cw, tiv, tt, tw
 
     def states(self):
         n, z, e = C.c_int32(), C.c_double(), C.c_double()

@@ -62,6 +62,8 @@ struct ed_solver {
     int Ltau = 0;
     std::vector<double> vm, tau, spinChi_tau;
     std::vector<cplx> spinChi_iv, spinChi_w;
+    std::vector<double> densChi_tau, densChi_tot_tau;            // (ED_SETUP.f90:346-354)
+    std::vector<cplx> densChi_iv, densChi_w, densChi_tot_iv, densChi_tot_w;
     double timings[4] = {0, 0, 0, 0};
 };
 
@@ -96,7 +98,7 @@ extern "C" void ed_input_defaults(ed_input *in)
     in->gs_threshold = 1e-9; in->hwband = 2.0;
     in->lanc_method = 0; in->lanc_nstates_sector = 6; in->lanc_nstates_total = 1;
     in->lanc_niter = 512; in->lanc_ngfiter = 200; in->lanc_tolerance = 1e-12; in->lanc_dim_threshold = 256;
-    in->chispin_flag = 0; in->Ltau = 1000;
+    in->chispin_flag = 0; in->Ltau = 1000; in->chidens_flag = 0;
     in->ed_twin = 0; in->ed_sparse_H = 1; in->ed_verbose = 3;
 }
 
@@ -541,6 +543,80 @@ static int build_chi_spin(ed_solver *s)
     return 0;
 }
 
+// add_to_lanczos_densChi / _tot (ED_GF_CHIDENS.f90:692-765, 876-948), T = 0: both signs.  iv/tau/w point at the channel's
+// first element, `stride` is the distance between consecutive frequencies.
+static void add_to_lanczos_denschi(ed_solver *s, double vnorm2, double Ei, const std::vector<double> &alanc,
+                                   const std::vector<double> &blanc, cplx *iv, double *tau_out, cplx *w_out, size_t stride)
+{
+    const ed_input &in = s->in;
+    const int nlanc = (int)alanc.size();
+    const double beta = in.beta;
+    const double pesoF = vnorm2 / s->zeta;
+    std::vector<double> d(alanc), e(nlanc, 0.0), Z((size_t)nlanc * nlanc, 0.0);
+    for (int i = 1; i < nlanc; i++) e[i] = blanc[i];
+    for (int i = 0; i < nlanc; i++) Z[i + (size_t)nlanc * i] = 1.0;
+    host_tql2(nlanc, d.data(), e.data(), Z.data());                                  // tql2, not eigh (:713-718)
+    for (int isign = 1; isign >= -1; isign -= 2)
+        for (int j = 0; j < nlanc; j++) {
+            const double dE = d[j] - Ei;
+            const double peso = pesoF * Z[(size_t)nlanc * j] * Z[(size_t)nlanc * j];
+            const double ex = std::exp(-beta * dE);
+            if (isign == 1) iv[0] += (beta * dE < 1e-1) ? -peso * beta : peso * (ex - 1.0) / dE;      // :727-731 (sic)
+            else            iv[0] += (beta * dE < 1e-1) ? peso * beta : peso * (1.0 - ex) / dE;       // :748-752
+            for (int i = 1; i <= in.Lmats; i++)
+                iv[stride * i] += isign == 1 ? peso * (ex - 1.0) / (cplx(0.0, s->vm[i]) - dE) : peso * (1.0 - ex) / (cplx(0.0, s->vm[i]) + dE);
+            for (int i = 0; i <= s->Ltau; i++)
+                tau_out[stride * i] += isign == 1 ? peso * std::exp(-s->tau[i] * dE) : peso * std::exp(-(beta - s->tau[i]) * dE);
+            for (int i = 0; i < in.Lreal; i++)
+                w_out[stride * i] += isign == 1 ? peso * (ex - 1.0) / (cplx(s->wr[i], in.eps) - dE) : peso * (1.0 - ex) / (cplx(s->wr[i], in.eps) + dE);
+        }
+}
+
+// build_chi_dens (ED_GF_CHIDENS.f90:21-66), the channels with real seeds: diagonal (:90-169) and total (:191-269).
+static int build_chi_dens(ed_solver *s)
+{
+    const ed_input &in = s->in;
+    const size_t nn = (size_t)in.Norb * in.Norb;
+    s->densChi_iv.assign(nn * (in.Lmats + 1), cplx(0, 0));
+    s->densChi_tau.assign(nn * (s->Ltau + 1), 0.0);
+    s->densChi_w.assign(nn * in.Lreal, cplx(0, 0));
+    s->densChi_tot_iv.assign(in.Lmats + 1, cplx(0, 0));
+    s->densChi_tot_tau.assign(s->Ltau + 1, 0.0);
+    s->densChi_tot_w.assign(in.Lreal, cplx(0, 0));
+    if (!in.chidens_flag) return 0;
+    const int nchan = in.Norb + (in.Norb > 1 ? 1 : 0);
+    for (int ic = 0; ic < nchan; ic++) {
+        const bool tot = ic == in.Norb;
+        for (size_t istate = 0; istate < s->states.size(); istate++) {
+            EdState &st = s->states[istate];
+            int64_t idim = 0;
+            edgpu_sector_dim(st.sec, &idim, nullptr, nullptr);
+            edgpu_vec *vv = nullptr;
+            GPU_TRY(s, edgpu_vec_alloc(st.sec, &vv));
+            double nrm = 0;
+            int rc = edgpu_apply_n(st.sec, tot ? 0 : ic + 1, st.vec, vv, 1, &nrm);
+            const int nlanc = (int)std::min<int64_t>(idim, in.lanc_ngfiter);
+            std::vector<double> alfa(nlanc, 0.0), beta(nlanc, 0.0);
+            int nused = 0;
+            if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_build_csr(st.sec);
+            if (!rc && nrm > 0.0) rc = edgpu_lanczos_tridiag(st.sec, vv, nlanc, 1e-13, alfa.data(), beta.data(), &nused);
+            if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_drop_csr(st.sec);
+            edgpu_vec_free(vv);
+            if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
+            if (nrm <= 0.0) continue;
+            if (tot) add_to_lanczos_denschi(s, nrm * nrm, st.e, alfa, beta, s->densChi_tot_iv.data(), s->densChi_tot_tau.data(), s->densChi_tot_w.data(), 1);
+            else {
+                const size_t o = (size_t)ic + (size_t)in.Norb * ic;                  // (iorb,iorb), column-major
+                add_to_lanczos_denschi(s, nrm * nrm, st.e, alfa, beta, s->densChi_iv.data() + o, s->densChi_tau.data() + o, s->densChi_w.data() + o, nn);
+            }
+        }
+    }
+    for (auto &v : s->densChi_tau) v /= s->zeta;                                     // :62-64 (the total channel is not divided again)
+    for (auto &v : s->densChi_w) v /= s->zeta;
+    for (auto &v : s->densChi_iv) v /= s->zeta;
+    return 0;
+}
+
 static cplx delta_bath(const ed_solver *s, cplx x, int ispin, int iorb)
 {
     // delta_bath_mats_main, normal/normal (ED_BATH_FUNCTIONS.f90:245-256)
@@ -613,6 +689,7 @@ extern "C" int ed_solve(ed_solver *s, const double *bath, int32_t bath_len, cons
     double t2 = now_s();
     build_sigma(s);
     if (int rc = build_chi_spin(s)) return rc;              // buildchi_impurity (ED_MAIN.f90:274)
+    if (int rc = build_chi_dens(s)) return rc;
     double t3 = now_s();
     if (int rc = observables(s)) return rc;                 // observables_impurity
     double t4 = now_s();
@@ -670,6 +747,17 @@ extern "C" int ed_get_spinchi(const ed_solver *s, double *chi_iv, double *chi_ta
     if (vm) copy_d(s->vm, vm);
     if (tau) copy_d(s->tau, tau);
     if (ltau) *ltau = s->Ltau;
+    return 0;
+}
+extern "C" int ed_get_denschi(const ed_solver *s, double *chi_iv, double *chi_tau, double *chi_w, double *tot_iv, double *tot_tau, double *tot_w)
+{
+    if (!s || s->densChi_iv.empty()) return 1;
+    if (chi_iv) copy_c(s->densChi_iv, chi_iv);
+    if (chi_tau) copy_d(s->densChi_tau, chi_tau);
+    if (chi_w) copy_c(s->densChi_w, chi_w);
+    if (tot_iv) copy_c(s->densChi_tot_iv, tot_iv);
+    if (tot_tau) copy_d(s->densChi_tot_tau, tot_tau);
+    if (tot_w) copy_c(s->densChi_tot_w, tot_w);
     return 0;
 }
 extern "C" int ed_get_state_count(const ed_solver *s, int32_t *n, double *zeta, double *egs)

@@ -161,20 +161,35 @@ extern "C" int edgpu_apply_c(edgpu_sector *si, edgpu_sector *so, int32_t isite, 
 
 // ---- diagonal seed operators of the susceptibility chains (ED_GF_CHISPIN.f90:93-100, 198-205) ----------------------
 // out = 1/2 (n_up - n_dw) in   over the impurity levels selected by `mask` (one orbital, or all of them for S_z^tot)
+// charge seeds (ED_GF_CHIDENS.f90:126-133, 227-234): out = (n_up + n_dw) in            (cdw = +1, scale = 1)
 __global__ void __launch_bounds__(256)
-k_apply_sz(uint32_t mask, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t *__restrict__ cfg_up,
+k_apply_sz(uint32_t mask, double cdw, double scale, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t *__restrict__ cfg_up,
            const uint32_t *__restrict__ cfg_dw, const double *__restrict__ in, double *__restrict__ out)
 {
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ru >= dim_up) return;
     const int nu = __popc(cfg_up[ru] & mask);
     for (int64_t rd = blockIdx.y; rd < dim_dw; rd += gridDim.y) {
-        const double sgn = (double)nu - (double)__popc(cfg_dw[rd] & mask);
-        out[rd * ld + ru] = 0.5 * sgn * in[rd * ld + ru];
+        const double sgn = (double)nu + cdw * (double)__popc(cfg_dw[rd] & mask);
+        out[rd * ld + ru] = scale * sgn * in[rd * ld + ru];
     }
 }
 
+static int apply_diag_seed(edgpu_sector *s, int32_t iorb, double cdw, double scale, const edgpu_vec *in, edgpu_vec *out,
+                           int32_t normalise, double *norm);
+
 extern "C" int edgpu_apply_sz(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm)
+{
+    return apply_diag_seed(s, iorb, -1.0, 0.5, in, out, normalise, norm);
+}
+
+extern "C" int edgpu_apply_n(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm)
+{
+    return apply_diag_seed(s, iorb, 1.0, 1.0, in, out, normalise, norm);
+}
+
+static int apply_diag_seed(edgpu_sector *s, int32_t iorb, double cdw, double scale, const edgpu_vec *in, edgpu_vec *out,
+                           int32_t normalise, double *norm)
 {
     if (!s || !in || !out || in->s != s || out->s != s) return s ? edgpu_fail(s->ctx, "edgpu_apply_sz: bad handles") : 1;
     edgpu_ctx *ctx = s->ctx;
@@ -183,7 +198,7 @@ extern "C" int edgpu_apply_sz(edgpu_sector *s, int32_t iorb, const edgpu_vec *in
     if (in->d == out->d) return edgpu_fail(ctx, "edgpu_apply_sz: in-place application is not allowed");
     const uint32_t mask = iorb == 0 ? (1u << norb) - 1u : 1u << (iorb - 1);
     dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)(s->dim_dw < 32768 ? s->dim_dw : 32768));
-    k_apply_sz<<<grid, 256, 0, ctx->stream>>>(mask, s->dim_up, s->dim_dw, s->ld, s->up->cfg, s->dw->cfg, in->d, out->d);
+    k_apply_sz<<<grid, 256, 0, ctx->stream>>>(mask, cdw, scale, s->dim_up, s->dim_dw, s->ld, s->up->cfg, s->dw->cfg, in->d, out->d);
     CUDA_TRY(ctx, cudaGetLastError());
     if (int rc = vec_dot(ctx, out->d, out->d, s->nalloc, ctx->d_scal)) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -43,7 +43,8 @@ typedef struct {
     int32_t gpu_hxv_kernel;         /* edgpu_params.hxv_kernel (0 auto) */
     int32_t chispin_flag;           /* CHISPIN_FLAG (ED_INPUT_VARS.f90:156): build the spin susceptibility in ed_solve */
     int32_t Ltau;                   /* LTAU (ED_INPUT_VARS.f90:148,211): imaginary-time points, raised to int(beta) */
-    int32_t reserved[6];
+    int32_t chidens_flag;           /* CHIDENS_FLAG (ED_INPUT_VARS.f90:157): charge susceptibility, diagonal + total channels */
+    int32_t reserved[5];
 } ed_input;
 
 void ed_input_defaults(ed_input *in);
@@ -86,6 +87,12 @@ int ed_get_grids(const ed_solver *s, double *wm, double *wr);
  * chi_iv (Norb+1, 0:Lmats) complex, chi_tau (Norb+1, 0:Ltau) real, chi_w (Norb+1, Lreal) complex, column-major;
  * vm(0:Lmats) bosonic Matsubara frequencies, tau(0:Ltau).  ltau returns the effective Ltau. */
 int ed_get_spinchi(const ed_solver *s, double *chi_iv, double *chi_tau, double *chi_w, double *vm, double *tau, int32_t *ltau);
+/* Charge susceptibility <n_a(tau) n_a(0)> (build_chi_dens, ED_GF_CHIDENS.f90:21-66), chidens_flag != 0: the channels whose
+ * seeds are real -- densChi(a,a) (lanc_ed_build_densChi_diag_c :90-169) and, for Norb > 1, densChi_tot (:191-269).
+ * The inter-orbital and spin-mixed channels (:291-673) use complex seeds (n_a + i n_b)|gs> and are NOT built: their
+ * entries stay zero.  chi_iv (Norb,Norb,0:Lmats) complex, chi_tau (Norb,Norb,0:Ltau) real, chi_w (Norb,Norb,Lreal)
+ * complex; tot_iv (0:Lmats) complex, tot_tau (0:Ltau) real, tot_w (Lreal) complex.  Grids as in ed_get_spinchi. */
+int ed_get_denschi(const ed_solver *s, double *chi_iv, double *chi_tau, double *chi_w, double *tot_iv, double *tot_tau, double *tot_w);
 
 /* state_list after diagonalize_impurity (ED_DIAG.f90:220-236, 383-416): number of kept states, zeta_function,
  * and per state: energy, nup, ndw. */

@@ -116,6 +116,8 @@ int edgpu_apply_c(edgpu_sector *s_in, edgpu_sector *s_out, int32_t isite, int32_
  * norm = sqrt(<out|out>) (before normalisation); normalise != 0 scales out to unit norm.  The chain itself is
  * edgpu_lanczos_tridiag on `out`. */
 int edgpu_apply_sz(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm);
+/* Seed of the charge-susceptibility chains (ED_GF_CHIDENS.f90:126-136, 227-237): out = (n_up + n_dw) |in>, same conventions. */
+int edgpu_apply_n(edgpu_sector *s, int32_t iorb, const edgpu_vec *in, edgpu_vec *out, int32_t normalise, double *norm);
 
 /* observables_impurity core (ED_OBSERVABLES.f90:127-158): accumulates (+=) like the reference.
  * dens,dens_up,dens_dw,docc,magz: [Norb]; sz2,n2: [Norb*Norb] column-major; s2tot scalar. */

@@ -130,6 +130,7 @@ class Params:
     ed_sparse_H: bool = True
     chispin_flag: bool = False
     Ltau: int = 1000
+    chidens_flag: bool = False
 
     @property
     def Ns(self):
@@ -346,6 +347,12 @@ class Result:
     spinChi_tau: np.ndarray | None = None
     spinChi_w: np.ndarray | None = None
     chi_chains: list = field(default_factory=list)
+    densChi_iv: np.ndarray | None = None
+    densChi_tau: np.ndarray | None = None
+    densChi_w: np.ndarray | None = None
+    densChi_tot_iv: np.ndarray | None = None
+    densChi_tot_tau: np.ndarray | None = None
+    densChi_tot_w: np.ndarray | None = None
 
 
 def sector_index(Ns, nup, ndw):
@@ -551,6 +558,76 @@ def build_chi_spin(model: Model, res: Result):
     return res
 
 
+def apply_n(Ns, Norb, iorb, smap, gs):
+    """Seed of the charge-susceptibility chain (ED_GF_CHIDENS.f90:126-133; iorb = None: total, :227-234):
+    vvinit(m) = (n_up + n_dw) gs(m) over the impurity level(s)."""
+    words = np.asarray(smap, dtype=np.uint64)
+    orbs = range(Norb) if iorb is None else [iorb]
+    sgn = np.zeros(words.size)
+    for a in orbs:
+        sgn += ((words >> np.uint64(a)) & np.uint64(1)).astype(float) + ((words >> np.uint64(a + Ns)) & np.uint64(1)).astype(float)
+    return sgn * gs
+
+
+def add_to_lanczos_denschi(p: Params, res: Result, vnorm2, Ei, alanc, blanc, isign, iv, tau_out, w_out):
+    """add_to_lanczos_densChi / _tot (ED_GF_CHIDENS.f90:692-765, 876-948), T = 0; iv/tau_out/w_out are views of the channel.
+    The sign of the static isign=+1 term (:727-731) is the reference's."""
+    beta = p.beta
+    pesoF = vnorm2 / res.zeta
+    lam, Z = tql2(np.asarray(alanc, dtype=float), np.asarray(blanc, dtype=float)[1:])
+    for j in range(len(alanc)):
+        dE = lam[j] - Ei
+        peso = pesoF * Z[0, j] * Z[0, j]
+        ex = np.exp(-beta * dE)
+        if isign == 1:
+            iv[0] += -peso * beta if beta * dE < 1e-1 else peso * (ex - 1.0) / dE
+            iv[1:] += peso * (ex - 1.0) / (1j * res.vm[1:] - dE)
+            tau_out[:] += peso * np.exp(-res.tau * dE)
+            w_out[:] += peso * (ex - 1.0) / ((res.wr + 1j * p.eps) - dE)
+        else:
+            iv[0] += peso * beta if beta * dE < 1e-1 else peso * (1.0 - ex) / dE
+            iv[1:] += peso * (1.0 - ex) / (1j * res.vm[1:] + dE)
+            tau_out[:] += peso * np.exp(-(beta - res.tau) * dE)
+            w_out[:] += peso * (1.0 - ex) / ((res.wr + 1j * p.eps) + dE)
+
+
+def build_chi_dens(model: Model, res: Result):
+    """build_chi_dens (ED_GF_CHIDENS.f90:21-66), the channels with REAL seeds: densChi(a,a) (lanc_ed_build_densChi_diag_c
+    :90-169) and densChi_tot for Norb > 1 (:191-269).  The inter-orbital / spin-mixed channels (:291-673) seed with
+    (n_a + i n_b)|gs> (complex vectors) and are not restated: their entries stay zero."""
+    p = model.p
+    Ns = p.Ns
+    Ltau = res.tau.size - 1
+    res.densChi_iv = np.zeros((p.Norb, p.Norb, p.Lmats + 1), dtype=np.complex128)
+    res.densChi_tau = np.zeros((p.Norb, p.Norb, Ltau + 1))
+    res.densChi_w = np.zeros((p.Norb, p.Norb, p.Lreal), dtype=np.complex128)
+    res.densChi_tot_iv = np.zeros(p.Lmats + 1, dtype=np.complex128)
+    res.densChi_tot_tau = np.zeros(Ltau + 1)
+    res.densChi_tot_w = np.zeros(p.Lreal, dtype=np.complex128)
+    if not p.chidens_flag:
+        return res
+    chans = list(range(p.Norb)) + ([None] if p.Norb > 1 else [])
+    for iorb in chans:
+        for st in res.states:
+            smap = build_sector(Ns, st.nup, st.ndw)
+            vv = apply_n(Ns, p.Norb, iorb, smap, st.vec)
+            n2 = float(np.vdot(vv, vv).real)
+            if n2 <= 0.0:
+                continue
+            nlanc = min(smap.size, p.lanc_ngfiter)
+            alfa, beta, nused = lanc_tridiag(model, smap, vv / np.sqrt(n2), nlanc)
+            for isign in (1, -1):
+                if iorb is None:
+                    add_to_lanczos_denschi(p, res, n2, st.e, alfa, beta, isign, res.densChi_tot_iv, res.densChi_tot_tau, res.densChi_tot_w)
+                else:
+                    add_to_lanczos_denschi(p, res, n2, st.e, alfa, beta, isign, res.densChi_iv[iorb, iorb], res.densChi_tau[iorb, iorb],
+                                           res.densChi_w[iorb, iorb])
+    res.densChi_tau /= res.zeta                                                # :62-64 (not the total channel)
+    res.densChi_w /= res.zeta
+    res.densChi_iv /= res.zeta
+    return res
+
+
 def delta_bath(model: Model, x, ispin, iorb):
     """delta_bath_mats_main, normal/normal (ED_BATH_FUNCTIONS.f90:245-256)."""
     p = model.p
@@ -607,6 +684,7 @@ def ed_solve(p: Params, bath: np.ndarray, hloc=None, sectors=None) -> Result:
     build_gf(model, res)
     build_sigma(model, res)
     build_chi_spin(model, res)
+    build_chi_dens(model, res)
     observables(model, res)
     res.model = model
     return res

@@ -140,6 +140,7 @@ def test_oracle_reproduces_golden_chi(oracle):
         r = oracle.ed_solve(p, oracle.init_bath(p))
         assert np.abs(r.spinChi_tau - GC[name + "_chi_tau"]).max() < 1e-10
         assert np.abs(r.spinChi_iv - GC[name + "_chi_iv"]).max() < 1e-9 * max(1.0, np.abs(GC[name + "_chi_iv"]).max())
+        assert np.abs(r.densChi_tau - GC[name + "_dchi_tau"]).max() < 1e-9 * max(1.0, np.abs(GC[name + "_dchi_tau"]).max())
 
 
 @pytest.mark.gpu
@@ -148,10 +149,14 @@ def test_gpu_reproduces_golden_chi(edb):
     for name, kw in _chi_cases():
         kw = dict(kw)
         kw["chispin_flag"] = 1
+        kw["chidens_flag"] = 1
         inp = edb.default_input(ed_sparse_H=0, **kw)
         sol = edb.Solver(inp)
         sol.solve()
         iv, ct, cw, vm, tau = sol.spinchi()
         assert np.abs(ct - GC[name + "_chi_tau"]).max() < 1e-8
         assert np.abs(iv - GC[name + "_chi_iv"]).max() < 1e-8 * max(1.0, np.abs(GC[name + "_chi_iv"]).max())
+        div, dct, dcw, tiv, tt, tw = sol.denschi()
+        assert np.abs(dct - GC[name + "_dchi_tau"]).max() < 1e-8 * max(1.0, np.abs(GC[name + "_dchi_tau"]).max())
+        assert np.abs(tt - GC[name + "_dchi_tot_tau"]).max() < 1e-8 * max(1.0, np.abs(GC[name + "_dchi_tot_tau"]).max())
         sol.close()

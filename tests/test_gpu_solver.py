@@ -16,7 +16,7 @@ def run_pair(oracle, edb, sectors=None, sparse=0, **kw):
                             lanc_method=p.lanc_method, lanc_nstates_sector=p.lanc_nstates_sector,
                             lanc_ngfiter=p.lanc_ngfiter, lanc_niter=p.lanc_niter, lanc_dim_threshold=p.lanc_dim_threshold,
                             lanc_tolerance=p.lanc_tolerance, gs_threshold=p.gs_threshold, ed_sparse_H=sparse,
-                            chispin_flag=int(p.chispin_flag), Ltau=p.Ltau)
+                            chispin_flag=int(p.chispin_flag), Ltau=p.Ltau, chidens_flag=int(p.chidens_flag))
     sol = edb.Solver(inp)
     assert np.array_equal(sol.bath, bath)                         # init_dmft_bath mirror
     if sectors is not None:
@@ -112,6 +112,22 @@ def test_spin_susceptibility_matches_oracle(oracle, edb):
         sol.close()
 
 
+def test_charge_susceptibility_matches_oracle(oracle, edb):
+    """build_chi_dens, diagonal and total channels (ED_GF_CHIDENS.f90:90-169, 191-269): edgpu_apply_n seeds + GF chains."""
+    for kw in (dict(Norb=1, Nbath=4, chidens_flag=True, Ltau=200),
+               dict(Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, lanc_dim_threshold=64, chidens_flag=True, chispin_flag=True, Ltau=64)):
+        p, ref, sol = run_pair(oracle, edb, **kw)
+        compare(p, ref, sol)
+        iv, ct, cw, tiv, tt, tw = sol.denschi()
+        assert ct.shape == ref.densChi_tau.shape
+        assert np.abs(ct - ref.densChi_tau).max() < 1e-8 * max(1.0, np.abs(ref.densChi_tau).max())
+        assert np.abs(iv - ref.densChi_iv).max() < 1e-8 * max(1.0, np.abs(ref.densChi_iv).max())
+        assert np.abs(tt - ref.densChi_tot_tau).max() < 1e-8 * max(1.0, np.abs(ref.densChi_tot_tau).max())
+        assert np.abs(tiv - ref.densChi_tot_iv).max() < 1e-8 * max(1.0, np.abs(ref.densChi_tot_iv).max())
+        assert np.abs(cw - ref.densChi_w).max() < 1e-4 * max(1.0, np.abs(ref.densChi_w).max())
+        sol.close()
+
+
 def test_apply_sz_seed(oracle, edb):
     """edgpu_apply_sz against the literal seed loop (ED_GF_CHISPIN.f90:93-100, 198-205), both layouts."""
     import ctypes as C
@@ -128,4 +144,7 @@ def test_apply_sz_seed(oracle, edb):
             ref = oracle.apply_sz(p.Ns, p.Norb, None if iorb == 0 else iorb - 1, smap, g)
             assert np.abs(vout.download() - ref).max() < 1e-14
             assert abs(nrm.value - np.linalg.norm(ref)) < 1e-12
+            ctx.check(edb.lib().edgpu_apply_n(s.h, iorb, vin.h, vout.h, 0, C.byref(nrm)))
+            ref = oracle.apply_n(p.Ns, p.Norb, None if iorb == 0 else iorb - 1, smap, g)
+            assert np.abs(vout.download() - ref).max() < 1e-14
         vin.free(); vout.free(); s.free(); ctx.close()

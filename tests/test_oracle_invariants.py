@@ -198,6 +198,26 @@ def test_spin_susceptibility_invariants(oracle):
     assert np.abs(r2.spinChi_tau - r2.spinChi_tau[:, ::-1]).max() < 1e-12
 
 
+def test_charge_susceptibility_invariants(oracle):
+    """build_chi_dens restatement (ED_GF_CHIDENS.f90, diagonal and total channels): chi(tau) = chi(beta - tau); for a unique
+    ground state chi(tau = 0) = <n^2> + <n>^2 (the seed n|gs> keeps the weight <n>^2/<n^2> on |gs> itself, which the
+    isign = -1 branch adds back at dE = 0); the reference's static isign = +1 term carries the opposite sign, so
+    chi(i nu = 0) cancels; inter-orbital entries stay zero."""
+    p = params(oracle, Norb=1, Nbath=3, Lmats=32, Lreal=16, beta=40.0, chidens_flag=True, Ltau=400, lanc_dim_threshold=8)
+    r = oracle.ed_solve(p, oracle.init_bath(p))
+    ct = r.densChi_tau[0, 0]
+    assert np.abs(ct - ct[::-1]).max() < 1e-12
+    if r.zeta == 1.0:
+        assert abs(ct[0] - (r.n2[0, 0] + r.dens[0] ** 2)) < 1e-6
+    assert abs(r.densChi_iv[0, 0, 0]) < 1e-9
+    p2 = params(oracle, Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.0, jh=0.2, Lmats=16, Lreal=8, beta=30.0, chidens_flag=True, Ltau=50,
+                lanc_dim_threshold=16)
+    r2 = oracle.ed_solve(p2, oracle.init_bath(p2))
+    assert np.abs(r2.densChi_tau[0, 1]).max() == 0.0 and np.abs(r2.densChi_tau[1, 0]).max() == 0.0
+    assert r2.densChi_tau[0, 0, 0] > 0.0 and r2.densChi_tot_tau[0] > 0.0
+    assert np.abs(r2.densChi_tot_tau - r2.densChi_tot_tau[::-1]).max() < 1e-12
+
+
 def test_ed_solve_arpack_and_lanczos_methods_agree(oracle):
     pa = oracle.Params(Norb=1, Nbath=4, Lmats=32, Lreal=32)          # reference defaults: arpack, 6 states/sector
     pl = params(oracle, Norb=1, Nbath=4, Lmats=32, Lreal=32)
