@@ -1410,16 +1410,17 @@ k_fringe_dw(int nfr, const int *__restrict__ fringe, int64_t ncols, int64_t ld, 
     }
 }
 
+template <bool SLABBED>
 __global__ void __launch_bounds__(256)
 k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, int64_t dim_up, int norb, int accumulate,
             const uint32_t *__restrict__ cfg_up, const uint32_t *__restrict__ cfg_dw,
             const double *__restrict__ e_up, const double *__restrict__ e_dw, const double *__restrict__ xtab,
             const uint32_t *__restrict__ hop_up, const uint8_t *__restrict__ nhop_up, const double *__restrict__ amp_up,
-            const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dot_out, SlabMap Mpar, int slabbed)
+            const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dot_out, SlabMap Mpar)
 {
     __shared__ double s_amp[256], s_x[32 * 32], s_red[8];
     __shared__ SlabMap M;
-    if (threadIdx.x == 0) M = Mpar;
+    if (SLABBED && threadIdx.x == 0) M = Mpar;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_amp[i] = amp_up[i];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_x[i] = xtab[i];
     __syncthreads();
@@ -1432,14 +1433,14 @@ k_fringe_up(int nfr, const int *__restrict__ fringe, int64_t nrows, int64_t ld, 
         const int64_t ru = fringe[q];
         // element (r, c) of the row shard: plain [nrows][ld] tile, or slab / peer addressing (see SlabMap)
         auto xat = [&](int64_t c) -> const double * {
-            if (!slabbed) return x + r * ld + c;
+            if (!SLABBED) return x + r * ld + c;
             const int p = slab_of(M, (int)c);
             return (M.peer ? M.xp[p] + M.xbase[p] : x + M.base[p]) + r * M.ldc[p] + (c - M.col0[p]);
         };
         const double xo = *xat(ru);
         double acc = (e_up[ru] + e_dw[r] + s_x[(cfg_dw[r] & impmask) * 32u + (cfg_up[ru] & impmask)]) * xo;
         double *yo;
-        if (!slabbed) yo = y + r * ld + ru;
+        if (!SLABBED) yo = y + r * ld + ru;
         else { const int p = slab_of(M, (int)ru); yo = (M.peer ? M.yp[p] : y) + M.base[p] + r * M.ldc[p] + (ru - M.col0[p]); }
         if (accumulate) acc += *yo;
         const int nu = nhop_up[ru];
@@ -1689,9 +1690,10 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
         const int64_t total = nrows * U.nfringe;
         const unsigned nb = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
         const bool d = dot_ok && slots + (int)nb <= kDotSlots;
-        k_fringe_up<<<nb, 256, 0, ctx->stream>>>(U.nfringe, U.d_fringe, nrows, ld, s->dim_up, NORB, accumulate, s->up->cfg, s->dw->cfg + row0,
-                                                 s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y,
-                                                 d ? dot + slots : nullptr, M, slabs ? 1 : 0);
+        auto fk = slabs ? k_fringe_up<true> : k_fringe_up<false>;
+        fk<<<nb, 256, 0, ctx->stream>>>(U.nfringe, U.d_fringe, nrows, ld, s->dim_up, NORB, accumulate, s->up->cfg, s->dw->cfg + row0,
+                                        s->up->ediag, s->dw->ediag + row0, ctx->d_xtab, s->up->hop, s->up->nhop, s->up->amp, x, y,
+                                        d ? dot + slots : nullptr, M);
         CUDA_TRY(ctx, cudaGetLastError());
         if (d) slots += (int)nb; else dot_ok = false;
     }
@@ -1712,13 +1714,14 @@ static int launch_star_up(edgpu_sector *s, const double *x, double *y, int64_t r
             const int lead = B.off & 1, ncopy = (lead + B.size + 1) & ~1;
             const size_t rowb = (size_t)(ncopy + 2) * 8;
             const size_t tabs = lean_tabs_bytes(NORB, bD, NH3) + 64;
-            // stages: 2 y images when they fit; x images as far ahead as shared memory allows when x comes over NVLink
+            // stages: 2 y images when they fit; 3 x images (measured 518 vs 512 matvec/s for 2, no gain beyond), as many as
+            // shared memory allows when x comes over NVLink; test-hook bit 9: 2 x images (the compile-time variant)
             const size_t avail = 227 * 1024 - 1024 - tabs;
             const size_t per = rowb * G + 64 * G;                                  // one stage (+ its diagonal terms)
             int nst = (int)std::min<size_t>(avail / per, (size_t)kMaxXS + 2);
             if (ctx->par.reserved[0] & 64) nst = std::min(nst, (ctx->par.reserved[0] & 128) ? 3 : 2);   // test hooks: few stages
             const int nys = nst >= 4 ? 2 : 1;
-            const int nxs = std::max(1, std::min(nst - nys, (slabs && slabs->peer) ? kMaxXS : 2));
+            const int nxs = std::max(1, std::min(nst - nys, (slabs && slabs->peer) ? kMaxXS : ((ctx->par.reserved[0] & 512) ? 2 : 3)));
             const size_t smem = (size_t)(nxs + nys) * rowb * G + sizeof(double) * 8 * G * nxs + tabs;
             if (nst >= 2 && smem <= 227 * 1024) {
                 auto kern = pick_up3<NORB>(NH3, !(nxs == 2 && nys == 2));

@@ -39,7 +39,7 @@ typedef struct {
     int32_t reserved[8];     /* reserved[0]: test hooks (bit 0: 2-column down strips, bit 1: single-stage up pass, bit 2: generic tile
                                 pass only, bit 3: no copy-engine kernels, bit 4: copy-engine kernels for every block size,
                                 bit 5: programmatic dependent launch of the copy-engine kernels, bit 6 (+ bit 7): at most
-                                2 (3) stages in the up pipeline) */
+                                2 (3) stages in the up pipeline, bit 9: 2 instead of 3 x images in the up pipeline) */
 } edgpu_params;
 
 /* init_ed_structure + setup_pointers_normal (ED_MAIN.f90:73,91; ED_SETUP.f90:150-360,372-496).

@@ -35,8 +35,8 @@ def test_star_hxv_matches_oracle_all_sectors(oracle, edb, name, flags):
 
 # 3 = fallback paths (2-column down strips + single-stage up pass), 4 = generic tile_pass everywhere,
 # 8 = LSU kernels instead of the copy-engine ones, 16 = copy-engine kernels for every block size,
-# +64 (+128) = at most 2 (3) stages in the up pipeline (1 x + 1 y image / 2 x + 1 y), +32 = programmatic dependent launch
-@pytest.mark.parametrize("flags", [0, 3, 4, 8, 16, 16 + 64, 16 + 64 + 128, 16 + 32])
+# +64 (+128) = at most 2 (3) stages in the up pipeline (1 x + 1 y image / 2 x + 1 y), +32 = programmatic dependent launch, +512 = 2 x images (compile-time stage counts)
+@pytest.mark.parametrize("flags", [0, 3, 4, 8, 16, 16 + 64, 16 + 64 + 128, 16 + 32, 16 + 512])
 @pytest.mark.parametrize("Norb,Nbath,sec", [(1, 9, (5, 5)), (1, 9, (6, 5)), (2, 4, (5, 5)), (2, 4, (4, 6)), (3, 2, (4, 5))])
 def test_star_hxv_medium_sectors(oracle, edb, Norb, Nbath, sec, flags):
     case = dict(Norb=Norb, Nbath=Nbath, uloc=tuple([2.0] * Norb), ust=0.7 if Norb > 1 else 0.0, jh=0.1 if Norb > 1 else 0.0)
