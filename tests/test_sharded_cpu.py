@@ -63,9 +63,22 @@ def worker(rank, world, port, dim_up, dim_dw, q, nchunks=1):
     err = (y_loc[:, :plan.ncols[rank]] - Y[:, plan.col0[rank]:plan.col0[rank] + plan.ncols[rank]]).abs().max().item()
     pad = y_loc[:, plan.ncols[rank]:].abs().max().item() if plan.ldc[rank] > plan.ncols[rank] else 0.0
     # Lanczos scalars through allreduce: alpha_1 of the chain started from X equals <X|H|X>/<X|X>
-    a, b = sh.lanczos_tridiag(x_loc.clone(), 3)
+    a, b = sh.lanczos_tridiag(x_loc.clone(), 4)
     a_ref = (X * Y).sum().item() / (X * X).sum().item()
-    q.put((rank, err, pad, abs(a[0] - a_ref), sum(plan.ncols), sum(plan.nrows)))
+    # the whole recurrence (unnormalised vectors, all-reduced scalars) against the textbook one on the dense operator
+    def H(V):
+        return D * V + Hdw @ V + V @ Hup.T
+    vin, vout, bb, ar, br = X / X.norm(), torch.zeros_like(X), 0.0, [], [0.0]
+    for _ in range(4):
+        t = H(vin) - bb * vout
+        aa = (vin * t).sum().item()
+        t = t - aa * vin
+        bb = t.norm().item()
+        vout, vin = vin, t / bb
+        ar.append(aa)
+        br.append(bb)
+    dlanc = max(np.abs(a - np.array(ar)).max(), np.abs(b - np.array(br[:4])).max()) / max(1.0, np.abs(ar).max())
+    q.put((rank, err, pad, max(abs(a[0] - a_ref), dlanc), sum(plan.ncols), sum(plan.nrows)))
     dist.destroy_process_group()
 
 
