@@ -13,13 +13,14 @@ workload (default: BASELINE config 4 -- Norb=2, Nbath=7, Ns=16, half-filling sec
           bandwidth (MEASURED_PEAKS.json).
 `cpu_baseline` / `--impl reference` = the CPU oracle (literal C restatement of directMatVec_cc; the Fortran
           reference cannot be built in this image) on all host cores over a bounded row sample.
-With N>1 (torchrun) the default is ONE sector vector sharded by up-spin column blocks over the ranks (BASELINE config 4:
-"direct H*v sharded over 1/2/4/8 GPUs") -> "scaling": "strong".  The down term is local; the up term exchanges rows either
-inside the copy-engine up kernel over CUDA-IPC peer memory (`--exchange peer`, default up to 4 ranks) or through two NCCL
-all-to-all transposes (`--exchange nccl`, default at 8 ranks).  The same line carries `independent_chains` (the other
-level of parallelism of the north star measured in the same run: one whole vector per GPU, no collective, weak scaling;
-`--mode chains` makes it the primary value) and an `e2e` leg (pinned host shards -> device, sharded Lanczos steps,
-alpha/beta -> host).
+`parity`  = one H*v of the Philox start vector compared with the CPU oracle on whole reference rows that touch every
+          (down-block, up-block) tile (oracle/parity_check.py), 1e-12 * |y|_inf; a mismatch fails the run.
+With N>1 (torchrun) the default is ONE sector vector sharded over the ranks -> "scaling": "strong".  Round 2 shards by
+CONSERVED OCCUPATION PAIRS (`--mode pairs`, edgpu_sector_build_shard): H is block diagonal over (down-block, up-block)
+pairs, every rank owns whole pairs, H*v needs no exchange; the Lanczos scalars of the e2e leg are summed with NCCL inside
+the C-ABI (edgpu_comm_init).  The line carries `parity_max_rel_err` of the sharded product against the oracle, a `cfg5`
+sub-record (Ns=18: every GPU alone vs sharded over N) and `independent_chains` (one whole vector per GPU, weak scaling).
+`--mode strips` is the round-1 scheme (up-spin column strips, NVLink exchange per product) kept for comparison.
 """
 from __future__ import annotations
 
@@ -156,6 +157,13 @@ def cpu_reference_sample(workload, seconds_target=15.0, threads=None, steps=1, w
     return mv_per_s, P, sample, tavg
 
 
+def dim_of(workload):
+    import math
+    Norb, Nbath, nup, ndw, _ = WORKLOADS[workload]
+    Ns = Norb * (Nbath + 1)
+    return math.comb(Ns, nup) * math.comb(Ns, ndw)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,10 +174,11 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "hxv_matvecs_per_s", "value": mv, "unit": "matvec/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tavg, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "bath": "init_dmft_bath noise=0 hwband=2", "uloc": 2.0,
-                   "note": "the Fortran reference cannot be built here (no Fortran compiler, SciFortran absent): this "
-                           "is the oracle port of its algorithm"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(args.workload, dim_of(args.workload), 2.0 * dim_of(args.workload) * 8.0 / max(1, args.gpus),
+                               "1 GPU" if args.gpus == 1 else f"sector vector sharded by conserved occupation pairs over {args.gpus} ranks (LPT over "
+                               "pair sizes); H*v has no exchange; Lanczos scalars by ncclAllReduce"),
+        "note": "the Fortran reference cannot be built here (no Fortran compiler, SciFortran absent): this is the oracle port of its algorithm on the host cores",
         "cpu_baseline": {"value": mv, "unit": "matvec/s", "cores": P, "kind": "port", "sample": sample},
         "e2e": {"value": mv, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,6 +333,238 @@ def run_sharded(args, edb, world, rank, local):
     return 0
 
 
+def make_model_ctx(edb, workload, local, stream, layout=0, kernel=0, flags=0):
+    """context + the synthetic Hamiltonian of SURVEY 8d (init_dmft_bath, Uloc=2, Ust=Jh=0, xmu=0, HFMODE=T)"""
+    import ctypes as C
+    import numpy as np
+    Norb, Nbath, nup, ndw, desc = WORKLOADS[workload]
+    ctx = edb.Context(Norb, Nbath, 1, True, device=local, stream=stream, layout=layout, hxv_kernel=kernel, debug_flags=flags)
+    inp = edb.default_input(Norb=Norb, Nbath=Nbath, uloc=[2.0] * Norb)
+    bath = np.zeros(edb.lib().ed_get_bath_dimension(inp))
+    tmp = C.c_void_p()
+    edb.lib().ed_init_solver(C.byref(inp), local, C.c_void_p(stream), bath.ctypes.data_as(edb.dp), bath.size, None, C.byref(tmp))
+    edb.lib().ed_finalize_solver(tmp)
+    ctx.set_hamiltonian(bath, [2.0] * Norb)
+    return ctx, bath
+
+
+PARITY_SEED = 20240607
+PARITY_TOL = 1e-12
+
+
+def oracle_model(workload, bath):
+    from oracle import ed_oracle as O
+    O.build()
+    Norb, Nbath, nup, ndw, _ = WORKLOADS[workload]
+    p = O.Params(Norb=Norb, Nbath=Nbath, uloc=tuple([2.0] * Norb), lanc_method="lanczos", lanc_nstates_sector=1)
+    return O, O.Model(p, bath)
+
+
+def parity_rows(workload, max_rows=24):
+    from oracle import ed_oracle as O
+    from oracle import parity_check as PC
+    O.build()
+    Norb, Nbath, nup, ndw, _ = WORKLOADS[workload]
+    return PC.pick_rows(O, Norb, Nbath, nup, ndw, per_block=3, max_rows=max_rows)
+
+
+def parity_check(workload, bath, rows, dim_up, fetch_rows):
+    """oracle as the CHECKER of one GPU product (x = Philox uniforms, seed PARITY_SEED)"""
+    from oracle import parity_check as PC
+    O, model = oracle_model(workload, bath)
+    Norb, Nbath, nup, ndw, _ = WORKLOADS[workload]
+    res = PC.check_rows(O, model, nup, ndw, PARITY_SEED, rows, dim_up, fetch_rows)
+    res["tol"] = PARITY_TOL
+    res["pass"] = bool(res["max_rel_err"] < PARITY_TOL)
+    res["what"] = ("y = H x, x = Philox uniforms: whole reference rows touching every (down-block, up-block) tile vs the "
+                   "window oracle (direct/HxV*.f90 row rule)")
+    return res
+
+
+def run_pairs(args, edb, world, rank, local):
+    """N>1: ONE sector vector sharded by conserved occupation pairs (edgpu_sector_build_shard): no exchange in H*v."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx, bath = make_model_ctx(edb, args.workload, local, stream, flags=args.flags)
+    # NCCL communicator of the C-ABI: rank 0 makes the id, the host broadcasts it (here through torch.distributed)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    s = ctx.sector_shard(nup, ndw, rank, world)
+    info = s.info()
+    dim = s.dim
+    x, y = s.vec(), s.vec()
+    x.fill_uniform(PARITY_SEED)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        s.hxv(x, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        s.hxv(x, y)
+    ev1.record()
+    barrier()
+    ms_mine = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = allmax(ms_mine)
+    ms_step = ms_total / args.steps
+    tmin = -allmax(-ms_mine) / args.steps
+    # ---- parity of the sharded product: every rank contributes its elements of the sampled rows (zeros elsewhere) ----
+    parity = None
+    if not args.no_cpu:
+        rows, dim_up, dim_dw = parity_rows(args.workload)
+        got = {}
+        for rd in rows:
+            t = torch.from_numpy(y.download_rows(rd, rd + 1)).cuda()
+            dist.all_reduce(t)
+            got[rd] = t.cpu().numpy()
+        if rank == 0:
+            parity = parity_check(args.workload, bath, rows, dim_up, lambda a, b: got[a])
+    # ---- end to end: complex(8) start vector in pinned host memory -> sharded chain through the C-ABI -> alpha/beta ----
+    e2e = None
+    if not args.no_e2e:
+        nlanc = args.nlanc
+        host = torch.empty(2 * dim, dtype=torch.float64).pin_memory()
+        hv = host.numpy()
+        hv[0::2] = 1.0 / np.sqrt(dim)
+        hv[1::2] = 0.0
+        a, b, nu = np.zeros(nlanc), np.zeros(nlanc), C.c_int32()
+        times = []
+        for i in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            ctx.check(edb.lib().edgpu_vec_upload(x.h, hv.ctypes.data, 1))
+            t1 = time.perf_counter()
+            ctx.check(edb.lib().edgpu_lanczos_tridiag(s.h, x.h, nlanc, 1e-13, a.ctypes.data_as(edb.dp), b.ctypes.data_as(edb.dp), C.byref(nu)))
+            barrier()
+            if i > 0:
+                times.append((time.perf_counter() - t0, t1 - t0))
+        te, tu = allmax(max(t[0] for t in times)), allmax(max(t[1] for t in times))
+        e2e = {"value": nlanc / te, "unit": "matvec/s", "h2d_bytes_per_step": int(world * dim * 16), "d2h_bytes_per_step": int(2 * nlanc * 8),
+               "call": f"edgpu_vec_upload(complex(8) host, every rank keeps its pairs) + edgpu_lanczos_tridiag(nlanc={nlanc}) on the "
+                       "pair-sharded sector, Lanczos scalars summed by ncclAllReduce inside the C-ABI", "s_per_call": te, "upload_s": tu,
+               "ms_per_lanczos_step": (te - tu) / nlanc * 1e3, "alpha0": float(a[0]), "beta1": float(b[1]) if nlanc > 1 else None}
+        del host
+    x.free(); y.free(); s.free()
+    # ---- independent chains (weak scaling, SURVEY 8e.1) and the cfg5 sub-record (the config the 70 % target names) ----
+    chains = None
+    try:
+        sf = ctx.sector(nup, ndw)
+        xf, yf = sf.vec().fill_normal(PARITY_SEED + rank), sf.vec()
+        for _ in range(args.warmup):
+            sf.hxv(xf, yf)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            sf.hxv(xf, yf)
+        ev1.record()
+        barrier()
+        tc = allmax(ev0.elapsed_time(ev1))
+        chains = {"value": world * args.steps / (tc * 1e-3), "unit": "matvec/s", "scaling": "weak", "ms_per_hxv_1gpu": tc / args.steps,
+                  "what": "independent chains: one whole sector vector per GPU, no collective"}
+        xf.free(); yf.free(); sf.free()
+    except Exception as e:
+        chains = {"error": str(e)[:200]}
+    sub5 = None
+    if args.cfg5 and args.workload != "cfg5":
+        try:
+            sub5 = cfg5_record(args, edb, world, rank, local, stream, barrier, allmax)
+        except Exception as e:
+            sub5 = {"error": str(e)[:300]}
+    alg_bytes = 2.0 * dim * 8.0
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    if rank == 0:
+        eff1 = (chains["ms_per_hxv_1gpu"] / (world * ms_step)) if chains and "ms_per_hxv_1gpu" in chains else None
+        line = {
+            "metric": "hxv_matvecs_per_s", "value": 1e3 / ms_step, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": bench_config(args.workload, dim, alg_bytes / world,
+                                   f"sector vector sharded by conserved occupation pairs over {world} ranks (LPT over pair sizes); H*v has no "
+                                   "exchange; Lanczos scalars by ncclAllReduce"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_launch_set": alg_bytes,
+                         "nvlink_bytes_per_hxv": 0, "ms_per_hxv_fastest_rank": tmin,
+                         "load_balance": tmin / ms_step, "local_doubles_rank0": info["nalloc"]},
+            "parity": parity, "parity_max_rel_err": parity["max_rel_err"] if parity else None,
+            "e2e": e2e, "cpu_baseline": None, "independent_chains": chains,
+            "efficiency_vs_1gpu_same_run": eff1, "cfg5": sub5,
+            "gpu_launches": int(args.steps * 4), "clocks": clocks,
+        }
+        print(json.dumps(line))
+        if parity is not None and not parity["pass"]:
+            dist.destroy_process_group()
+            return 1
+    dist.destroy_process_group()
+    return 0
+
+
+def cfg5_record(args, edb, world, rank, local, stream, barrier, allmax):
+    """Ns=18 (2.36e9 states, 18.9 GB per vector): every GPU alone on the whole vector, then the vector sharded by pairs over
+    the ranks; efficiency = t(1 GPU) / (N * t(N GPUs)), device times, max over ranks."""
+    import torch
+    Norb, Nbath, nup, ndw, desc = WORKLOADS["cfg5"]
+    ctx, bath = make_model_ctx(edb, "cfg5", local, stream)
+    steps = 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(sec):
+        x, y = sec.vec().fill_uniform(PARITY_SEED), sec.vec()
+        sec.hxv(x, y); sec.hxv(x, y)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            sec.hxv(x, y)
+        ev1.record()
+        barrier()
+        t = allmax(ev0.elapsed_time(ev1)) / steps
+        x.free(); y.free()
+        return t
+
+    s1 = ctx.sector(nup, ndw)
+    t1 = timed(s1)
+    dim = s1.dim
+    s1.free()
+    sn = ctx.sector_shard(nup, ndw, rank, world)
+    tn = timed(sn)
+    sn.free()
+    ctx.close()
+    return {"workload": f"cfg5: {desc}", "ms_per_hxv_1gpu": t1, "ms_per_hxv_sharded": tn, "n_gpus": world,
+            "efficiency": t1 / (world * tn), "matvec_per_s_sharded": 1e3 / tn, "dim": dim,
+            "definition": "t(1 GPU, whole vector, max over the N GPUs each running it alone) / (N * t(vector sharded by pairs over N GPUs, max over ranks)), CUDA events"}
+
+
+def bench_config(workload, dim, bytes_per_rank, parallelism):
+    desc = WORKLOADS[workload][4]
+    return {"workload": f"{workload}: {desc}", "bath": "init_dmft_bath noise=0 hwband=2", "uloc": 2.0, "dim": dim,
+            "vector": "Philox (counter = reference index)",
+            "l2": (f"inputs exceed L2: {bytes_per_rank / 1e9:.3f} GB touched per rank and step" if bytes_per_rank > 3e8
+                   else "vector fits in L2 (launch-bound case)"),
+            "parallelism": parallelism}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -339,9 +580,10 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the ed_solve wall-time section")
     ap.add_argument("--solve-cfg3", action="store_true", help="also time a full ed_solve of BASELINE config 3 (Ns=14, 225 sectors)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="auto", choices=["auto", "shard", "chains"],
-                    help="N>1: 'shard' = one sector vector sharded by up-spin column blocks with all-to-all transposes "
-                         "(strong scaling); 'chains' = independent H*v streams per rank (weak scaling)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "pairs", "strips", "chains"],
+                    help="N>1: 'pairs' (default) = one sector vector sharded by conserved occupation pairs, no exchange; 'strips' = "
+                         "round-1 scheme (up-spin column strips + NVLink exchange); 'chains' = independent H*v streams per rank")
+    ap.add_argument("--cfg5", type=int, default=1, help="N>1: add the Ns=18 sub-record (1 GPU vs sharded)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="sharded mode: exchange fused into the up kernel over peer memory (CUDA IPC), or NCCL all-to-all "
                          "transposes; auto = what measured faster on B200 x8 (peer up to 4 ranks, nccl at 8)")
@@ -373,8 +615,10 @@ def main():
     edb = importlib.import_module("dmft-ed_b200")
     mode = args.mode
     if mode == "auto":
-        mode = "shard" if world > 1 else "chains"
-    if world > 1 and mode == "shard":
+        mode = "pairs" if world > 1 else "chains"
+    if world > 1 and mode == "pairs":
+        return run_pairs(args, edb, world, rank, local)
+    if world > 1 and mode == "strips":
         return run_sharded(args, edb, world, rank, local)
     Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
     stream = torch.cuda.current_stream().cuda_stream
@@ -393,7 +637,7 @@ def main():
     s = ctx.sector(nup, ndw)
     dim = s.dim
     x, y = s.vec(), s.vec()
-    x.fill_normal(20240607 + rank)          # Philox N(0,1), SURVEY 8d
+    x.fill_uniform(PARITY_SEED + rank)      # Philox uniforms in (-1,1), counter = reference index
     ctx.sync()
 
     def barrier():
@@ -492,6 +736,14 @@ def main():
                            "sectors": (si.Nbath * si.Norb + si.Norb + 1) ** 2, "scan": "all sectors, lanc_method=lanczos, direct H*v"}
             so.close()
 
+    # ---- parity of the timed product against the oracle (rank 0, N=1): sampled reference rows -------------------------
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        x.fill_uniform(PARITY_SEED)
+        s.hxv(x, y)
+        rows, dim_up, _ = parity_rows(args.workload)
+        parity = parity_check(args.workload, sol_bath, rows, dim_up, y.download_rows)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -502,12 +754,10 @@ def main():
     if rank == 0:
         line = {
             "metric": "hxv_matvecs_per_s", "value": value, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world == 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "bath": "init_dmft_bath noise=0 hwband=2", "uloc": 2.0,
-                       "vector": "Philox N(0,1) seed 20240607", "dim": dim,
-                       "l2": f"inputs exceed L2: {alg_bytes / 1e9:.3f} GB touched per step" if alg_bytes > 3e8 else "vector fits in L2 (launch-bound case)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks, independent H*v streams (chain-level)"},
+            "config": bench_config(args.workload, dim, alg_bytes, "1 GPU" if world == 1 else f"{world} ranks, independent H*v streams (chain-level)"),
+            "parity": parity, "parity_max_rel_err": parity["max_rel_err"] if parity else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes,
                          "ms_per_hxv_events": ms_kernel},
@@ -515,6 +765,8 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line))
+        if parity is not None and not parity["pass"]:
+            return 1
     if world > 1:
         dist.destroy_process_group()
     return 0

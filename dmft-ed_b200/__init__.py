@@ -50,7 +50,7 @@ class ed_input(C.Structure):
 # every symbol declared in include/edgpu.h and include/ed_b200.h (checked by tests/test_abi.py)
 EDGPU_SYMBOLS = [
     "edgpu_init", "edgpu_finalize", "edgpu_last_error", "edgpu_version", "edgpu_ns", "edgpu_set_hamiltonian",
-    "edgpu_sector_build", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
+    "edgpu_sector_build", "edgpu_sector_build_shard", "edgpu_sector_info", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize", "edgpu_vec_download_rows", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
     "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
@@ -98,6 +98,12 @@ def lib():
     L.edgpu_set_hamiltonian.argtypes = [vp, dp, C.c_int32, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
     L.edgpu_sector_build.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.edgpu_sector_free.argtypes = [vp]
+    L.edgpu_sector_build_shard.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.edgpu_sector_info.argtypes = [vp, i32p, i64p, i32p, i32p]
+    L.edgpu_comm_unique_id.argtypes = [vp, C.c_char_p]
+    L.edgpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    L.edgpu_comm_finalize.argtypes = [vp]
+    L.edgpu_vec_download_rows.argtypes = [vp, C.c_int64, C.c_int64, vp]
     L.edgpu_sector_dim.argtypes = [vp, i64p, i64p, i64p]
     L.edgpu_sector_map.argtypes = [vp, C.c_int64, C.c_int64, u64p]
     L.edgpu_sector_map_check.argtypes = [vp, u64p, i64p]
@@ -205,6 +211,17 @@ class Context:
             hp = _p(self._hl)
         self.check(lib().edgpu_set_hamiltonian(self.h, _p(bath), bath.size, hp, _p(ul), ust, jh, jx, jp, xmu))
 
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.check(lib().edgpu_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank, nranks):
+        self.check(lib().edgpu_comm_init(self.h, uid, rank, nranks))
+
+    def sector_shard(self, nup, ndw, rank, nranks):
+        return Sector(self, nup, ndw, rank, nranks)
+
     def sector(self, nup, ndw):
         return Sector(self, nup, ndw)
 
@@ -223,15 +240,23 @@ class Context:
 
 
 class Sector:
-    def __init__(self, ctx: Context, nup, ndw):
+    def __init__(self, ctx: Context, nup, ndw, rank=0, nranks=1):
         self.ctx = ctx
         h = C.c_void_p()
-        ctx.check(lib().edgpu_sector_build(ctx.h, nup, ndw, C.byref(h)))
+        if nranks > 1:
+            ctx.check(lib().edgpu_sector_build_shard(ctx.h, nup, ndw, rank, nranks, C.byref(h)))
+        else:
+            ctx.check(lib().edgpu_sector_build(ctx.h, nup, ndw, C.byref(h)))
         self.h = h
         d, du, dd = C.c_int64(), C.c_int64(), C.c_int64()
         lib().edgpu_sector_dim(h, C.byref(d), C.byref(du), C.byref(dd))
         self.dim, self.dim_up, self.dim_dw = d.value, du.value, dd.value
         self.nup, self.ndw = nup, ndw
+
+    def info(self):
+        k, n, r, nr = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        self.ctx.check(lib().edgpu_sector_info(self.h, C.byref(k), C.byref(n), C.byref(r), C.byref(nr)))
+        return {"layout_kind": k.value, "nalloc": n.value, "shard_rank": r.value, "shard_nranks": nr.value}
 
     def map(self, first=0, count=None):
         count = self.dim - first if count is None else count
@@ -335,6 +360,11 @@ class Vec:
     def download(self, cplx=False):
         out = np.empty(self.s.dim, dtype=np.complex128 if cplx else np.float64)
         self.s.ctx.check(lib().edgpu_vec_download(self.h, out.ctypes.data, int(cplx)))
+        return out
+
+    def download_rows(self, rd0, rd1):
+        out = np.empty((rd1 - rd0) * self.s.dim_up, dtype=np.float64)
+        self.s.ctx.check(lib().edgpu_vec_download_rows(self.h, rd0, rd1, out.ctypes.data))
         return out
 
     def fill_normal(self, seed):

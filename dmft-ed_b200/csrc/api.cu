@@ -73,7 +73,7 @@ extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu
     h.e.assign((size_t)h.nspin * h.norb * h.nbath, 0.0);
     h.v.assign((size_t)h.nspin * h.norb * h.nbath, 0.0);
     h.hloc.assign((size_t)h.nspin * h.norb * h.norb, 0.0);
-    const size_t nscal = 8 + 2 * 4096;
+    const size_t nscal = kScalSlots;
     if (cudaMalloc(&ctx->d_partials, sizeof(double) * kRedBlocks * 4) != cudaSuccess ||
         cudaMalloc(&ctx->d_dotpart, sizeof(double) * 16384) != cudaSuccess ||
         cudaMalloc(&ctx->d_scal, sizeof(double) * nscal) != cudaSuccess ||
@@ -91,6 +91,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    edgpu_comm_finalize(ctx);
     ctx->bases.clear();
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -146,7 +147,21 @@ extern "C" int edgpu_set_hamiltonian(edgpu_ctx *ctx, const double *bath, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------------------
+static int sector_build_impl(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int rank, int nranks, edgpu_sector **out);
+void pair_layout_forget(edgpu_sector *s, const double *x);
+
 extern "C" int edgpu_sector_build(edgpu_ctx *ctx, int32_t nup, int32_t ndw, edgpu_sector **out)
+{
+    return sector_build_impl(ctx, nup, ndw, 0, 1, out);
+}
+
+extern "C" int edgpu_sector_build_shard(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int32_t rank, int32_t nranks, edgpu_sector **out)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) return ctx ? edgpu_fail(ctx, "edgpu_sector_build_shard: bad rank %d of %d", rank, nranks) : 1;
+    return sector_build_impl(ctx, nup, ndw, rank, nranks, out);
+}
+
+static int sector_build_impl(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int rank, int nranks, edgpu_sector **out)
 {
     if (!ctx || !out) return ctx ? edgpu_fail(ctx, "edgpu_sector_build: null argument") : 1;
     *out = nullptr;
@@ -163,7 +178,27 @@ extern "C" int edgpu_sector_build(edgpu_ctx *ctx, int32_t nup, int32_t ndw, edgp
     s->ld = s->dim_up;
     if (s->up->layout == 2) s->ld = (s->dim_up + 3) / 4 * 4;                  // 32-byte aligned rows for the tiled kernels
     s->nalloc = s->dim_dw * s->ld;
+    // pair-tile layout + fiber kernels (hxv_fiber.cu): hxv_kernel = 3 forces them, auto takes them for large sectors;
+    // a sharded sector (nranks > 1) exists only in that layout
+    const bool want_pairs = ctx->par.hxv_kernel == 3 || nranks > 1 || (ctx->par.hxv_kernel == 0 && s->dim >= (1ll << 21));
+    if (want_pairs && pair_layout_supported(s)) {
+        if (int rc = pair_layout_build(s, rank, nranks)) { delete s; return rc; }
+    } else if (ctx->par.hxv_kernel == 3 || nranks > 1) {
+        delete s;
+        return edgpu_fail(ctx, "edgpu_sector_build: the pair-tile layout (fiber kernels, sharding) needs bath_type=normal with diagonal impHloc, Norb 2-3, Nbath 2-7, no Jx/Jp");
+    }
     *out = s;
+    return 0;
+}
+
+/* layout facts of a sector: kind 0 = one Dimdw x ld tile, 3 = pair tiles; elements stored per vector on this rank */
+extern "C" int edgpu_sector_info(const edgpu_sector *s, int32_t *layout_kind, int64_t *nalloc, int32_t *shard_rank, int32_t *shard_nranks)
+{
+    if (!s) return 1;
+    if (layout_kind) *layout_kind = s->pl ? 3 : 0;
+    if (nalloc) *nalloc = s->nalloc;
+    if (shard_rank) *shard_rank = s->shard_rank;
+    if (shard_nranks) *shard_nranks = s->shard_nranks;
     return 0;
 }
 
@@ -237,6 +272,7 @@ extern "C" int edgpu_vec_free(edgpu_vec *v)
 {
     if (!v) return 0;
     cudaStreamSynchronize(v->s->ctx->stream);
+    pair_layout_forget(v->s, v->d);
     cudaFree(v->d);
     delete v;
     return 0;
@@ -256,7 +292,7 @@ extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cpl
     edgpu_sector *s = v->s;
     edgpu_ctx *ctx = s->ctx;
     const size_t bytes = sizeof(double) * (size_t)s->dim * (is_cplx ? 2 : 1);
-    if (!is_cplx && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {     // reference layout: direct copy
+    if (!is_cplx && !s->pl && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {     // reference layout: direct copy
         CUDA_TRY(ctx, cudaMemcpyAsync(v->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return 0;
@@ -304,7 +340,7 @@ extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_c
     edgpu_sector *s = v->s;
     edgpu_ctx *ctx = s->ctx;
     const size_t bytes = sizeof(double) * (size_t)s->dim * (is_cplx ? 2 : 1);
-    if (!is_cplx && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {
+    if (!is_cplx && !s->pl && s->ld == s->dim_up && !s->up->ref2int && !s->dw->ref2int) {
         CUDA_TRY(ctx, cudaMemcpyAsync(host, v->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return 0;
@@ -315,6 +351,27 @@ extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_c
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_vec_download: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+/* reference rows [rd0, rd1) of the vector (reference order, real): host[(rd - rd0)*DimUp + ru] */
+extern "C" int edgpu_vec_download_rows(const edgpu_vec *v, int64_t rd0, int64_t rd1, double *host)
+{
+    if (!v || !host) return 1;
+    edgpu_sector *s = v->s;
+    edgpu_ctx *ctx = s->ctx;
+    if (rd0 < 0 || rd1 < rd0 || rd1 > s->dim_dw) return edgpu_fail(ctx, "edgpu_vec_download_rows: rows [%lld,%lld) outside 0..%lld", (long long)rd0, (long long)rd1, (long long)s->dim_dw);
+    if (rd1 == rd0) return 0;
+    const size_t bytes = sizeof(double) * (size_t)(rd1 - rd0) * (size_t)s->dim_up;
+    double *stage = nullptr;
+    if (int rc = stage_alloc(ctx, bytes, &stage)) return rc;
+    int rc = vec_convert_rows(s, 2, rd0, rd1, v->d, stage, ctx->stream);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_vec_download_rows: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(ctx->stream);
     cudaFree(stage);
@@ -345,6 +402,10 @@ extern "C" int edgpu_vec_dot(const edgpu_vec *a, const edgpu_vec *b, double *out
     if (!a || !b || !out || a->s->nalloc != b->s->nalloc) return 1;
     edgpu_ctx *ctx = a->s->ctx;
     if (int rc = vec_dot(ctx, a->d, b->d, a->s->nalloc, ctx->d_scal)) return rc;
+    if (a->s->shard_nranks > 1) {                                  // sharded sector: the global dot product on every rank
+        if (comm_nranks(ctx) != a->s->shard_nranks) return edgpu_fail(ctx, "edgpu_vec_dot: sharded sector without a matching communicator (edgpu_comm_init)");
+        if (int rc = comm_allreduce_sum(ctx, ctx->d_scal, 1)) return rc;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *out = ctx->h_scal[0];
@@ -363,6 +424,7 @@ extern "C" int edgpu_vec_scale(edgpu_vec *a, double alpha)
 static bool use_star(const edgpu_sector *s)
 {
     const edgpu_ctx *ctx = s->ctx;
+    if (s->pl) return false;
     if (s->up->layout != 2 || s->dw->layout != 2 || ctx->par.hxv_kernel == 1 || ctx->ham.jhflag) return false;
     return ctx->par.hxv_kernel == 2 || s->dim >= (1ll << 21);
 }
@@ -371,6 +433,7 @@ bool hxv_uses_star(const edgpu_sector *s) { return !s->csr && use_star(s); }
 
 int hxv_dispatch(edgpu_sector *s, const double *x, double *y)
 {
+    if (s->pl) return hxv_fiber(s, x, y, nullptr, nullptr);
     if (s->csr) return hxv_csr(s, x, y);
     if (use_star(s)) return hxv_star(s, x, y);
     return hxv_generic(s, x, y);
@@ -484,7 +547,8 @@ extern "C" int edgpu_bench_hxv(edgpu_sector *s, const edgpu_vec *x, edgpu_vec *y
     if (ms_avg) *ms_avg = total / iters;
     if (launches) {
         int per = 1;
-        if (s->csr) per = 1;
+        if (s->pl) per = hxv_fiber_launches(s);
+        else if (s->csr) per = 1;
         else if (use_star(s)) per = hxv_star_launches(s);
         else per = 1 + (ctx->ham.jhflag ? 1 : 0);
         *launches = (int64_t)per * iters;
@@ -503,7 +567,7 @@ extern "C" int edgpu_shard_ld(const edgpu_sector *s, int64_t *ld_full)
 extern "C" int edgpu_shard_hxv_dw(edgpu_sector *s, int64_t ncols, int64_t ldc, const void *x_dev, void *y_dev)
 {
     if (!s || !x_dev || !y_dev) return 1;
-    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_dw: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
+    if (s->pl || s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_dw: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
     if (ncols < 0 || ldc < ncols || (ldc & 3)) return edgpu_fail(s->ctx, "edgpu_shard_hxv_dw: bad column shard (ncols=%lld, ldc=%lld)", (long long)ncols, (long long)ldc);
     return hxv_star_dw(s, (const double *)x_dev, (double *)y_dev, ncols, ldc);
 }
@@ -511,7 +575,7 @@ extern "C" int edgpu_shard_hxv_dw(edgpu_sector *s, int64_t ncols, int64_t ldc, c
 extern "C" int edgpu_shard_hxv_up(edgpu_sector *s, int64_t row0, int64_t nrows, const void *x_dev, void *y_dev, int32_t accumulate)
 {
     if (!s || !x_dev || !y_dev) return 1;
-    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
+    if (s->pl || s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: needs the star-product layout (no Jx/Jp, no inter-orbital Hloc)");
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up: bad row shard");
     if (nrows == 0) return 0;
     return hxv_star_up(s, (const double *)x_dev, (double *)y_dev, row0, nrows, s->ld, accumulate);
@@ -521,7 +585,7 @@ extern "C" int edgpu_shard_hxv_up_slabs(edgpu_sector *s, int64_t row0, int64_t n
                                         const int64_t *ldc, const void *x_dev, void *y_dev, int32_t accumulate)
 {
     if (!s || !x_dev || !y_dev || !col0 || !ldc) return 1;
-    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: needs the star-product layout");
+    if (s->pl || s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: needs the star-product layout");
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_slabs: bad row shard");
     if (nrows == 0) return 0;
     return hxv_star_up_slabs(s, (const double *)x_dev, (double *)y_dev, row0, nrows, nslab, col0, ldc, accumulate);
@@ -532,7 +596,7 @@ extern "C" int edgpu_shard_hxv_up_peers(edgpu_sector *s, int64_t row0, int64_t n
                                         int32_t accumulate)
 {
     if (!s || !x_shards || !y_shards || !col0 || !ldc) return 1;
-    if (s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: needs the star-product layout");
+    if (s->pl || s->up->layout != 2 || s->ctx->ham.jhflag) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: needs the star-product layout");
     if (row0 < 0 || nrows < 0 || row0 + nrows > s->dim_dw) return edgpu_fail(s->ctx, "edgpu_shard_hxv_up_peers: bad row shard");
     if (nrows == 0) return 0;
     return hxv_star_up_peers(s, (const double *const *)x_shards, (double *const *)y_shards, row0, nrows, nranks, col0, ldc, accumulate, x_row0);
@@ -607,7 +671,12 @@ extern "C" int edgpu_shard_perm(const edgpu_sector *s, uint32_t *r2i_up, uint32_
 }
 
 // ---- CSR entry points (csr.cu) ----------------------------------------------------------------------------
-extern "C" int edgpu_sector_build_csr(edgpu_sector *s) { return s ? csr_build(s) : 1; }
+extern "C" int edgpu_sector_build_csr(edgpu_sector *s)
+{
+    if (!s) return 1;
+    if (s->pl) return edgpu_fail(s->ctx, "edgpu_sector_build_csr: the stored (CSR) path needs the single-tile layout (hxv_kernel 0-2 on a sector below 2^21 states, or hxv_kernel = 1/2)");
+    return csr_build(s);
+}
 extern "C" int edgpu_sector_drop_csr(edgpu_sector *s) { if (!s) return 1; cudaStreamSynchronize(s->ctx->stream); s->csr.reset(); return 0; }
 extern "C" int edgpu_sector_csr_nnz(const edgpu_sector *s, int64_t *nnz)
 {

@@ -4,18 +4,21 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
+SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu comm.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
 mkdir -p ../build
 OBJS=""
+PIDS=""
 for f in $SRCS; do
   [ -f "$f" ] || continue
   o=../build/$(basename ${f%.*}).o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ edgpu_internal.h -nt "$o" ] || [ ../../include/edgpu.h -nt "$o" ] || [ -f host/ed_host.h -a host/ed_host.h -nt "$o" ] || [ ../../include/ed_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ edgpu_internal.h -nt "$o" ] || [ ../../include/edgpu.h -nt "$o" ] || [ star_info.h -nt "$o" ] || [ -f host/ed_host.h -a host/ed_host.h -nt "$o" ] || [ ../../include/ed_b200.h -nt "$o" ]; then
     echo "nvcc $f"
+    rm -f "$o"
     $NVCC $FLAGS ${EXTRA_FLAGS} -x cu -c "$f" -o "$o" &
+    PIDS="$PIDS $!"
   fi
   OBJS="$OBJS $o"
 done
-wait
-$NVCC -shared -o ../libedgpu.so $OBJS -lcudart
+for p in $PIDS; do wait $p || { echo "build.sh: a compile job failed" >&2; exit 1; }; done
+$NVCC -shared -o ../libedgpu.so $OBJS -lcudart -ldl
 echo "built $(cd ..; pwd)/libedgpu.so"

@@ -46,6 +46,34 @@ struct HopPair {
 
 // Star-product description of one spin basis (layout 2). A "star" = impurity orbital a + its Nbath bath levels.
 struct StarInfo;
+// Per-spin tables of the fiber kernels (hxv_fiber.cu) and the pair-tile layout of a sector ("layout 3").
+struct FibSpin;
+struct PairLayout;
+
+// Address of element (internal down index id, internal up index iu) of a sector vector.
+//   mode 0: one Dimdw x ld tile, id*ld + iu                                   (layouts 1 and 2)
+//   mode 3: pair tiles -- the vector is the concatenation of the OWNED (down-block, up-block) pairs; pair (bi,bj) is an
+//           R x C matrix in 4x4 micro-tiles: ((rp/4)*C4 + cp/4)*16 + (rp%4)*4 + cp%4, with rp / cp the padded
+//           position of the configuration inside its block (hxv_fiber.cu).  Returns -1 for a pair this rank does not own.
+struct VAddr {
+    int mode = 0;
+    int nbu = 0;
+    int64_t ld = 0;
+    const int2 *rowinfo = nullptr;      // [dim_dw] (down-block, rp)
+    const int2 *colinfo = nullptr;      // [dim_up] (up-block, cp)
+    const int64_t *pbase = nullptr;     // [nbd*nbu] first element of the pair, -1 = not owned
+    const int *c4 = nullptr;            // [nbu] micro-tile columns of the up-block
+#ifdef __CUDACC__
+    __device__ __forceinline__ int64_t operator()(int64_t id, int64_t iu) const
+    {
+        if (mode == 0) return id * ld + iu;
+        const int2 r = rowinfo[id], c = colinfo[iu];
+        const int64_t b = pbase[(int64_t)r.x * nbu + c.x];
+        if (b < 0) return -1;
+        return b + ((int64_t)(r.y >> 2) * c4[c.x] + (c.y >> 2)) * 16 + (r.y & 3) * 4 + (c.y & 3);
+    }
+#endif
+};
 
 // Per-spin, per-particle-number tables shared by all sectors that use them.
 struct SpinBasis {
@@ -63,6 +91,7 @@ struct SpinBasis {
     int maxhop = 0;
     double *amp = nullptr;             // [256] device: signed amplitudes, code = 2*idx + (negative)
     std::shared_ptr<StarInfo> star;    // non-null when layout 2
+    std::shared_ptr<FibSpin> fib;      // fiber-kernel tables (built on demand from `star`)
     ~SpinBasis();
 };
 
@@ -76,6 +105,10 @@ struct CsrMatrix {
     uint8_t *rowlen = nullptr;         // [dim] device, true row lengths
     ~CsrMatrix();
 };
+
+struct EdComm;                         // comm.cu: NCCL communicator of the sharded Lanczos path
+static constexpr int kLancMaxSteps = 4096;                         // longest Lanczos chain (d_scal holds the coefficients)
+static constexpr int kScalSlots = 8 + 2 * (kLancMaxSteps + 1);     // device scalars: 8 working slots + alanc + blanc
 
 struct edgpu_ctx {
     edgpu_params par;
@@ -99,6 +132,7 @@ struct edgpu_ctx {
     size_t stage_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    EdComm *comm = nullptr;            // set by edgpu_comm_init: reductions of sharded sectors are summed over the ranks
 };
 
 struct edgpu_sector {
@@ -107,7 +141,9 @@ struct edgpu_sector {
     std::shared_ptr<SpinBasis> up, dw;
     int64_t dim_up = 0, dim_dw = 0, dim = 0;
     int64_t ld = 0;                    // leading dimension (elements) of the Dimdw x Dimup tile, >= dim_up
-    int64_t nalloc = 0;                // dim_dw * ld
+    int64_t nalloc = 0;                // elements of a vector of this sector: dim_dw * ld, or the owned pair tiles
+    std::shared_ptr<PairLayout> pl;    // non-null: vectors live in the pair-tile layout (hxv_fiber.cu)
+    int shard_rank = 0, shard_nranks = 1;   // pair tiles dealt over `shard_nranks` processes (this one owns `shard_rank`)
     std::unique_ptr<CsrMatrix> csr;
     // scratch vectors owned by the sector (Lanczos workspace), allocated lazily
     double *work[3] = {nullptr, nullptr, nullptr};
@@ -118,6 +154,12 @@ struct edgpu_vec {
     double *d = nullptr;               // [s->nalloc], pads (ld > dim_up) are kept at zero
 };
 
+VAddr sector_vaddr(const edgpu_sector *s);
+int pair_layout_build(edgpu_sector *s, int rank, int nranks);       // decides fiber support, fills s->pl / s->nalloc
+bool pair_layout_supported(const edgpu_sector *s);
+int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndot);
+int hxv_fiber_launches(const edgpu_sector *s);
+
 // ---- internal entry points (implemented across the .cu files) ----
 int build_spin_basis(edgpu_ctx *ctx, int pspin, int n, std::shared_ptr<SpinBasis> &out);
 int hxv_generic(edgpu_sector *s, const double *x, double *y);
@@ -127,6 +169,9 @@ bool hxv_uses_star(const edgpu_sector *s);
 int hxv_csr(edgpu_sector *s, const double *x, double *y);
 int hxv_dispatch(edgpu_sector *s, const double *x, double *y);
 int upload_xtab(edgpu_ctx *ctx);
+
+int comm_nranks(const edgpu_ctx *ctx);
+int comm_allreduce_sum(edgpu_ctx *ctx, double *d_buf, int n);
 
 // vector kernels (lanczos.cu)
 constexpr int kRedBlocks = 1184;       // 148 SMs x 8

@@ -157,7 +157,7 @@ int sector_work(edgpu_sector *s, int i, double **p)
 }
 
 // Device scalar slots (ctx->d_scal): [0] norm / b , [1] a , [2] zero constant, [8 + k] alanc[k], [8 + NMAX + k] blanc[k]
-static constexpr int kScalB = 0, kScalArr = 8, kLancMax = 4096;
+static constexpr int kScalB = 0, kScalArr = 8, kLancMax = kLancMaxSteps;
 
 // a = (sum of the partials) / nrm^2
 __global__ void k_lanc_alpha(const double *__restrict__ partials, int n, const double *__restrict__ nrm, double *__restrict__ out)
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict_
                                                              const double *__restrict__ cur, const double *__restrict__ p_bprev,
                                                              const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
                                                              const double *__restrict__ p_a, int64_t n, double *__restrict__ partials,
-                                                             double *__restrict__ b_out, unsigned int *__restrict__ ticket)
+                                                             double *__restrict__ b_out, unsigned int *__restrict__ ticket, int mode)
 {
     const double nc = *p_ncur, c_old = *p_bprev / *p_nold, c_cur = *p_a / nc;
     double acc = 0.0;
@@ -203,15 +203,30 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict_
         acc += t * t;
     }
     block_store_partial(acc, partials + blockIdx.x);
-    finalize_by_last_block(partials, gridDim.x, 1, nullptr, b_out, ticket);
+    finalize_by_last_block(partials, gridDim.x, mode, nullptr, b_out, ticket);
 }
 
 __global__ void k_set_one(double *p) { *p = 1.0; }
 
+// last step of a reduction that was summed over the ranks (sharded sectors): mode 1: sqrt ; 2: / (*nrm)^2
+__global__ void k_fin(double *p, int mode, const double *__restrict__ nrm)
+{
+    if (mode == 1) *p = sqrt(*p);
+    else if (mode == 2) { const double d = *nrm; *p = *p / (d * d); }
+}
+
+static inline bool is_sharded(const edgpu_sector *s) { return s->shard_nranks > 1; }
+static int check_comm(edgpu_sector *s)
+{
+    if (is_sharded(s) && comm_nranks(s->ctx) != s->shard_nranks)
+        return edgpu_fail(s->ctx, "sharded sector (%d ranks) but the communicator has %d ranks: call edgpu_comm_init first", s->shard_nranks, comm_nranks(s->ctx));
+    return 0;
+}
+
 // Device scalar slots: [0] norm, [3] the constant 1, [kScalArr + k] alanc[k], [kScalArr + kLancMax + k] blanc[k]
 static int reset_scalars(edgpu_ctx *ctx)
 {
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (kScalArr + 2 * kLancMax), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * kScalSlots, ctx->stream));
     k_set_one<<<1, 1, 0, ctx->stream>>>(ctx->d_scal + 3);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
@@ -231,16 +246,28 @@ static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, in
     const double *p_nold = iter <= 2 ? one : d_b + (iter - 2);
     unsigned int *ticket = reinterpret_cast<unsigned int *>(ctx->d_scal + 4);    // zero between launches (reset by the last block)
     int ndot = -1;
-    if (hxv_uses_star(s)) {
+    if (s->pl) {
+        if (int rc = hxv_fiber(s, cur, u, ctx->d_dotpart, &ndot)) return rc;
+    } else if (hxv_uses_star(s)) {
         if (int rc = hxv_star_dot(s, cur, u, ctx->d_dotpart, &ndot)) return rc;
     } else if (int rc = hxv_dispatch(s, cur, u)) return rc;
-    if (ndot >= 0) {
+    const bool sh = is_sharded(s);
+    if (ndot >= 0 && sh) {
+        // partial <w,u> of the local pair tiles -> sum over the ranks -> / b^2
+        k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_dotpart, ndot, d_a + (iter - 1), 0);
+        if (int rc = comm_allreduce_sum(ctx, d_a + (iter - 1), 1)) return rc;
+        k_fin<<<1, 1, 0, ctx->stream>>>(d_a + (iter - 1), 2, p_ncur);
+    } else if (ndot >= 0) {
         k_lanc_alpha<<<1, 256, 0, ctx->stream>>>(ctx->d_dotpart, ndot, p_ncur, d_a + (iter - 1));
     } else {
         k_dot_alpha<<<nb, kRedThreads, 0, ctx->stream>>>(cur, u, n, ctx->d_partials, p_ncur, d_a + (iter - 1), ticket);
     }
     k_lanc_c_norm<<<nb, kRedThreads, 0, ctx->stream>>>(old, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials,
-                                                       d_b + iter, ticket);
+                                                       d_b + iter, ticket, sh ? 0 : 1);
+    if (sh) {
+        if (int rc = comm_allreduce_sum(ctx, d_b + iter, 1)) return rc;
+        k_fin<<<1, 1, 0, ctx->stream>>>(d_b + iter, 1, nullptr);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -251,7 +278,13 @@ static int normalise(edgpu_sector *s, double *v)
     const int64_t n = s->nalloc;
     const int nb = red_blocks(n);
     k_dot<<<nb, kRedThreads, 0, ctx->stream>>>(v, v, n, ctx->d_partials);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, ctx->d_scal + kScalB, 1);
+    if (is_sharded(s)) {
+        k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, ctx->d_scal + kScalB, 0);
+        if (int rc = comm_allreduce_sum(ctx, ctx->d_scal + kScalB, 1)) return rc;
+        k_fin<<<1, 1, 0, ctx->stream>>>(ctx->d_scal + kScalB, 1, nullptr);
+    } else {
+        k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partials, nb, ctx->d_scal + kScalB, 1);
+    }
     k_div<<<nb, kRedThreads, 0, ctx->stream>>>(v, ctx->d_scal + kScalB, n);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
@@ -266,6 +299,7 @@ extern "C" int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlan
     if (!s || !v || v->s != s) return s ? edgpu_fail(s->ctx, "edgpu_lanczos_tridiag: bad vector/sector") : 1;
     edgpu_ctx *ctx = s->ctx;
     if (nlanc < 1 || nlanc > kLancMax) return edgpu_fail(ctx, "edgpu_lanczos_tridiag: nlanc=%d out of range", nlanc);
+    if (int rc = check_comm(s)) return rc;
     double *cur = v->d, *old, *u;
     if (int rc = sector_work(s, 0, &old)) return rc;
     if (int rc = sector_work(s, 1, &u)) return rc;
@@ -303,6 +337,7 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
     if (!s || !v0 || v0->s != s) return s ? edgpu_fail(s->ctx, "edgpu_lanczos_gs: bad vector/sector") : 1;
     edgpu_ctx *ctx = s->ctx;
     if (nitermax < 1 || nitermax > kLancMax - 1) return edgpu_fail(ctx, "edgpu_lanczos_gs: nitermax=%d out of range", nitermax);
+    if (int rc = check_comm(s)) return rc;
     if (ncheck < 1) ncheck = 10;
     const int64_t n = s->nalloc;
     double *w0, *w1, *w2;

@@ -14,7 +14,7 @@ int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 // mode 2: ref (real) <- internal        ; 3: interleaved complex (imag=0) <- internal
 // mode 4: internal <- imag part of complex source ; 5: complex.imag <- internal (real part untouched)
 __global__ void __launch_bounds__(256)
-k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, int64_t ld,
+k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, VAddr va,
           const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw,
           const double *__restrict__ src, double *__restrict__ dst)
 {
@@ -24,14 +24,15 @@ k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, int64_t ld
     const int64_t iu = r2i_up ? (int64_t)r2i_up[ru] : ru;
     for (int64_t rd = rd_begin + blockIdx.y; rd < rd_end; rd += gridDim.y) {
         const int64_t id = r2i_dw ? (int64_t)r2i_dw[rd] : rd;
-        const int64_t iref = (rd - rd_begin) * dim_up + ru, iint = id * ld + iu;
+        const int64_t iref = (rd - rd_begin) * dim_up + ru, iint = va(id, iu);
+        // iint < 0: the element belongs to a pair tile of another rank (sharded vectors): nothing to import, zero on export
         switch (mode) {
-        case 0: dst[iint] = src[iref]; break;
-        case 1: dst[iint] = src[2 * iref]; break;
-        case 2: dst[iref] = src[iint]; break;
-        case 3: dst[2 * iref] = src[iint]; dst[2 * iref + 1] = 0.0; break;
-        case 4: dst[iint] = src[2 * iref + 1]; break;
-        case 5: dst[2 * iref + 1] = src[iint]; break;
+        case 0: if (iint >= 0) dst[iint] = src[iref]; break;
+        case 1: if (iint >= 0) dst[iint] = src[2 * iref]; break;
+        case 2: dst[iref] = iint >= 0 ? src[iint] : 0.0; break;
+        case 3: dst[2 * iref] = iint >= 0 ? src[iint] : 0.0; dst[2 * iref + 1] = 0.0; break;
+        case 4: if (iint >= 0) dst[iint] = src[2 * iref + 1]; break;
+        case 5: dst[2 * iref + 1] = iint >= 0 ? src[iint] : 0.0; break;
         }
     }
 }
@@ -42,7 +43,7 @@ static dim3 grid2d(const edgpu_sector *s) {
 
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst)
 {
-    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, 0, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, src, dst);
+    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, 0, s->dim_dw, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
@@ -52,7 +53,7 @@ int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const 
 {
     if (rd1 <= rd0) return 0;
     dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)std::min<int64_t>(rd1 - rd0, 32768));
-    k_convert<<<grid, 256, 0, st>>>(mode, s->dim_up, rd0, rd1, s->ld, s->up->ref2int, s->dw->ref2int, src, dst);
+    k_convert<<<grid, 256, 0, st>>>(mode, s->dim_up, rd0, rd1, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
@@ -73,7 +74,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 }
 
 __global__ void __launch_bounds__(256)
-k_fill_random(int uniform, uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_t ld,
+k_fill_random(int uniform, uint64_t seed, int64_t dim_up, int64_t dim_dw, VAddr va,
               const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw, double *__restrict__ dst)
 {
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,6 +83,8 @@ k_fill_random(int uniform, uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_
     for (int64_t rd = blockIdx.y; rd < dim_dw; rd += gridDim.y) {
         const int64_t id = r2i_dw ? (int64_t)r2i_dw[rd] : rd;
         const uint64_t idx = (uint64_t)(rd * dim_up + ru);
+        const int64_t ia = va(id, iu);
+        if (ia < 0) continue;                                 // pair tile of another rank
         uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         const uint64_t a = ((uint64_t)c[0] << 21) ^ (uint64_t)(c[1] >> 11);
@@ -91,16 +94,16 @@ k_fill_random(int uniform, uint64_t seed, int64_t dim_up, int64_t dim_dw, int64_
         if (uniform) {
             // (a52 + 0.5)/2^51 - 1 in (-1,1): every step is exact in fp64 => bit-identical to the host generator
             const uint64_t a52 = ((uint64_t)c[0] << 20) ^ (uint64_t)(c[1] >> 12);
-            dst[id * ld + iu] = ((double)a52 + 0.5) * (1.0 / 2251799813685248.0) - 1.0;
+            dst[ia] = ((double)a52 + 0.5) * (1.0 / 2251799813685248.0) - 1.0;
         } else {
-            dst[id * ld + iu] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+            dst[ia] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
         }
     }
 }
 
 int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst)
 {
-    k_fill_random<<<grid2d(s), 256, 0, s->ctx->stream>>>(uniform, seed, s->dim_up, s->dim_dw, s->ld, s->up->ref2int, s->dw->ref2int, dst);
+    k_fill_random<<<grid2d(s), 256, 0, s->ctx->stream>>>(uniform, seed, s->dim_up, s->dim_dw, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, dst);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
@@ -109,7 +112,7 @@ int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst)
 // sign rule of ED_SETUP.f90:1080-1106 on the full word: an up operator at bit a sees the up bits below a; a down
 // operator additionally passes all n_up up bits.  Output is written everywhere (zero where the operator kills).
 __global__ void __launch_bounds__(256)
-k_apply_c(int bit, int is_dw, int nup_in, int64_t dim_up_o, int64_t dim_dw_o, int64_t ld_o, int64_t ld_i,
+k_apply_c(int bit, int is_dw, int nup_in, int64_t dim_up_o, int64_t dim_dw_o, VAddr va_o, VAddr va_i,
           const uint32_t *__restrict__ cfg_up_o, const uint32_t *__restrict__ cfg_dw_o,
           const uint32_t *__restrict__ rank_up_i, const uint32_t *__restrict__ rank_dw_i,
           const double *__restrict__ in, double *__restrict__ out)
@@ -126,9 +129,10 @@ k_apply_c(int bit, int is_dw, int nup_in, int64_t dim_up_o, int64_t dim_dw_o, in
         double val = 0.0;
         if (iu != 0xFFFFFFFFu && id != 0xFFFFFFFFu) {         // popcount of the source matches the input sector
             int par = is_dw ? (nup_in + __popc(ds & (m - 1u))) : __popc(us & (m - 1u));
-            val = (par & 1) ? -in[(int64_t)id * ld_i + iu] : in[(int64_t)id * ld_i + iu];
+            const double vin = in[va_i((int64_t)id, (int64_t)iu)];
+            val = (par & 1) ? -vin : vin;
         }
-        out[rd * ld_o + ru] = val;
+        out[va_o(rd, ru)] = val;
     }
 }
 
@@ -147,7 +151,8 @@ extern "C" int edgpu_apply_c(edgpu_sector *si, edgpu_sector *so, int32_t isite, 
     dim3 grid((unsigned)((so->dim_up + 255) / 256), (unsigned)(so->dim_dw < 32768 ? so->dim_dw : 32768));
     // The toggled bit must be SET in the output for cdg and CLEAR for c: the rank LUT of the input sector rejects
     // sources with the wrong popcount, which is exactly that condition.
-    k_apply_c<<<grid, 256, 0, ctx->stream>>>(bit, is_dw, si->nup, so->dim_up, so->dim_dw, so->ld, si->ld,
+    if (si->shard_nranks > 1 || so->shard_nranks > 1) return edgpu_fail(ctx, "edgpu_apply_c: not available on sharded sectors (the seed is built on one rank)");
+    k_apply_c<<<grid, 256, 0, ctx->stream>>>(bit, is_dw, si->nup, so->dim_up, so->dim_dw, sector_vaddr(so), sector_vaddr(si),
                                             so->up->cfg, so->dw->cfg, si->up->rank, si->dw->rank, in->d, out->d);
     CUDA_TRY(ctx, cudaGetLastError());
     if (int rc = vec_dot(ctx, out->d, out->d, so->nalloc, ctx->d_scal)) return rc;
@@ -163,7 +168,7 @@ extern "C" int edgpu_apply_c(edgpu_sector *si, edgpu_sector *so, int32_t isite, 
 // out = 1/2 (n_up - n_dw) in   over the impurity levels selected by `mask` (one orbital, or all of them for S_z^tot)
 // charge seeds (ED_GF_CHIDENS.f90:126-133, 227-234): out = (n_up + n_dw) in            (cdw = +1, scale = 1)
 __global__ void __launch_bounds__(256)
-k_apply_sz(uint32_t mask, double cdw, double scale, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t *__restrict__ cfg_up,
+k_apply_sz(uint32_t mask, double cdw, double scale, int64_t dim_up, int64_t dim_dw, VAddr va, const uint32_t *__restrict__ cfg_up,
            const uint32_t *__restrict__ cfg_dw, const double *__restrict__ in, double *__restrict__ out)
 {
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,7 +176,8 @@ k_apply_sz(uint32_t mask, double cdw, double scale, int64_t dim_up, int64_t dim_
     const int nu = __popc(cfg_up[ru] & mask);
     for (int64_t rd = blockIdx.y; rd < dim_dw; rd += gridDim.y) {
         const double sgn = (double)nu + cdw * (double)__popc(cfg_dw[rd] & mask);
-        out[rd * ld + ru] = scale * sgn * in[rd * ld + ru];
+        const int64_t a = va(rd, ru);
+        if (a >= 0) out[a] = scale * sgn * in[a];
     }
 }
 
@@ -198,7 +204,7 @@ static int apply_diag_seed(edgpu_sector *s, int32_t iorb, double cdw, double sca
     if (in->d == out->d) return edgpu_fail(ctx, "edgpu_apply_sz: in-place application is not allowed");
     const uint32_t mask = iorb == 0 ? (1u << norb) - 1u : 1u << (iorb - 1);
     dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)(s->dim_dw < 32768 ? s->dim_dw : 32768));
-    k_apply_sz<<<grid, 256, 0, ctx->stream>>>(mask, cdw, scale, s->dim_up, s->dim_dw, s->ld, s->up->cfg, s->dw->cfg, in->d, out->d);
+    k_apply_sz<<<grid, 256, 0, ctx->stream>>>(mask, cdw, scale, s->dim_up, s->dim_dw, sector_vaddr(s), s->up->cfg, s->dw->cfg, in->d, out->d);
     CUDA_TRY(ctx, cudaGetLastError());
     if (int rc = vec_dot(ctx, out->d, out->d, s->nalloc, ctx->d_scal)) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -212,7 +218,7 @@ static int apply_diag_seed(edgpu_sector *s, int32_t iorb, double cdw, double sca
 // ---- observables: joint distribution of the impurity bits -------------------------------------------------
 // rowsum[rd][ui] = sum_{ru : imp(u)=ui} gs[rd][ru]^2 ; the host combines rows by imp(d) (fixed order => deterministic).
 __global__ void __launch_bounds__(256)
-k_obs_rows(int norb, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t *__restrict__ cfg_up,
+k_obs_rows(int norb, int64_t dim_up, int64_t dim_dw, VAddr va, const uint32_t *__restrict__ cfg_up,
            const double *__restrict__ gs, double *__restrict__ rowsum)
 {
     extern __shared__ double sh[];                      // [nimp][256]
@@ -221,7 +227,8 @@ k_obs_rows(int norb, int64_t dim_up, int64_t dim_dw, int64_t ld, const uint32_t 
     for (int64_t rd = blockIdx.x; rd < dim_dw; rd += gridDim.x) {
         for (int k = 0; k < nimp; k++) sh[k * 256 + threadIdx.x] = 0.0;
         for (int64_t ru = threadIdx.x; ru < dim_up; ru += 256) {
-            const double g = gs[rd * ld + ru];
+            const int64_t a = va(rd, ru);
+            const double g = a >= 0 ? gs[a] : 0.0;
             sh[(cfg_up[ru] & mask) * 256 + threadIdx.x] += g * g;
         }
         __syncthreads();
@@ -245,7 +252,7 @@ extern "C" int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double pe
     double *d_rows = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&d_rows, sizeof(double) * (size_t)s->dim_dw * nimp));
     const unsigned nb = (unsigned)(s->dim_dw < 4096 ? s->dim_dw : 4096);
-    k_obs_rows<<<nb, 256, sizeof(double) * 256 * nimp, ctx->stream>>>(norb, s->dim_up, s->dim_dw, s->ld, s->up->cfg, gs->d, d_rows);
+    k_obs_rows<<<nb, 256, sizeof(double) * 256 * nimp, ctx->stream>>>(norb, s->dim_up, s->dim_dw, sector_vaddr(s), s->up->cfg, gs->d, d_rows);
     CUDA_TRY(ctx, cudaGetLastError());
     std::vector<double> rows((size_t)s->dim_dw * nimp);
     std::vector<uint32_t> cfgd((size_t)s->dim_dw);

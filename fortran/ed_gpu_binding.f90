@@ -116,6 +116,39 @@ MODULE ED_GPU_BINDING
        integer(c_int32_t),value :: iorb,normalise
        real(c_double)           :: norm
      end function edgpu_apply_sz
+     integer(c_int) function edgpu_apply_n(sec,iorb,vin,vout,normalise,norm) bind(C,name="edgpu_apply_n")
+       import :: c_ptr,c_int,c_int32_t,c_double
+       type(c_ptr),value        :: sec,vin,vout
+       integer(c_int32_t),value :: iorb,normalise
+       real(c_double)           :: norm
+     end function edgpu_apply_n
+     integer(c_int) function edgpu_sector_drop_csr(s) bind(C,name="edgpu_sector_drop_csr")
+       import :: c_int,c_ptr
+       type(c_ptr),value :: s
+     end function edgpu_sector_drop_csr
+     integer(c_int) function edgpu_sector_build_shard(ctx,nup,ndw,rank,nranks,s) bind(C,name="edgpu_sector_build_shard")
+       import :: c_int,c_ptr,c_int32_t
+       type(c_ptr),value        :: ctx
+       integer(c_int32_t),value :: nup,ndw,rank,nranks
+       type(c_ptr),intent(out)  :: s
+     end function edgpu_sector_build_shard
+     integer(c_int) function edgpu_comm_unique_id(ctx,id) bind(C,name="edgpu_comm_unique_id")
+       import :: c_int,c_ptr,c_char
+       type(c_ptr),value      :: ctx
+       character(kind=c_char) :: id(128)
+     end function edgpu_comm_unique_id
+     integer(c_int) function edgpu_comm_init(ctx,id,rank,nranks) bind(C,name="edgpu_comm_init")
+       import :: c_int,c_ptr,c_char,c_int32_t
+       type(c_ptr),value        :: ctx
+       character(kind=c_char)   :: id(128)
+       integer(c_int32_t),value :: rank,nranks
+     end function edgpu_comm_init
+     integer(c_int) function edgpu_vec_upload(v,host,is_cplx) bind(C,name="edgpu_vec_upload")
+       import :: c_int,c_ptr,c_int32_t,c_double
+       type(c_ptr),value        :: v
+       real(c_double)           :: host(*)
+       integer(c_int32_t),value :: is_cplx
+     end function edgpu_vec_upload
      integer(c_int) function edgpu_observables(s,gs,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot) bind(C,name="edgpu_observables")
        import :: c_int,c_ptr,c_double
        type(c_ptr),value            :: s,gs
@@ -126,7 +159,8 @@ MODULE ED_GPU_BINDING
 
   public :: gpu_ctx
   public :: gpu_init, gpu_finalize, gpu_set_hamiltonian, gpu_check
-  public :: gpu_lanc_eigh, gpu_lanc_gf_chain, gpu_observables
+  public :: gpu_lanc_eigh, gpu_lanc_gf_chain, gpu_lanc_spinchi_chain, gpu_lanc_denschi_chain, gpu_observables
+  public :: gpu_comm_init, gpu_shard_lanc_tridiag
   public :: edgpu_sector_build, edgpu_sector_free, edgpu_vec_free, edgpu_hxv
 
 contains
@@ -185,6 +219,8 @@ contains
     call gpu_check(edgpu_vec_alloc(sec,vec),"gpu_lanc_eigh")
     call gpu_check(edgpu_vec_fill_uniform(vec,1234567_c_int64_t),"gpu_lanc_eigh")
     call gpu_check(edgpu_lanczos_gs(sec,vec,int(Nitermax,c_int32_t),tol,10_c_int32_t,e0,nlanc,c_null_ptr,c_null_ptr),"sp_lanc_eigh")
+    ! delete_Hv_sector (ED_DIAG.f90:186): the stored matrix goes, the sector handle stays in the state list
+    if(sparse_H)call gpu_check(edgpu_sector_drop_csr(sec),"delete_Hv_sector")
   end subroutine gpu_lanc_eigh
 
   !> replaces one half of lanc_build_gf_normal_c (ED_GF_NORMAL.f90:150-200 for cdg, :203-253 for c):
@@ -197,13 +233,18 @@ contains
     type(c_ptr)             :: sec_j,vv
     integer(c_int32_t)      :: nused
     integer(c_int)          :: ierr
+    integer(c_int64_t)      :: jdim,jdimup,jdimdw
     call gpu_check(edgpu_sector_build(gpu_ctx,int(jup,c_int32_t),int(jdw,c_int32_t),sec_j),"build_sector")
     call gpu_check(edgpu_vec_alloc(sec_j,vv),"gpu_lanc_gf_chain")
     call gpu_check(edgpu_apply_c(sec_i,sec_j,int(isite,c_int32_t),merge(1_c_int32_t,0_c_int32_t,dagger),vec_i,vv,1_c_int32_t,norm2),"apply_c")
-    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_j),"ed_buildH_c")
-    call gpu_check(edgpu_lanczos_tridiag(sec_j,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    alfa_=0d0; beta_=0d0
+    if(norm2>0d0)then              ! an annihilated seed contributes nothing: no 0/0 chain (host/ed_main.cpp build_gf)
+       call gpu_check(edgpu_sector_dim(sec_j,jdim,jdimup,jdimdw),"vecDim_Hv_sector")
+       if(sparse_H.AND.jdim>1)call gpu_check(edgpu_sector_build_csr(sec_j),"ed_buildH_c")
+       call gpu_check(edgpu_lanczos_tridiag(sec_j,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    endif
     ierr=edgpu_vec_free(vv)
-    ierr=edgpu_sector_free(sec_j)
+    ierr=edgpu_sector_free(sec_j)    ! frees the CSR with the sector
   end subroutine gpu_lanc_gf_chain
 
   !> replaces the seed loop + sp_lanc_tridiag of lanc_ed_build_spinChi_c (ED_GF_CHISPIN.f90:89-122; iorb=0: the S_z^tot
@@ -218,10 +259,66 @@ contains
     integer(c_int)          :: ierr
     call gpu_check(edgpu_vec_alloc(sec_i,vv),"gpu_lanc_spinchi_chain")
     call gpu_check(edgpu_apply_sz(sec_i,int(iorb,c_int32_t),vec_i,vv,1_c_int32_t,norm),"apply_sz")
-    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_i),"ed_buildH_c")
-    call gpu_check(edgpu_lanczos_tridiag(sec_i,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    alfa_=0d0; beta_=0d0
+    if(norm>0d0)then
+       if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_i),"ed_buildH_c")
+       call gpu_check(edgpu_lanczos_tridiag(sec_i,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+       if(sparse_H)call gpu_check(edgpu_sector_drop_csr(sec_i),"delete_Hv_sector")
+    endif
     ierr=edgpu_vec_free(vv)
   end subroutine gpu_lanc_spinchi_chain
+
+  !> replaces the seed loop + sp_lanc_tridiag of lanc_ed_build_densChi_diag_c (ED_GF_CHIDENS.f90:122-152; iorb=0: the total
+  !> charge variant lanc_ed_build_densChi_tot_c, :223-253).  Seed = (n_up+n_dw)|gs> of orbital iorb; norm = |seed|.
+  subroutine gpu_lanc_denschi_chain(sec_i,vec_i,iorb,sparse_H,nlanc,norm,alfa_,beta_)
+    type(c_ptr),intent(in)  :: sec_i,vec_i
+    integer,intent(in)      :: iorb,nlanc
+    logical,intent(in)      :: sparse_H
+    real(8),intent(out)     :: norm,alfa_(nlanc),beta_(nlanc)
+    type(c_ptr)             :: vv
+    integer(c_int32_t)      :: nused
+    integer(c_int)          :: ierr
+    call gpu_check(edgpu_vec_alloc(sec_i,vv),"gpu_lanc_denschi_chain")
+    call gpu_check(edgpu_apply_n(sec_i,int(iorb,c_int32_t),vec_i,vv,1_c_int32_t,norm),"apply_n")
+    alfa_=0d0; beta_=0d0
+    if(norm>0d0)then
+       if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec_i),"ed_buildH_c")
+       call gpu_check(edgpu_lanczos_tridiag(sec_i,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+       if(sparse_H)call gpu_check(edgpu_sector_drop_csr(sec_i),"delete_Hv_sector")
+    endif
+    ierr=edgpu_vec_free(vv)
+  end subroutine gpu_lanc_denschi_chain
+
+  !> MPI build (ED_MAIN.f90:62-71 ed_set_MpiComm): one process per GPU.  Rank 0 creates the NCCL id, MPI broadcasts it.
+  !> Call once after gpu_init.  `comm` is the MPI communicator of the solver (MpiComm).
+  subroutine gpu_comm_init(comm,rank,nranks)
+    integer,intent(in)     :: comm,rank,nranks
+    character(kind=c_char) :: id(128)
+    integer                :: ierr
+    if(rank==0)call gpu_check(edgpu_comm_unique_id(gpu_ctx,id),"ncclGetUniqueId")
+    call MPI_Bcast(id,128,MPI_CHARACTER,0,comm,ierr)
+    call gpu_check(edgpu_comm_init(gpu_ctx,id,int(rank,c_int32_t),int(nranks,c_int32_t)),"ncclCommInitRank")
+  end subroutine gpu_comm_init
+
+  !> replaces  call sp_lanc_tridiag(MpiComm,spHtimesV_cc,vvloc,alfa_,beta_)  of the MPI build (ED_GF_NORMAL.f90:187-192 with
+  !> spHtimesV_cc => directMatVec_MPI_cc, ED_HAMILTONIAN_DIRECT_HxV.f90:97-195): the sector is sharded by conserved
+  !> occupation pairs, every rank passes the FULL seed in the reference order (it keeps its own pairs), no Allgatherv.
+  subroutine gpu_shard_lanc_tridiag(jup,jdw,rank,nranks,vvinit,nlanc,alfa_,beta_)
+    integer,intent(in)      :: jup,jdw,rank,nranks,nlanc
+    complex(8),intent(in)   :: vvinit(:)
+    real(8),intent(out)     :: alfa_(nlanc),beta_(nlanc)
+    type(c_ptr)             :: sec_j,vv
+    integer(c_int32_t)      :: nused
+    integer(c_int)          :: ierr
+    real(c_double),pointer  :: raw(:)
+    call gpu_check(edgpu_sector_build_shard(gpu_ctx,int(jup,c_int32_t),int(jdw,c_int32_t),int(rank,c_int32_t),int(nranks,c_int32_t),sec_j),"build_sector")
+    call gpu_check(edgpu_vec_alloc(sec_j,vv),"gpu_shard_lanc_tridiag")
+    call c_f_pointer(c_loc(vvinit),raw,[2*size(vvinit)])
+    call gpu_check(edgpu_vec_upload(vv,raw,1_c_int32_t),"vvinit")
+    call gpu_check(edgpu_lanczos_tridiag(sec_j,vv,int(nlanc,c_int32_t),1d-13,alfa_,beta_,nused),"sp_lanc_tridiag")
+    ierr=edgpu_vec_free(vv)
+    ierr=edgpu_sector_free(sec_j)
+  end subroutine gpu_shard_lanc_tridiag
 
   !> replaces the i-loop of observables_impurity (ED_OBSERVABLES.f90:127-158) for one state
   subroutine gpu_observables(sec,vec,peso,dens,dens_up,dens_dw,docc,magz,sz2,n2,s2tot)

@@ -35,11 +35,13 @@ typedef struct {
     int32_t norb, nbath, nspin;
     int32_t hfmode;          /* HFMODE */
     int32_t layout;          /* 0 = auto, 1 = reference (colex) order on device, 2 = star-product order */
-    int32_t hxv_kernel;      /* 0 = auto, 1 = generic table kernel, 2 = star-product tile kernels */
+    int32_t hxv_kernel;      /* 0 = auto, 1 = generic table kernel, 2 = star-product tile kernels (one Dimdw x ld tile),
+                                3 = fiber kernels on the pair-tile layout (hxv_fiber.cu; auto picks them for sectors >= 2^21 states) */
     int32_t reserved[8];     /* reserved[0]: test hooks (bit 0: 2-column down strips, bit 1: single-stage up pass, bit 2: generic tile
                                 pass only, bit 3: no copy-engine kernels, bit 4: copy-engine kernels for every block size,
                                 bit 5: programmatic dependent launch of the copy-engine kernels, bit 6 (+ bit 7): at most
-                                2 (3) stages in the up pipeline, bit 9: 2 instead of 3 x images in the up pipeline) */
+                                2 (3) stages in the up pipeline, bit 9: 2 instead of 3 x images in the up pipeline);
+                                fiber kernels: bit 2 = thread-per-element pair kernels only, bit 4 = fiber kernels for every block size */
 } edgpu_params;
 
 /* init_ed_structure + setup_pointers_normal (ED_MAIN.f90:73,91; ED_SETUP.f90:150-360,372-496).
@@ -60,6 +62,23 @@ int edgpu_set_hamiltonian(edgpu_ctx *ctx, const double *bath, int32_t bath_len, 
  * ED_HAMILTONIAN.f90:42-149).  Device-resident per-spin tables; the full map is never needed by H*v. */
 int edgpu_sector_build(edgpu_ctx *ctx, int32_t nup, int32_t ndw, edgpu_sector **s);
 int edgpu_sector_free(edgpu_sector *s);
+/* The same sector SHARDED over `nranks` processes (one per GPU): H is block diagonal over (down-block, up-block) pairs of
+ * conserved star occupations, so whole pairs are dealt to the ranks (longest-processing-time-first over their sizes) and a
+ * rank stores and multiplies only its own pairs -- H*v needs no exchange at all, only the Lanczos scalars are summed
+ * (edgpu_shard_lanczos_tridiag).  Replaces the row-block decomposition + MPI_Allgatherv of directMatVec_MPI_cc
+ * (ED_HAMILTONIAN_DIRECT_HxV.f90:97-195, ED_HAMILTONIAN.f90:56-62).  Vectors of such a sector hold the local pairs only;
+ * upload / fill / download address them by the global reference index (download writes 0 for foreign elements). */
+int edgpu_sector_build_shard(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int32_t rank, int32_t nranks, edgpu_sector **s);
+/* Communicator of the sharded path: the ONLY collective left is the sum of the Lanczos scalars (2 doubles per step), done
+ * with NCCL over NVLink/NVSwitch (libnccl.so.2 is loaded at run time).  Rank 0 calls edgpu_comm_unique_id, the host
+ * broadcasts the 128 bytes (MPI_Bcast in the reference's MPI world, ED_MAIN.f90:62-71 ed_set_MpiComm), every rank calls
+ * edgpu_comm_init.  Afterwards edgpu_vec_dot, edgpu_lanczos_tridiag and edgpu_lanczos_gs on a sharded sector return the
+ * GLOBAL results on every rank (same call sequence on all ranks, like the reference's MPI Lanczos). */
+int edgpu_comm_unique_id(edgpu_ctx *ctx, unsigned char id[128]);
+int edgpu_comm_init(edgpu_ctx *ctx, const unsigned char id[128], int32_t rank, int32_t nranks);
+int edgpu_comm_finalize(edgpu_ctx *ctx);
+/* layout_kind: 0 = one Dimdw x ld tile, 3 = pair tiles; nalloc: doubles stored per vector on this rank */
+int edgpu_sector_info(const edgpu_sector *s, int32_t *layout_kind, int64_t *nalloc, int32_t *shard_rank, int32_t *shard_nranks);
 int edgpu_sector_dim(const edgpu_sector *s, int64_t *dim, int64_t *dim_up, int64_t *dim_dw);
 /* type(sector_map)%map (ED_VARS_GLOBAL.f90:28-31), 64-bit, entries [first, first+count): built by a device
  * kernel and copied to host_out. */
@@ -73,6 +92,8 @@ int edgpu_vec_alloc(edgpu_sector *s, edgpu_vec **v);
 int edgpu_vec_free(edgpu_vec *v);
 int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cplx);    /* complex: real part is taken */
 int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_cplx); /* complex: imag = 0 */
+/* reference rows [rd0, rd1) (down-spin colex ranks) of the vector: host[(rd - rd0)*DimUp + ru], real */
+int edgpu_vec_download_rows(const edgpu_vec *v, int64_t rd0, int64_t rd1, double *host);
 int edgpu_vec_fill_normal(edgpu_vec *v, uint64_t seed);   /* Philox4x32-10 N(0,1), element index = counter */
 /* Philox uniforms in (-1,1), exact arithmetic (bit-identical to the oracle's generator): Lanczos start vector,
  * standing in for the random_number() start of sp_lanc_eigh (.repo/PLAIN_LANCZOS.f90:310-318) */

@@ -755,3 +755,69 @@ void ora_philox_normal(uint64_t seed, int64_t i0, int64_t n, double *out)
         out[q] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
     }
 }
+
+/* ------------------------------------------------------------------ window oracle ---------------------------- */
+/* Rows of H v for sectors too large to hold map + complex vectors on the host (Ns=16: 4 GB, Ns=18: 57 GB).
+ * Same per-row rule as ora_gather_hxv (diag_terms / offdiag_terms, i.e. direct/HxV*.f90 in stored/row form);
+ * only the two LOOKUPS are replaced by closed forms that tests/test_oracle_invariants.py pins to the literal ones:
+ *   map(i)            -> colex unrank of (i mod DimUp, i / DimUp)     (ED_SETUP.f90:899-916 ordering)
+ *   binary_search(k)  -> colex rank of the two Ns-bit halves of k     (ED_SETUP.f90:1307-1324)
+ * and vin(j) is the Philox uniform with counter j (ora_philox_uniform), imaginary part 0, so nothing of size Dim is
+ * ever stored.  rows[n]: 0-based reference indices i; out[n]: Re (H v)(i)  (Im is identically 0 for real vin). */
+static uint64_t colex_unrank(int64_t r, int n)
+{
+    uint64_t w = 0;
+    for (int k = n; k >= 1; k--) {
+        int p = k - 1;
+        while (ora_binomial(p + 1, k) <= r) p++;
+        w |= 1ull << p;
+        r -= ora_binomial(p, k);
+    }
+    return w;
+}
+
+static int64_t colex_rank(uint64_t w)
+{
+    int64_t r = 0;
+    int i = 1;
+    for (int p = 0; p < 64; p++)
+        if ((w >> p) & 1ull) { r += ora_binomial(p, i); i++; }
+    return r;
+}
+
+uint64_t ora_map_entry(int Ns, int nup, int ndw, int64_t i)
+{
+    const int64_t dim_up = ora_binomial(Ns, nup);
+    (void)ndw;
+    return colex_unrank(i % dim_up, nup) | (colex_unrank(i / dim_up, ndw) << Ns);
+}
+
+void ora_window_hxv(const ora_model *M, int nup, int ndw, uint64_t seed, const int64_t *rows, int64_t n, double *out)
+{
+    const int Ns = M->Ns;
+    const int64_t dim_up = ora_binomial(Ns, nup);
+    const uint64_t lo = (1ull << Ns) - 1ull;
+    ora_term t[ORA_MAXTERMS];
+    for (int64_t q = 0; q < n; q++) {
+        const int64_t i = rows[q];
+        const uint64_t m = ora_map_entry(Ns, nup, ndw, i);
+        cplx h[3];
+        diag_terms(M, m, h);
+        double vi;
+        ora_philox_uniform(seed, i, 1, &vi);
+        cplx acc = 0.0;
+        for (int part = 0; part < 3; part++) {
+            acc = acc + h[part] * vi;
+            int nt = offdiag_terms(M, m, part, t);
+            for (int k = 0; k < nt; k++) {
+                const uint64_t w = t[k].k;
+                if (__builtin_popcountll(w & lo) != nup || __builtin_popcountll(w >> Ns) != ndw) continue;   /* binary_search miss */
+                const int64_t j = colex_rank(w & lo) + colex_rank(w >> Ns) * dim_up;
+                double vj;
+                ora_philox_uniform(seed, j, 1, &vj);
+                acc = acc + conj(t[k].amp) * vj;
+            }
+        }
+        out[q] = creal(acc);
+    }
+}

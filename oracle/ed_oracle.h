@@ -95,6 +95,12 @@ void ora_observables(int Ns, int Norb, const uint64_t *map, int64_t dim, const d
                      double *dens, double *dens_up, double *dens_dw, double *docc, double *magz,
                      double *sz2, double *n2, double *s2tot);
 
+/* Window oracle for sectors whose map + vectors do not fit the host: rows of H v with vin = Philox uniforms
+ * (counter = reference index), map entries and binary searches replaced by colex (un)rank closed forms.
+ * ora_map_entry(i) = map(i+1) of build_sector (ED_SETUP.f90:899-916). */
+uint64_t ora_map_entry(int Ns, int nup, int ndw, int64_t i);
+void ora_window_hxv(const ora_model *m, int nup, int ndw, uint64_t seed, const int64_t *rows, int64_t n, double *out);
+
 /* Counter-based N(0,1) generator shared with the CUDA library (Philox4x32-10 + Box-Muller). */
 void ora_philox_normal(uint64_t seed, int64_t i0, int64_t n, double *out);
 /* uniform in (-1,1); exact arithmetic, bit-identical on CPU and GPU (Lanczos start vectors) */

@@ -73,6 +73,9 @@ def lib():
     L.ora_observables.argtypes = [C.c_int, C.c_int, u64p, C.c_int64, dp, C.c_double] + [dp] * 8
     L.ora_philox_normal.argtypes = [C.c_uint64, C.c_int64, C.c_int64, dp]
     L.ora_philox_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_int64, dp]
+    L.ora_map_entry.restype = C.c_uint64
+    L.ora_map_entry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64]
+    L.ora_window_hxv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, i64p, C.c_int64, dp]
     L.ora_num_threads.restype = C.c_int
     L.ora_gather_hxv_mt.restype = C.c_double
     L.ora_gather_hxv_mt.argtypes = [C.c_void_p, u64p, C.c_int64, dp, dp, C.c_int64, C.c_int64, C.c_int]
@@ -218,6 +221,19 @@ def gather_hxv(model: Model, smap: np.ndarray, v: np.ndarray, i0=0, i1=None) -> 
     lib().ora_gather_hxv(model.h, _u64p(smap), smap.size, _dp(vin.view(np.float64)), _dp(hv.view(np.float64)),
                          i0, i1)
     return hv
+
+
+def window_hxv(model: Model, nup: int, ndw: int, seed: int, rows) -> np.ndarray:
+    """Re (H v)(i) for the reference indices `rows` with v = philox_uniform(seed): needs no map and no vector
+    (ora_window_hxv), so it works at Ns=16/18 where the literal oracle does not fit the host."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    out = np.empty(rows.size)
+    lib().ora_window_hxv(model.h, nup, ndw, seed, _i64p(rows), rows.size, _dp(out))
+    return out
+
+
+def map_entry(Ns, nup, ndw, i) -> int:
+    return int(lib().ora_map_entry(Ns, nup, ndw, int(i)))
 
 
 def stored_build(model: Model, smap: np.ndarray):
