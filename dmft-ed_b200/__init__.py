@@ -54,7 +54,7 @@ EDGPU_SYMBOLS = [
     "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
-    "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_apply_sz", "edgpu_apply_n", "edgpu_observables",
+    "edgpu_sector_dense", "edgpu_lanczos_gs", "edgpu_lanczos_eigs", "edgpu_lanczos_tridiag", "edgpu_apply_c", "edgpu_apply_sz", "edgpu_apply_n", "edgpu_observables",
     "edgpu_shard_ld", "edgpu_shard_hxv_dw", "edgpu_shard_hxv_up", "edgpu_shard_hxv_up_slabs", "edgpu_shard_perm",
     "edgpu_shard_hxv_up_peers", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_ipc_export", "edgpu_ipc_open", "edgpu_ipc_close", "edgpu_copy_async",
     "edgpu_bench_hxv", "edgpu_device_info", "edgpu_sync",
@@ -125,6 +125,7 @@ def lib():
     L.edgpu_sector_dense.argtypes = [vp, dp]
     L.edgpu_lanczos_gs.argtypes = [vp, vp, C.c_int32, C.c_double, C.c_int32, dp, i32p, dp, dp]
     L.edgpu_lanczos_tridiag.argtypes = [vp, vp, C.c_int32, C.c_double, dp, dp, i32p]
+    L.edgpu_lanczos_eigs.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_uint64, dp, C.POINTER(vp), i32p, i32p]
     L.edgpu_apply_c.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, dp]
     L.edgpu_apply_sz.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, dp]
     L.edgpu_apply_n.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, dp]
@@ -311,6 +312,20 @@ class Sector:
         b = np.zeros(nitermax + 1)
         self.ctx.check(lib().edgpu_lanczos_gs(self.h, v0.h, nitermax, threshold, ncheck, C.byref(e0), C.byref(nl), _p(a), _p(b)))
         return e0.value, nl.value, a[: nl.value], b[: nl.value]
+
+    def lanczos_eigs(self, neigen, ncv=None, tol=1e-12, maxrestart=300, seed=1234567):
+        """edgpu_lanczos_eigs: (evals[neigen], [Vec...], nconv, nmatvec)"""
+        ncv = ncv or 10 * neigen
+        ev = np.zeros(neigen)
+        hs = (C.c_void_p * neigen)()
+        nc, nm = C.c_int32(), C.c_int32()
+        self.ctx.check(lib().edgpu_lanczos_eigs(self.h, neigen, ncv, maxrestart, tol, seed, _p(ev), hs, C.byref(nc), C.byref(nm)))
+        vecs = []
+        for h in hs:
+            v = Vec.__new__(Vec)
+            v.s, v.h = self, C.c_void_p(h)
+            vecs.append(v)
+        return ev, vecs, nc.value, nm.value
 
     def lanczos_tridiag(self, v, nlanc, threshold=1e-13):
         a = np.zeros(nlanc)

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu comm.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
+SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu comm.cu eigs.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
 mkdir -p ../build
 OBJS=""
 PIDS=""

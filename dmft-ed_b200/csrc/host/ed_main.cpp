@@ -331,13 +331,28 @@ static int ed_diag(ed_solver *s)
                 if (!rc) rc = edgpu_vec_fill_uniform(v, 1234567ull);      // start vector (reference: random_number)
                 double e0 = 0;
                 int nl = 0;
+                if (!rc && in.lanc_method == 0 && neigen > 1) {
+                    // sp_eigh (ARPACK, ED_DIAG.f90:149-166): Neigen pairs from a basis of Nblock vectors (:98
+                    // Nblock = min(dim, lanc_ncv_factor*Neigen + lanc_ncv_add), defaults 10 and 0) -- needed to keep
+                    // EVERY member of a ground state that is degenerate inside the sector (:224-235)
+                    const int factor = in.reserved[0] > 0 ? in.reserved[0] : 10, add = in.reserved[1];
+                    const int ncv = (int)std::min<int64_t>(dim, (int64_t)factor * neigen + add);
+                    edgpu_vec_free(v); v = nullptr;
+                    std::vector<double> ev(neigen);
+                    std::vector<edgpu_vec *> vv(neigen, nullptr);
+                    int nconv = 0, nmv = 0;
+                    rc = edgpu_lanczos_eigs(sec, (int)neigen, ncv, std::max(1, in.lanc_niter), in.lanc_tolerance, 1234567ull, ev.data(), vv.data(), &nconv, &nmv);
+                    if (rc) { for (auto *q : vv) if (q) edgpu_vec_free(q); edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
+                    for (int64_t i = 0; i < neigen; i++) { evals.push_back(ev[i]); evecs.push_back(vv[i]); }
+                    s->sector_nlanc[{nup, ndw}] = nmv;
+                } else {
                 if (!rc) rc = edgpu_lanczos_gs(sec, v, (int)nitermax, in.lanc_tolerance, 10, &e0, &nl, nullptr, nullptr);
                 if (rc) { if (v) edgpu_vec_free(v); edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
-                // lanc_method=arpack asks for Neigen pairs; at T=0 only states within gs_threshold of the minimum are
-                // kept (:224-235), so the device solver returns the lowest pair (finite-T spectra: out of scope).
+                // lanc_nstates_sector = 1 (or lanc_method=lanczos): the lowest pair by plain Lanczos (sp_lanc_eigh, :173-181)
                 evals.push_back(e0);
                 evecs.push_back(v);
                 s->sector_nlanc[{nup, ndw}] = nl;
+                }
                 if (in.ed_sparse_H) edgpu_sector_drop_csr(sec);
             } else {
                 H.assign((size_t)dim * dim, 0.0);

@@ -167,6 +167,8 @@ struct PairLayout {
     int ng1 = 0, ng2 = 0;
     int64_t g1_elems = 0, g2_elems = 0;
     int nl = 0;
+    int slot = kSlot;                                      // pipeline slot size the tile schedules were built for
+    int skip1 = 0, skip2 = 0;                              // test hooks: leave a pass to the thread-per-element kernels
     std::map<const double *, CUtensorMap *> tmaps;         // per source pointer: one 3-D map per pair (device array)
     ~PairLayout()
     {
@@ -335,6 +337,16 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     P->nbd = (int)FD.blocks.size(); P->nbu = (int)FU.blocks.size(); P->nl = FU.nl;
     const int nbd = P->nbd, nbu = P->nbu;
     const bool force_fiber = (ctx->par.reserved[0] & 16) != 0, force_generic = (ctx->par.reserved[0] & 4) != 0;
+    const bool gen1 = force_generic || (ctx->par.reserved[0] & 1024) != 0, gen2 = force_generic || (ctx->par.reserved[0] & 2048) != 0;
+    if (ctx->par.reserved[0] & 4096) {
+        // test hook: shrink the pipeline slot so that the largest image of this sector needs BOTH slots (the two-slot
+        // path that only the 4900-configuration blocks of Ns=16 take in production)
+        int64_t big = 0;
+        for (const FibBlockDev &B : FU.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.C4 * 128);
+        for (const FibBlockDev &B : FD.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.nbox * B.BR * 128);
+        if (big > 256) P->slot = (int)std::min<int64_t>(kSlot, ((big / 2 + 127) / 128) * 128);
+    }
+    const int slot = P->slot;
     // ownership: LPT over pair sizes (deterministic: ties by pair index)
     std::vector<int64_t> psize((size_t)nbd * nbu);
     std::vector<int> order((size_t)nbd * nbu), owner((size_t)nbd * nbu, 0);
@@ -381,11 +393,11 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     for (int p = 0; p < (int)P->pairs.size(); p++) {
         const PairDev &pd = P->pairs[p];
         const FibBlockDev &BD = FD.blocks[pd.bi], &BU = FU.blocks[pd.bj];
-        const bool fu = !force_generic && BU.fiber && (force_fiber || BU.size >= kFibMinBlock);
-        const bool fd = !force_generic && BD.fiber && (force_fiber || BD.size >= kFibMinBlock);
+        const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock);
+        const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock);
         if (fu) {
             const int64_t bb = (int64_t)BU.C4 * 128;
-            int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, kSlot / bb));
+            int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, slot / bb));
             for (int a = 0; a < BD.R4; a += G) {
                 FibTile t; memset(&t, 0, sizeof(t));
                 t.pair = p; t.blk = pd.bj; t.a = a; t.b = std::min(G, BD.R4 - a);
@@ -396,7 +408,7 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
         } else { g1.push_back(p); P->g1_elems += (int64_t)BD.size * BU.size; }
         if (fd) {
             const int64_t sb = (int64_t)BD.nbox * BD.BR * 128;
-            int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, kSlot / sb));
+            int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, slot / sb));
             for (int a = 0; a < BU.C4; a += G) {
                 FibTile t; memset(&t, 0, sizeof(t));
                 t.pair = p; t.blk = pd.bi; t.a = a; t.b = std::min(G, BU.C4 - a);
@@ -493,6 +505,7 @@ struct FibArgs {
     const FibTile *tiles;
     int ntiles;
     uint32_t impmask;
+    int slot;                           // bytes per pipeline slot (kSlot; smaller in the two-slot test mode)
     const double *x;
     double *y;
     const double *e_dw;                 // pass 1: per-row diagonal energy and configuration word of the down spin
@@ -609,12 +622,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             int use[2] = {0, 0}, pos = 0;
             for (int i = 0; i < myn; i++) {
                 const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
-                const bool two = t.bytes > kSlot;
+                const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
                 if (use[s] > 0) fmbar_wait(bempty + 8 * s, (uint32_t)(use[s] - 1) & 1u);
                 if (two && use[1] > 0) fmbar_wait(bempty + 8, (uint32_t)(use[1] - 1) & 1u);
                 fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
-                const uint32_t dst = slot0 + (uint32_t)s * kSlot;
+                const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
                 const char *src = reinterpret_cast<const char *>(A.x + t.off);
                 for (int ofs = 0; ofs < t.bytes; ofs += 32768) {
                     const int n = t.bytes - ofs < 32768 ? t.bytes - ofs : 32768;
@@ -629,7 +642,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     int cuse[2] = {0, 0}, pos = 0;
     for (int i = 0; i < myn; i++) {
         const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
-        const bool two = t.bytes > kSlot;
+        const bool two = t.bytes > A.slot;
         const int s = two ? 0 : pos;
         fmbar_wait(bfull + 8 * s, (uint32_t)cuse[s] & 1u);
         const FibBlockDev BU = A.blk_f[t.blk];
@@ -654,7 +667,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                 dgbase = __ldg(A.e_dw + id);
                 impd = __ldg(A.cfg_dw + id) & A.impmask;
             }
-            const uint32_t img = slot0 + (uint32_t)s * kSlot + (uint32_t)g * band_bytes;
+            const uint32_t img = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * band_bytes;
             double *yband = A.y + t.off + (int64_t)g * BU.C4 * 16;
             fib::static_for<NL - 1>([&](auto mm) {
                 constexpr int M0 = decltype(mm)::value + 1;
@@ -752,12 +765,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
             for (int i = 0; i < myn; i++) {
                 const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
                 const FibBlockDev BD = A.blk_f[t.blk];
-                const bool two = t.bytes > kSlot;
+                const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
                 if (use[s] > 0) fmbar_wait(bempty + 8 * s, (uint32_t)(use[s] - 1) & 1u);
                 if (two && use[1] > 0) fmbar_wait(bempty + 8, (uint32_t)(use[1] - 1) & 1u);
                 fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
-                const uint32_t dst = slot0 + (uint32_t)s * kSlot;
+                const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
                 const uint32_t sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * 128u;
                 for (int g = 0; g < t.b; g++)
                     for (int b = 0; b < BD.nbox; b++)
@@ -773,7 +786,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
     const int warp = tid >> 5, lane = tid & 31;
     for (int i = 0; i < myn; i++) {
         const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
-        const bool two = t.bytes > kSlot;
+        const bool two = t.bytes > A.slot;
         const int s = two ? 0 : pos;
         fmbar_wait(bfull + 8 * s, (uint32_t)cuse[s] & 1u);
         const FibBlockDev BD = A.blk_f[t.blk];
@@ -791,7 +804,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
             const OuterEnt *ent = A.outer + BD.tab + (active ? o : 0);
             const int nslot = active ? ent->nslot : 0;
             const int wmax = __reduce_max_sync(0xffffffffu, nslot);
-            const uint32_t img = slot0 + (uint32_t)s * kSlot + (uint32_t)g * sbytes;
+            const uint32_t img = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * sbytes;
             double *ystrip = A.y + pd.base + (int64_t)(t.a + g) * 16;
             fib::static_for<NL - 1>([&](auto mm) {
                 constexpr int M0 = decltype(mm)::value + 1;
@@ -982,7 +995,7 @@ static int launch_fiber(edgpu_sector *s, const double *x, double *y, double *dot
     int nd = 0;
     FibArgs A;
     memset(&A, 0, sizeof(A));
-    A.pairs = P.d_pairs; A.x = x; A.y = y; A.impmask = (1u << ctx->ham.norb) - 1u;
+    A.pairs = P.d_pairs; A.x = x; A.y = y; A.impmask = (1u << ctx->ham.norb) - 1u; A.slot = P.slot;
     A.e_dw = s->dw->ediag; A.cfg_dw = s->dw->cfg; A.xtab = ctx->d_xtab;
     PairGenArgs G{};
     G.pairs = P.d_pairs; G.blk_u = FU.d_blocks; G.blk_d = FD.d_blocks; G.va = sector_vaddr(s);

@@ -41,7 +41,8 @@ typedef struct {
                                 pass only, bit 3: no copy-engine kernels, bit 4: copy-engine kernels for every block size,
                                 bit 5: programmatic dependent launch of the copy-engine kernels, bit 6 (+ bit 7): at most
                                 2 (3) stages in the up pipeline, bit 9: 2 instead of 3 x images in the up pipeline);
-                                fiber kernels: bit 2 = thread-per-element pair kernels only, bit 4 = fiber kernels for every block size */
+                                fiber kernels: bit 2 = thread-per-element pair kernels only, bit 4 = fiber kernels for every block size,
+                                bit 10 / 11 = pass 1 / pass 2 by the thread-per-element kernels, bit 12 = small pipeline slots (two-slot images) */
 } edgpu_params;
 
 /* init_ed_structure + setup_pointers_normal (ED_MAIN.f90:73,91; ED_SETUP.f90:150-360,372-496).
@@ -122,6 +123,12 @@ int edgpu_sector_dense(edgpu_sector *s, double *hmat);
  * nitermax+1 (blanc[0] unused, Fortran blanc(1)); may be NULL. */
 int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax, double threshold, int32_t ncheck,
                      double *e0, int32_t *nlanc, double *alanc, double *blanc);
+/* sp_eigh = ARPACK 'SA' (ED_DIAG.f90:149-166): the `neigen` lowest eigenpairs from a basis of `ncv` vectors
+ * (Nblock, ED_DIAG.f90:98) by thick-restart Lanczos with full re-orthogonalisation on the device (eigs.cu).
+ * tol = lanc_tolerance (ARPACK's residual criterion); evals[neigen] ascending; vecs[neigen] receives new vector handles
+ * (free with edgpu_vec_free); nconv = converged pairs, nmatvec = H*v applications. */
+int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, int32_t maxrestart, double tol, uint64_t seed,
+                       double *evals, edgpu_vec **vecs, int32_t *nconv, int32_t *nmatvec);
 /* sp_lanc_tridiag (ED_GF_NORMAL.f90:187-192,240-245; ancestor .repo/PLAIN_LANCZOS.f90:154-180).
  * v is normalised and destroyed.  alfa[nlanc], beta[nlanc] (beta[0] unused) are zero-filled first. */
 int edgpu_lanczos_tridiag(edgpu_sector *s, edgpu_vec *v, int32_t nlanc, double threshold,

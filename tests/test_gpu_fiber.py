@@ -1,7 +1,9 @@
 """GPU (B200): the pair-tile layout + fiber kernels (hxv_kernel=3, hxv_fiber.cu) against the oracle.
 
 debug flags: 16 = fiber kernels for every block they can take (also the tiny ones), 4 = thread-per-element pair kernels
-only, 0 = the production split (fiber kernels for blocks >= 256 configurations)."""
+only, 0 = the production split (fiber kernels for blocks >= 256 configurations), +4096 = small pipeline slots so that the
+largest images take BOTH slots (the path of the 4900-configuration blocks of Ns=16), 1024 / 2048 = one pass by the
+thread-per-element kernels."""
 import numpy as np
 import pytest
 
@@ -17,7 +19,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("flags", [16, 4, 0])
+@pytest.mark.parametrize("flags", [16, 4, 0, 16 + 4096, 16 + 1024, 16 + 2048])
 @pytest.mark.parametrize("name", ["2orb_nb2", "2orb_nb3", "3orb_nb2"])
 def test_fiber_hxv_matches_oracle_all_sectors(oracle, edb, name, flags):
     p, model, ctx, rng = make(oracle, edb, CASES[name], hxv_kernel=3, debug_flags=flags)
@@ -38,7 +40,7 @@ def test_fiber_hxv_matches_oracle_all_sectors(oracle, edb, name, flags):
     ctx.close()
 
 
-@pytest.mark.parametrize("flags", [16, 0])
+@pytest.mark.parametrize("flags", [16, 0, 16 + 4096])
 @pytest.mark.parametrize("name,sec", [("2orb_nb4_nspin2", (5, 5)), ("2orb_nb4_nspin2", (4, 6)), ("3orb_nb2", (4, 5)), ("2orb_nb3", (4, 4))])
 def test_fiber_medium_sectors_chain_and_seeds(oracle, edb, name, sec, flags):
     p, model, ctx, rng = make(oracle, edb, CASES[name], hxv_kernel=3, debug_flags=flags)
