@@ -50,7 +50,7 @@ class ed_input(C.Structure):
 # every symbol declared in include/edgpu.h and include/ed_b200.h (checked by tests/test_abi.py)
 EDGPU_SYMBOLS = [
     "edgpu_init", "edgpu_finalize", "edgpu_last_error", "edgpu_version", "edgpu_ns", "edgpu_set_hamiltonian",
-    "edgpu_sector_build", "edgpu_sector_build_shard", "edgpu_sector_info", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize", "edgpu_vec_download_rows", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
+    "edgpu_sector_build", "edgpu_sector_build_shard", "edgpu_sector_info", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize", "edgpu_comm_info", "edgpu_comm_allreduce_host", "edgpu_vec_download_rows", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
     "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",
     "edgpu_sector_build_csr", "edgpu_sector_drop_csr", "edgpu_sector_csr_nnz", "edgpu_sector_csr_download",
@@ -60,7 +60,7 @@ EDGPU_SYMBOLS = [
     "edgpu_bench_hxv", "edgpu_device_info", "edgpu_sync",
 ]
 ED_SYMBOLS = [
-    "ed_input_defaults", "ed_get_bath_dimension", "ed_init_solver", "ed_finalize_solver", "ed_last_error", "ed_solve",
+    "ed_input_defaults", "ed_get_bath_dimension", "ed_init_solver", "ed_finalize_solver", "ed_comm_unique_id", "ed_set_comm", "ed_last_error", "ed_solve",
     "ed_get_sigma_matsubara", "ed_get_sigma_real", "ed_get_gimp_matsubara", "ed_get_gimp_real",
     "ed_get_g0imp_matsubara", "ed_get_g0imp_real", "ed_get_dens", "ed_get_dens_up", "ed_get_dens_dw", "ed_get_docc",
     "ed_get_mag", "ed_get_sz2_n2", "ed_get_grids", "ed_get_spinchi", "ed_get_denschi", "ed_get_state_count", "ed_get_state", "ed_get_state_vector",
@@ -103,6 +103,10 @@ def lib():
     L.edgpu_comm_unique_id.argtypes = [vp, C.c_char_p]
     L.edgpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     L.edgpu_comm_finalize.argtypes = [vp]
+    L.edgpu_comm_info.argtypes = [vp, i32p, i32p]
+    L.edgpu_comm_allreduce_host.argtypes = [vp, dp, C.c_int64, C.c_int32]
+    L.ed_comm_unique_id.argtypes = [vp, C.c_char_p]
+    L.ed_set_comm.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     L.edgpu_vec_download_rows.argtypes = [vp, C.c_int64, C.c_int64, vp]
     L.edgpu_sector_dim.argtypes = [vp, i64p, i64p, i64p]
     L.edgpu_sector_map.argtypes = [vp, C.c_int64, C.c_int64, u64p]
@@ -449,6 +453,15 @@ class Solver:
     def check(self, rc):
         if rc != 0:
             raise EdgpuError(lib().ed_last_error(self.h).decode())
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.check(lib().ed_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def set_comm(self, uid: bytes, rank, nranks):
+        """distributed ed_solve: sectors and ground-state chains dealt over the ranks (ED_MAIN.f90:598-636 analogue)"""
+        self.check(lib().ed_set_comm(self.h, uid, rank, nranks))
 
     def set_sectors(self, pairs):
         a = np.ascontiguousarray(np.array(pairs, dtype=np.int32).reshape(-1))

@@ -23,6 +23,7 @@ int hxv_star_up_peers(edgpu_sector *s, const double *const *xp, double *const *y
 int hxv_star_up_slabs(edgpu_sector *s, const double *x, double *y, int64_t row0, int64_t nrows, int nslab,
                       const int64_t *col0, const int64_t *ldc, int accumulate);
 int csr_download(const edgpu_sector *s, int64_t *rowptr, int64_t *cols, double *vals);
+int dense_rows(edgpu_sector *s, double *d_H);
 
 static thread_local std::string g_null_err;
 
@@ -180,7 +181,9 @@ static int sector_build_impl(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int rank,
     s->nalloc = s->dim_dw * s->ld;
     // pair-tile layout + fiber kernels (hxv_fiber.cu): hxv_kernel = 3 forces them, auto takes them for large sectors;
     // a sharded sector (nranks > 1) exists only in that layout
-    const bool want_pairs = ctx->par.hxv_kernel == 3 || nranks > 1 || (ctx->par.hxv_kernel == 0 && s->dim >= (1ll << 21));
+    // reserved[1] bit 0: the caller will store H (ed_sparse_H=T -> CSR), which needs the single-tile layout
+    const bool want_pairs = ctx->par.hxv_kernel == 3 || nranks > 1 ||
+                            (ctx->par.hxv_kernel == 0 && s->dim >= (1ll << 21) && !(ctx->par.reserved[1] & 1));
     if (want_pairs && pair_layout_supported(s)) {
         if (int rc = pair_layout_build(s, rank, nranks)) { delete s; return rc; }
     } else if (ctx->par.hxv_kernel == 3 || nranks > 1) {
@@ -480,6 +483,20 @@ extern "C" int edgpu_sector_dense(edgpu_sector *s, double *hmat)
     edgpu_ctx *ctx = s->ctx;
     if (s->dim > 4096) return edgpu_fail(ctx, "edgpu_sector_dense: dim=%lld too large", (long long)s->dim);
     const int64_t n = s->dim;
+    {
+        // one launch: every thread writes the (sparse) row of its reference state into the dense matrix
+        double *d_H = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&d_H, sizeof(double) * (size_t)n * (size_t)n));
+        const int rc = dense_rows(s, d_H);
+        if (rc == 0) {
+            cudaError_t e = cudaMemcpy(hmat, d_H, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyDeviceToHost);
+            cudaFree(d_H);
+            if (e != cudaSuccess) return edgpu_fail(ctx, "edgpu_sector_dense: %s", cudaGetErrorString(e));
+            return 0;
+        }
+        cudaFree(d_H);
+        if (!ctx->ham.jhflag) return rc;          // a real error; with Jx/Jp fall through to H applied to unit vectors
+    }
     double *x, *y, *yr;
     if (int rc = sector_work(s, 0, &x)) return rc;
     if (int rc = sector_work(s, 1, &y)) return rc;

@@ -98,6 +98,35 @@ extern "C" int edgpu_comm_finalize(edgpu_ctx *ctx)
 }
 
 int comm_nranks(const edgpu_ctx *ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
+int comm_rank(const edgpu_ctx *ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+
+extern "C" int edgpu_comm_info(const edgpu_ctx *ctx, int32_t *rank, int32_t *nranks)
+{
+    if (!ctx) return 1;
+    if (rank) *rank = comm_rank(ctx);
+    if (nranks) *nranks = comm_nranks(ctx);
+    return 0;
+}
+
+/* host[0..n) <- reduction over the ranks (op 0: sum, 1: min, 2: max); staged through device memory on the context stream */
+extern "C" int edgpu_comm_allreduce_host(edgpu_ctx *ctx, double *host, int64_t n, int32_t op)
+{
+    if (!ctx || !host || n < 0) return 1;
+    if (!ctx->comm || ctx->comm->nranks == 1 || n == 0) return 0;
+    NcclApi *api = nccl_api(ctx);
+    if (!api) return 1;
+    double *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(double) * (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(d, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    int r = 0;
+    if (e == cudaSuccess) r = api->allreduce(d, d, (size_t)n, kNcclFloat64, op == 1 ? 3 /* ncclMin */ : op == 2 ? 2 /* ncclMax */ : kNcclSum, ctx->comm->comm, ctx->stream);
+    if (e == cudaSuccess && r == 0) e = cudaMemcpyAsync(host, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (r != 0) return edgpu_fail(ctx, "ncclAllReduce failed: %s", api->errstr ? api->errstr(r) : "?");
+    if (e != cudaSuccess || e2 != cudaSuccess) return edgpu_fail(ctx, "edgpu_comm_allreduce_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return 0;
+}
 
 // in-place sum of n doubles at d_buf over all ranks, ordered on the context stream
 int comm_allreduce_sum(edgpu_ctx *ctx, double *d_buf, int n)

@@ -105,7 +105,11 @@ __global__ void k_copy_scaled(double *__restrict__ dst, const double *__restrict
 
 /* sp_eigh (ED_DIAG.f90:149-166): the `neigen` lowest eigenpairs of the sector.  ncv: basis size (Nblock); tol: lanc_tolerance;
  * evals[neigen] ascending; vecs[neigen]: handles allocated here (caller frees with edgpu_vec_free); nconv: converged pairs;
- * nmatvec: H*v applications. */
+ * nmatvec: H*v applications.
+ * A Krylov space of ONE start vector holds one vector per eigenspace, so a degenerate level shows up once (ARPACK finds
+ * the copies only through rounding noise).  Multiplicities matter here -- every member of a degenerate ground level must
+ * enter the state list (ED_DIAG.f90:224-235) -- so the converged vectors are LOCKED and the run is repeated from a fresh
+ * random vector in their orthogonal complement until the lowest value found there lies above the neigen-th locked one. */
 extern "C" int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, int32_t maxrestart, double tol, uint64_t seed,
                                   double *evals, edgpu_vec **vecs, int32_t *nconv, int32_t *nmatvec)
 {
@@ -113,13 +117,16 @@ extern "C" int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, 
     edgpu_ctx *ctx = s->ctx;
     if (s->shard_nranks > 1) return edgpu_fail(ctx, "edgpu_lanczos_eigs: not available on sharded sectors");
     const int64_t n = s->nalloc;
-    int m = (int)std::min<int64_t>(std::min<int64_t>(ncv, kMaxBasis), s->dim);
-    if (m < neigen + 1 && m < s->dim) m = (int)std::min<int64_t>(s->dim, neigen + 1);
-    if (neigen > m) return edgpu_fail(ctx, "edgpu_lanczos_eigs: neigen=%d exceeds the basis size %d", neigen, m);
+    if (neigen > s->dim) return edgpu_fail(ctx, "edgpu_lanczos_eigs: neigen=%d exceeds the sector dimension", neigen);
+    const int maxlock = (int)std::min<int64_t>(s->dim, 2 * neigen + 2);            // locked vectors kept at V[0..nlock)
+    int m = (int)std::min<int64_t>(std::min<int64_t>(ncv, kMaxBasis - maxlock), s->dim);
+    if (m < neigen + 1) m = (int)std::min<int64_t>(s->dim, neigen + 1);
+    if (m + maxlock > kMaxBasis) return edgpu_fail(ctx, "edgpu_lanczos_eigs: basis of %d + %d locked vectors exceeds %d", m, maxlock, kMaxBasis);
     if (maxrestart < 1) maxrestart = 300;
+    const int nvtot = maxlock + m + 1;
     double *V = nullptr, *d_part = nullptr, *d_h = nullptr, *d_S = nullptr;
-    cudaError_t ce = cudaMalloc(&V, sizeof(double) * (size_t)n * (size_t)(m + 1));
-    if (ce != cudaSuccess) return edgpu_fail(ctx, "edgpu_lanczos_eigs: cudaMalloc of %d basis vectors (%lld doubles each) failed: %s", m + 1, (long long)n, cudaGetErrorString(ce));
+    cudaError_t ce = cudaMalloc(&V, sizeof(double) * (size_t)n * (size_t)nvtot);
+    if (ce != cudaSuccess) return edgpu_fail(ctx, "edgpu_lanczos_eigs: cudaMalloc of %d basis vectors (%lld doubles each) failed: %s", nvtot, (long long)n, cudaGetErrorString(ce));
     auto cleanup = [&]() { cudaFree(V); cudaFree(d_part); cudaFree(d_h); cudaFree(d_S); };
     if (cudaMalloc(&d_part, sizeof(double) * (size_t)kMdBlocks * kMaxBasis) != cudaSuccess || cudaMalloc(&d_h, sizeof(double) * 2 * kMaxBasis) != cudaSuccess ||
         cudaMalloc(&d_S, sizeof(double) * (size_t)kMaxBasis * kMaxBasis) != cudaSuccess) { cleanup(); return edgpu_fail(ctx, "edgpu_lanczos_eigs: scratch allocation failed"); }
@@ -127,10 +134,10 @@ extern "C" int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, 
     const int nb = (int)std::min<int64_t>(kMdBlocks, (n + kMdThreads - 1) / kMdThreads);
     auto vec = [&](int i) { return V + (size_t)i * n; };
     int rc = 0, matvecs = 0;
-    auto fail = [&](const char *msg) { cleanup(); return edgpu_fail(ctx, "edgpu_lanczos_eigs: %s", msg); };
-    std::vector<double> h(kMaxBasis), T((size_t)m * m, 0.0), S((size_t)m * m), theta(m);
-    // orthogonalise w against V_0..V_{nv-1} twice; the summed coefficients land in hout[0..nv)
+    std::vector<double> h(kMaxBasis);
+    // orthogonalise w against V_0..V_{nv-1} (locked + active) twice; the summed coefficients land in hout[0..nv)
     auto orth = [&](double *w, int nv, double *hout) -> int {
+        if (nv == 0) return 0;
         cudaMemsetAsync(d_h + kMaxBasis, 0, sizeof(double) * kMaxBasis, st);
         for (int pass = 0; pass < 2; pass++) {
             k_mdot<<<nb, kMdThreads, 0, st>>>(V, n, nv, w, n, d_part);
@@ -147,84 +154,126 @@ extern "C" int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, 
         out = std::sqrt(ctx->h_scal[0]);
         return 0;
     };
-    // start vector
-    CUDA_TRY(ctx, cudaMemsetAsync(V, 0, sizeof(double) * (size_t)n * (size_t)(m + 1), st));
-    if ((rc = vec_fill_random(s, 1, seed, vec(0)))) { cleanup(); return rc; }
-    double nrm = 0.0;
-    if (norm_of(vec(0), nrm) || nrm == 0.0) return fail("zero start vector");
-    if ((rc = vec_scale(ctx, vec(0), 1.0 / nrm, n))) { cleanup(); return rc; }
-    int k = 0, mcur = m, converged = 0;
-    double beta_m = 0.0, tnorm = 0.0;
-    bool done = false;
-    for (int restart = 0; restart <= maxrestart && !done; restart++) {
-        bool invariant = false;
-        for (int j = k; j < mcur; j++) {
-            double *w = vec(j + 1 <= m ? j + 1 : m);             // the next basis slot doubles as the work vector
-            if ((rc = hxv_dispatch(s, vec(j), w))) { cleanup(); return rc; }
-            matvecs++;
-            if (orth(w, j + 1, h.data())) return fail("orthogonalisation failed");
-            for (int i = 0; i <= j; i++) { T[i + (size_t)m * j] = h[i]; T[j + (size_t)m * i] = h[i]; }
-            double b = 0.0;
-            if (norm_of(w, b)) return fail("norm failed");
-            tnorm = std::max(tnorm, std::fabs(h[j]) + b);
-            if (b <= 1e-13 * std::max(1.0, tnorm)) {             // invariant subspace: the Ritz pairs of T[0..j] are exact
-                mcur = j + 1; beta_m = 0.0; invariant = true;
-                break;
+    CUDA_TRY(ctx, cudaMemsetAsync(V, 0, sizeof(double) * (size_t)n * (size_t)nvtot, st));
+    std::vector<double> lockval;                      // eigenvalues of the locked vectors V[0..nlock), ascending
+    int nlock = 0, converged_total = 0;
+    double tnorm = 0.0;
+    // one thick-restart run in the complement of the locked vectors: the `want` lowest Ritz pairs end up in
+    // V[nlock .. nlock+got), values in out[]
+    auto run = [&](int want, uint64_t sd, std::vector<double> &out, int &got, int &nconverged) -> int {
+        const int base = nlock;
+        auto act = [&](int i) { return vec(base + i); };
+        const int mrun = (int)std::min<int64_t>(m, s->dim - nlock);
+        want = std::min(want, mrun);
+        got = 0; nconverged = 0;
+        if (want < 1) return 0;
+        std::vector<double> T((size_t)mrun * mrun, 0.0);
+        if (int r = vec_fill_random(s, 1, sd, act(0))) return r;
+        if (orth(act(0), base, h.data())) return edgpu_fail(ctx, "edgpu_lanczos_eigs: orthogonalisation failed");
+        double nrm = 0.0;
+        if (norm_of(act(0), nrm) || nrm == 0.0) return edgpu_fail(ctx, "edgpu_lanczos_eigs: zero start vector");
+        if (int r = vec_scale(ctx, act(0), 1.0 / nrm, n)) return r;
+        int k = 0, mcur = mrun;
+        double beta_m = 0.0;
+        for (int restart = 0; restart <= maxrestart; restart++) {
+            bool invariant = false;
+            for (int j = k; j < mcur; j++) {
+                double *w = act(j + 1);                               // the next basis slot doubles as the work vector
+                if (int r = hxv_dispatch(s, act(j), w)) return r;
+                matvecs++;
+                if (orth(w, base + j + 1, h.data())) return edgpu_fail(ctx, "edgpu_lanczos_eigs: orthogonalisation failed");
+                for (int i = 0; i <= j; i++) { T[i + (size_t)mrun * j] = h[base + i]; T[j + (size_t)mrun * i] = h[base + i]; }
+                double b = 0.0;
+                if (norm_of(w, b)) return edgpu_fail(ctx, "edgpu_lanczos_eigs: norm failed");
+                tnorm = std::max(tnorm, std::fabs(h[base + j]) + b);
+                if (b <= 1e-12 * std::max(1.0, tnorm)) {              // invariant subspace: the Ritz pairs of T[0..j] are exact
+                    mcur = j + 1; beta_m = 0.0; invariant = true;
+                    break;
+                }
+                if (int r = vec_scale(ctx, w, 1.0 / b, n)) return r;
+                if (j + 1 < mcur) { T[(j + 1) + (size_t)mrun * j] = b; T[j + (size_t)mrun * (j + 1)] = b; }
+                else beta_m = b;                                       // w = residual direction
             }
-            if ((rc = vec_scale(ctx, w, 1.0 / b, n))) { cleanup(); return rc; }
-            if (j + 1 < mcur) { T[(j + 1) + (size_t)m * j] = b; T[j + (size_t)m * (j + 1)] = b; }
-            else beta_m = b;                                      // w = V_m: residual direction
+            std::vector<double> A((size_t)mcur * mcur), wv(mcur);
+            for (int i = 0; i < mcur; i++)
+                for (int j = 0; j < mcur; j++) A[i + (size_t)mcur * j] = T[i + (size_t)mrun * j];
+            if (ed_host_eigh(mcur, A.data(), wv.data())) return edgpu_fail(ctx, "edgpu_lanczos_eigs: dense eigensolver failed");
+            const int w2 = std::min(want, mcur);
+            int conv = 0;
+            for (int i = 0; i < w2; i++) {
+                const double res = std::fabs(beta_m * A[(mcur - 1) + (size_t)mcur * i]);
+                const double thr = std::max(tol, 2.3e-16) * std::max(3.7e-11, std::fabs(wv[i]));      // eps^(2/3), ARPACK dsconv
+                if (res <= thr) conv++;
+            }
+            const bool last = invariant || conv == w2 || restart == maxrestart;
+            const int K = last ? w2 : std::min(mcur - 1, want + std::max(1, (mcur - want) / 2));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_S, A.data(), sizeof(double) * (size_t)mcur * mcur, cudaMemcpyHostToDevice, st));
+            {
+                const size_t smem = sizeof(double) * (size_t)mcur * kCombT;
+                static size_t cur_smem = 0;
+                if (smem > cur_smem) { CUDA_TRY(ctx, cudaFuncSetAttribute((const void *)k_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur_smem = smem; }
+                const int gb = (int)std::min<int64_t>(ctx->sm_count * 2, (n + kCombT - 1) / kCombT);
+                k_combine<<<gb, kCombT, smem, st>>>(act(0), n, mcur, K, d_S, n);
+                CUDA_TRY(ctx, cudaGetLastError());
+            }
+            if (last) {
+                out.assign(wv.begin(), wv.begin() + w2);
+                got = w2; nconverged = conv;
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                return 0;
+            }
+            k_copy_scaled<<<nb, kMdThreads, 0, st>>>(act(K), act(mcur), 1.0, n);
+            std::fill(T.begin(), T.end(), 0.0);
+            for (int i = 0; i < K; i++) {
+                T[i + (size_t)mrun * i] = wv[i];
+                const double a = beta_m * A[(mcur - 1) + (size_t)mcur * i];
+                T[K + (size_t)mrun * i] = a; T[i + (size_t)mrun * K] = a;
+            }
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            k = K;
         }
-        // Ritz pairs of the mcur x mcur projection
-        std::vector<double> A((size_t)mcur * mcur), wv(mcur);
-        for (int i = 0; i < mcur; i++)
-            for (int j = 0; j < mcur; j++) A[i + (size_t)mcur * j] = T[i + (size_t)m * j];
-        if (ed_host_eigh(mcur, A.data(), wv.data())) return fail("dense eigensolver failed");
-        const int want = std::min(neigen, mcur);
-        converged = 0;
-        for (int i = 0; i < want; i++) {
-            const double res = std::fabs(beta_m * A[(mcur - 1) + (size_t)mcur * i]);
-            const double thr = std::max(tol, 2.3e-16) * std::max(3.7e-11, std::fabs(wv[i]));      // eps^(2/3)
-            if (res <= thr) converged++;
+        return 0;
+    };
+    // sweep 1: the neigen lowest (distinct) levels; further sweeps: missed copies of degenerate levels
+    for (int sweep = 0; sweep < 2 * neigen + 2; sweep++) {
+        std::vector<double> out;
+        int got = 0, nconvd = 0;
+        const int want = sweep == 0 ? neigen : std::min(neigen, 2);
+        if ((rc = run(want, seed + 7919ull * (uint64_t)sweep, out, got, nconvd))) { cleanup(); return rc; }
+        if (got == 0) break;                                        // the complement is empty
+        if (sweep == 0) {
+            lockval = out; nlock = got; converged_total = nconvd;
+            if (nlock >= s->dim) break;
+            continue;
         }
-        const bool last = invariant || converged == want || restart == maxrestart;
-        const int K = last ? want : std::min(mcur - 1, neigen + std::max(1, (mcur - neigen) / 2));
-        // V[:, 0..K) <- V S
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_S, A.data(), sizeof(double) * (size_t)mcur * mcur, cudaMemcpyHostToDevice, st));
-        {
-            const size_t smem = sizeof(double) * (size_t)mcur * kCombT;
-            static size_t cur_smem = 0;
-            if (smem > cur_smem) { CUDA_TRY(ctx, cudaFuncSetAttribute((const void *)k_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur_smem = smem; }
-            const int gb = (int)std::min<int64_t>(ctx->sm_count * 2, (n + kCombT - 1) / kCombT);
-            k_combine<<<gb, kCombT, smem, st>>>(V, n, mcur, K, d_S, n);
-            CUDA_TRY(ctx, cudaGetLastError());
-        }
-        if (last) {
-            for (int i = 0; i < want; i++) evals[i] = wv[i];
-            done = true;
-            break;
-        }
-        // residual direction becomes basis vector K; T = diag(theta) + arrow
-        k_copy_scaled<<<nb, kMdThreads, 0, st>>>(vec(K), vec(mcur), 1.0, n);
-        std::fill(T.begin(), T.end(), 0.0);
-        for (int i = 0; i < K; i++) {
-            T[i + (size_t)m * i] = wv[i];
-            const double a = beta_m * A[(mcur - 1) + (size_t)mcur * i];
-            T[K + (size_t)m * i] = a; T[i + (size_t)m * K] = a;
-        }
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        k = K;
+        // keep the new vectors whose value belongs to the neigen lowest of (locked + new)
+        std::vector<double> sorted(lockval);
+        std::sort(sorted.begin(), sorted.end());
+        const double cut = (int)sorted.size() >= neigen ? sorted[neigen - 1] : 1e300;
+        const double slack = 1e-9 * std::max(1.0, std::fabs(cut));
+        int take = 0;
+        while (take < got && (out[take] <= cut + slack) && nlock + take < maxlock) take++;
+        if (take == 0) break;                                       // nothing below the neigen-th level was missed
+        for (int i = 0; i < take; i++) lockval.push_back(out[i]);
+        nlock += take;
+        converged_total += std::min(take, nconvd);
+        // the locked set stays orthonormal (new vectors were built in the complement); order is fixed at the end
     }
-    const int want = std::min(neigen, mcur);
+    // lowest neigen of the locked pairs, ascending
+    std::vector<int> idx(lockval.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return lockval[a] < lockval[b]; });
+    const int have = (int)std::min<size_t>(idx.size(), (size_t)neigen);
     for (int i = 0; i < neigen; i++) vecs[i] = nullptr;
-    for (int i = 0; i < want; i++) {
+    for (int i = 0; i < have; i++) {
+        evals[i] = lockval[idx[i]];
         if ((rc = edgpu_vec_alloc(s, &vecs[i]))) { cleanup(); return rc; }
-        CUDA_TRY(ctx, cudaMemcpyAsync(vecs[i]->d, vec(i), sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(vecs[i]->d, vec(idx[i]), sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     cleanup();
-    if (nconv) *nconv = converged;
+    if (nconv) *nconv = std::min(converged_total, have);
     if (nmatvec) *nmatvec = matvecs;
-    if (want < neigen) return edgpu_fail(ctx, "edgpu_lanczos_eigs: the Krylov space closed after %d vectors (< neigen=%d)", want, neigen);
+    if (have < neigen) return edgpu_fail(ctx, "edgpu_lanczos_eigs: only %d of %d eigenpairs found", have, neigen);
     return 0;
 }

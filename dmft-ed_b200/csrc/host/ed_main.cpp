@@ -65,6 +65,7 @@ struct ed_solver {
     std::vector<double> densChi_tau, densChi_tot_tau;            // (ED_SETUP.f90:346-354)
     std::vector<cplx> densChi_iv, densChi_w, densChi_tot_iv, densChi_tot_w;
     double timings[4] = {0, 0, 0, 0};
+    int rank = 0, nranks = 1;                 // ed_set_comm: sectors / states dealt over the ranks
 };
 
 static int fail(ed_solver *s, const char *fmt, ...)
@@ -157,6 +158,7 @@ extern "C" int ed_init_solver(const ed_input *in, int device, void *stream, doub
     memset(&p, 0, sizeof(p));
     p.norb = in->Norb; p.nbath = in->Nbath; p.nspin = in->Nspin; p.hfmode = in->hfmode;
     p.layout = in->gpu_layout; p.hxv_kernel = in->gpu_hxv_kernel;
+    p.reserved[1] = in->ed_sparse_H ? 1 : 0;          // stored H (CSR) lives in the single-tile layout
     if (edgpu_init(&p, device, stream, &s->ctx) != 0) {
         fprintf(stderr, "ed_init_solver: %s\n", edgpu_last_error(nullptr));
         delete s;
@@ -180,6 +182,26 @@ static void free_states(ed_solver *s)
     for (auto *q : secs) edgpu_sector_free(q);
     s->states.clear();
 }
+
+extern "C" int ed_comm_unique_id(ed_solver *s, unsigned char id[128])
+{
+    if (!s) return 1;
+    GPU_TRY(s, edgpu_comm_unique_id(s->ctx, id));
+    return 0;
+}
+
+extern "C" int ed_set_comm(ed_solver *s, const unsigned char id[128], int32_t rank, int32_t nranks)
+{
+    if (!s) return 1;
+    GPU_TRY(s, edgpu_comm_init(s->ctx, id, rank, nranks));
+    s->rank = rank; s->nranks = nranks;
+    return 0;
+}
+
+// sum / min of host arrays over the ranks of the distributed solve (no-op on one rank)
+static int allsum(ed_solver *s, double *v, size_t n) { return s->nranks > 1 ? edgpu_comm_allreduce_host(s->ctx, v, (int64_t)n, 0) : 0; }
+static int allsum(ed_solver *s, std::vector<double> &v) { return allsum(s, v.data(), v.size()); }
+static int allsum(ed_solver *s, std::vector<cplx> &v) { return allsum(s, reinterpret_cast<double *>(v.data()), 2 * v.size()); }
 
 extern "C" int ed_finalize_solver(ed_solver *s)
 {
@@ -302,9 +324,12 @@ static int ed_diag(ed_solver *s)
     s->sector_e.clear();
     s->sector_nlanc.clear();
     double oldzero = 1000.0;
+    int isec = -1;
     for (int nup = 0; nup <= Ns; nup++)
         for (int ndw = 0; ndw <= Ns; ndw++) {                                  // isector order, ED_SETUP.f90:382-393
             if (!s->mask.empty() && std::find(s->mask.begin(), s->mask.end(), std::make_pair(nup, ndw)) == s->mask.end()) continue;
+            isec++;
+            if (s->nranks > 1 && isec % s->nranks != s->rank) continue;        // distributed scan: this sector belongs to another rank
             edgpu_sector *sec = nullptr;
             GPU_TRY(s, edgpu_sector_build(s->ctx, nup, ndw, &sec));
             int64_t dim = 0;
@@ -396,6 +421,35 @@ static int ed_diag(ed_solver *s)
             }
             if (!used) edgpu_sector_free(sec);
         }
+    if (s->nranks > 1) {
+        // the running minimum of :224-235 was local: agree on the global ground energy, keep the local states within
+        // gs_threshold of it, and share the sector energies
+        double emin = 1e300;
+        for (auto &st : s->states) emin = std::min(emin, st.e);
+        GPU_TRY(s, edgpu_comm_allreduce_host(s->ctx, &emin, 1, 1));
+        std::vector<EdState> keep;
+        std::vector<edgpu_sector *> used, drop;
+        for (auto &st : s->states) {
+            if (std::fabs(st.e - emin) <= in.gs_threshold) { keep.push_back(st); used.push_back(st.sec); }
+            else { if (st.vec) edgpu_vec_free(st.vec); drop.push_back(st.sec); }
+        }
+        for (auto *q : drop)
+            if (std::find(used.begin(), used.end(), q) == used.end()) { edgpu_sector_free(q); used.push_back(q); }
+        s->states.swap(keep);
+        double cnt = (double)s->states.size();
+        GPU_TRY(s, edgpu_comm_allreduce_host(s->ctx, &cnt, 1, 0));
+        const int nsec = (Ns + 1) * (Ns + 1);
+        std::vector<double> tab(2 * (size_t)nsec, 0.0);
+        for (auto &kv : s->sector_e) { tab[kv.first.first * (Ns + 1) + kv.first.second] = kv.second; tab[nsec + kv.first.first * (Ns + 1) + kv.first.second] = 1.0; }
+        GPU_TRY(s, allsum(s, tab));
+        for (int a = 0; a <= Ns; a++)
+            for (int b = 0; b <= Ns; b++)
+                if (tab[nsec + a * (Ns + 1) + b] > 0.5) s->sector_e[{a, b}] = tab[a * (Ns + 1) + b];
+        if (cnt < 0.5) return fail(s, "ed_diag: no state found");
+        s->egs = emin;
+        s->zeta = cnt;
+        return 0;
+    }
     if (s->states.empty()) return fail(s, "ed_diag: no state found");
     // ed_post_diag (ED_DIAG.f90:403-416), T=0
     s->egs = s->states[0].e;
@@ -482,6 +536,9 @@ static int build_gf(ed_solver *s)
                 }
             }
         }
+    // distributed solve: every rank summed over ITS states, G is the sum over all of them
+    GPU_TRY(s, allsum(s, s->Gmats));
+    GPU_TRY(s, allsum(s, s->Greal));
     return 0;
 }
 
@@ -552,6 +609,9 @@ static int build_chi_spin(ed_solver *s)
             if (nrm > 0.0) add_to_lanczos_spinchi(s, tot ? nrm * nrm : nrm, st.e, alfa, beta, ic);
         }
     }
+    GPU_TRY(s, allsum(s, s->spinChi_tau));
+    GPU_TRY(s, allsum(s, s->spinChi_w));
+    GPU_TRY(s, allsum(s, s->spinChi_iv));
     for (auto &v : s->spinChi_tau) v /= s->zeta;                                     // :36-38
     for (auto &v : s->spinChi_w) v /= s->zeta;
     for (auto &v : s->spinChi_iv) v /= s->zeta;
@@ -626,6 +686,8 @@ static int build_chi_dens(ed_solver *s)
             }
         }
     }
+    GPU_TRY(s, allsum(s, s->densChi_tau)); GPU_TRY(s, allsum(s, s->densChi_w)); GPU_TRY(s, allsum(s, s->densChi_iv));
+    GPU_TRY(s, allsum(s, s->densChi_tot_tau)); GPU_TRY(s, allsum(s, s->densChi_tot_w)); GPU_TRY(s, allsum(s, s->densChi_tot_iv));
     for (auto &v : s->densChi_tau) v /= s->zeta;                                     // :62-64 (the total channel is not divided again)
     for (auto &v : s->densChi_w) v /= s->zeta;
     for (auto &v : s->densChi_iv) v /= s->zeta;
@@ -686,6 +748,11 @@ static int observables(ed_solver *s)
     for (auto &st : s->states)
         GPU_TRY(s, edgpu_observables(st.sec, st.vec, 1.0 / s->zeta, s->dens.data(), s->dens_up.data(), s->dens_dw.data(),
                                      s->docc.data(), s->magz.data(), s->sz2.data(), s->n2.data(), &s->s2tot));
+    if (s->nranks > 1) {
+        GPU_TRY(s, allsum(s, s->dens)); GPU_TRY(s, allsum(s, s->dens_up)); GPU_TRY(s, allsum(s, s->dens_dw));
+        GPU_TRY(s, allsum(s, s->docc)); GPU_TRY(s, allsum(s, s->magz)); GPU_TRY(s, allsum(s, s->sz2)); GPU_TRY(s, allsum(s, s->n2));
+        GPU_TRY(s, allsum(s, &s->s2tot, 1));
+    }
     return 0;
 }
 

@@ -103,7 +103,9 @@ __device__ __forceinline__ double out(const double (&x)[N], const double *__rest
 // tables
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int kHS = 12;                      // gather slots per fiber (stars 1.. of the same spin)
-static constexpr int kSlot = 115712;                // bytes per pipeline slot (2 slots = 226 KB of dynamic shared memory)
+static constexpr int kSlot = 110592;                // bytes per pipeline slot (2 slots = 216 KB of dynamic shared memory)
+static constexpr int kStab = 10240;                 // shared-memory copy of the outer table of the current block (SOuter entries)
+static constexpr int kStabHS = 7;                   // slots per entry of that copy (blocks with more slots read the global table)
 static constexpr int kFibMinBlock = 256;            // blocks smaller than this use the thread-per-element pair kernels
 
 struct FibBlockDev {
@@ -115,7 +117,7 @@ struct FibBlockDev {
     int tab;                    // first entry of the block in the outer table
     int fiber;                  // fiber kernels apply (else the generic pair kernels)
     int BR, nbox;               // down pass: bands per tensor box, boxes per strip
-    int pad;
+    int hsmax;                  // largest slot count of a fiber of the block
 };
 
 struct __align__(16) OuterEnt {  // one value of the outer index o (stars 1..) of a block; 128 bytes
@@ -129,6 +131,15 @@ struct __align__(16) OuterEnt {  // one value of the outer index o (stars 1..) o
     int pad1[2];
 };
 static_assert(sizeof(OuterEnt) == 128, "OuterEnt must be 128 bytes");
+
+struct __align__(16) SOuter {     // shared-memory form of OuterEnt with the amplitudes resolved; 112 bytes
+    double eo;
+    int impbits, nslot, neg, pad;
+    int delta[kStabHS];
+    int pad2;
+    double amp[kStabHS];
+};
+static_assert(sizeof(SOuter) == 112, "SOuter must be 112 bytes");
 
 struct FibConst {               // by-value kernel argument: compile-time indexed => constant-bank operands
     double e0[256];             // star-0 energies, [ccoff(NL, m) + i]
@@ -292,6 +303,7 @@ static int build_fib_spin(edgpu_ctx *ctx, SpinBasis *b)
         const int64_t band_bytes = (int64_t)fb.C4 * 128, strip_bytes = (int64_t)fb.nbox * fb.BR * 128;
         fb.fiber = (nl >= 3 && nl <= 8 && norb >= 2 && fb.m0 >= 1 && fb.m0 <= nl - 1 && band_bytes <= 2 * kSlot && strip_bytes <= 2 * kSlot &&
                     hsmax <= (nl >= 7 ? 7 : kHS)) ? 1 : 0;
+        fb.hsmax = hsmax;
         F->blocks.push_back(fb);
     }
     cudaStream_t st = ctx->stream;
@@ -419,7 +431,8 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
         } else { g2.push_back(p); P->g2_elems += (int64_t)BD.size * BU.size; }
     }
     // big tiles first (a CTA's sequence is then descending: two-slot tiles precede one-slot tiles, see the pipeline)
-    auto bysize = [](const FibTile &a, const FibTile &b) { return a.bytes > b.bytes; };
+    // (equal sizes: by block, so that a CTA meets long runs of the same block)
+    auto bysize = [](const FibTile &a, const FibTile &b) { return a.bytes != b.bytes ? a.bytes > b.bytes : a.blk < b.blk; };
     std::stable_sort(t1.begin(), t1.end(), bysize);
     std::stable_sort(t2.begin(), t2.end(), bysize);
     P->n1 = (int)t1.size(); P->n2 = (int)t2.size(); P->ng1 = (int)g1.size(); P->ng2 = (int)g2.size();
@@ -463,6 +476,30 @@ __device__ __forceinline__ void fmbar_wait(uint32_t bar, uint32_t parity)
         "FDONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// one lane polls, the warp follows (32 spinning lanes per warp only burn issue slots of the warps that still compute)
+__device__ __forceinline__ void fmbar_wait_warp(uint32_t bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) fmbar_wait(bar, parity);
+    __syncwarp();
+}
+// the producer thread shares a scheduler with consumer warps: poll with a pause instead of burning its issue slots
+__device__ __forceinline__ void fmbar_wait_backoff(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void fbulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ftma_prefetch_3d(const CUtensorMap *tm, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -476,6 +513,12 @@ __device__ __forceinline__ double2 flds128(uint32_t addr)
 {
     double2 v;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int flds32(uint32_t addr)
+{
+    int v;
+    asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ double flds64(uint32_t addr)
@@ -506,17 +549,24 @@ struct FibArgs {
     int ntiles;
     uint32_t impmask;
     int slot;                           // bytes per pipeline slot (kSlot; smaller in the two-slot test mode)
+    int dbg;                            // measurement hooks: bit 0 = consumers skip the fibers (load pipeline only)
     const double *x;
     double *y;
     const double *e_dw;                 // pass 1: per-row diagonal energy and configuration word of the down spin
     const uint32_t *cfg_dw;
     const double *xtab;
     const CUtensorMap *tmaps;           // pass 2: one 3-D tensor map per pair over x
+    const CUtensorMap *tmaps_y;         // pass 2: the same over y (L2 prefetch of the read-modify-write operand)
     double *dot_out;                    // pass 2: per-CTA partial <x, y> (nullptr: not wanted)
 };
 
-// 12 warps (11 consumers + producer) = 3 per scheduler -> 168 registers per thread; 16 warps -> 128 for the short fibers
-template <int NL> struct FibCfg { static constexpr int NC = (NL >= 7) ? 352 : 480; static constexpr int NT = NC + 32; };
+// Long fibers (7-8 levels per star): 8 warps (7 consumers + producer) = 2 per scheduler -> 255 registers per thread and NO
+// spills (local memory has no L1 to live in next to 226 KB of shared memory: every spill reload is an L2 round trip, which
+// made the 12-warp / 168-register build latency-bound); short fibers: 16 warps, 128 registers.
+#ifndef EDGPU_FIB_NC_BIG
+#define EDGPU_FIB_NC_BIG 224
+#endif
+template <int NL> struct FibCfg { static constexpr int NC = (NL >= 7) ? EDGPU_FIB_NC_BIG : 480; static constexpr int NT = NC + 32; };
 
 // ---- pass 1: one fiber (row r4 of the band, outer index o) of the up spin ----
 // Two phases so that only HALF of the fiber lives in registers at a time (a whole 70-element fiber plus the slot
@@ -524,7 +574,7 @@ template <int NL> struct FibCfg { static constexpr int NC = (NL >= 7) ? 352 : 48
 // imp=0 outputs, phase 1 the other way round; the own element (diagonal term) is re-read from the image with the gathers.
 template <int NL, int M0, int HS, int PART>
 __device__ __forceinline__ void fiber_up_phase(const FibArgs &A, uint32_t own /* img + oE */, uint32_t ownO, const uint32_t (&sE)[HS], const uint32_t (&sO)[HS],
-                                               const double (&amp)[HS], double dg, double sig, double *yE, double *yO, double &carry)
+                                               const double (&amp)[HS], double dg, double sig, double *yE, double *yO)
 {
     constexpr int NB = NL - 1, D0 = fib::cbinom(NL, M0), A0 = fib::cbinom(NB, M0), NP = (D0 + 1) / 2, COFF = fib::ccoff(NL, M0);
     constexpr int IN_LO = PART == 0 ? (A0 & ~1) : 0, IN_HI = PART == 0 ? 2 * NP : ((A0 + 1) & ~1), NIN = IN_HI - IN_LO;
@@ -558,18 +608,34 @@ __device__ __forceinline__ void fiber_up_phase(const FibArgs &A, uint32_t own /*
                 const double in1 = fib::out<NB, M0, K + 1, IN_LO>(in, A.cst.v0);
                 r1 = fma(dg + A.cst.e0[COFF + K + 1], xo.y, fma(sig, in1, PART == 0 ? g1 : -g1));
             }
-            // a pair that straddles the imp=0 / imp=1 boundary (A0 odd) is stored by phase 1, element 0 carried over
-            if constexpr (PART == 0 && do0 && !do1 && K + 1 < D0) carry = r0;
-            else {
-                if constexpr (PART == 1 && !do0) r0 = carry;
-                fstg128(((K & 3) == 0 ? yE : yO) + (K >> 2) * 16, r0, r1);
-            }
+            // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
+            double *yp = ((K & 3) == 0 ? yE : yO) + (K >> 2) * 16;
+            if constexpr (do0 && do1) fstg128(yp, r0, r1);
+            else if constexpr (do0 && K + 1 >= D0) fstg128(yp, r0, 0.0);        // last pair of an odd fiber: the pad stays zero
+            else if constexpr (do0) yp[0] = r0;
+            else if constexpr (do1) yp[1] = r1;
         });
     }
 }
 
-template <int NL, int M0, int HS>
-__device__ __forceinline__ void fiber_up(const FibArgs &A, const OuterEnt *__restrict__ ent, int nslot, bool active, uint32_t img, int r4, int o,
+// Slot data of one fiber: from the shared-memory copy of the block's outer table (stab != 0: address of the SOuter entry)
+// or from the global table (blocks whose table does not fit the copy).
+struct FiberMeta {
+    uint32_t stab;                    // shared address of the SOuter entry, 0 = use `ent`
+    const OuterEnt *ent;
+    __device__ __forceinline__ int nslot() const { return stab ? flds32(stab + 12u) : ent->nslot; }
+    __device__ __forceinline__ int impbits() const { return stab ? flds32(stab + 8u) : ent->impbits; }
+    __device__ __forceinline__ int neg() const { return stab ? flds32(stab + 16u) : ent->neg; }
+    __device__ __forceinline__ double eo() const { return stab ? flds64(stab) : ent->eo; }
+    __device__ __forceinline__ int delta(int s2) const { return stab ? flds32(stab + 24u + 4u * (uint32_t)s2) : ent->delta[s2]; }
+    __device__ __forceinline__ double amp(int s2, const double *__restrict__ amps) const
+    {
+        return stab ? flds64(stab + 56u + 8u * (uint32_t)s2) : __ldg(amps + ent->code[s2]);
+    }
+};
+
+template <int NL, int M0, int HS, int PART>
+__device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, int nslot, bool active, uint32_t img, int r4, int o,
                                          int d0p, double dgbase, uint32_t impd, double *yband)
 {
     if (!active) return;
@@ -583,22 +649,44 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const OuterEnt *__res
 #pragma unroll
     for (int s = 0; s < HS; s++) {
         const bool on = s < nslot;
-        const int cs = (o + (on ? ent->delta[s] : 0)) * d0p;
+        const int cs = (o + (on ? F.delta(s) : 0)) * d0p;
         const uint32_t Ts = (uint32_t)(cs >> 2) * 128u + (uint32_t)r4 * 32u;
         const bool qs = (cs & 3) != 0;
         sE[s] = img + (qs ? Ts + 16u : Ts);
         sO[s] = img + (qs ? Ts + 128u : Ts + 16u);
-        amp[s] = on ? __ldg(A.amps + ent->code[s]) : 0.0;
+        amp[s] = on ? F.amp(s, A.amps) : 0.0;
     }
-    const int ib = ent->impbits;
+    const int ib = F.impbits() | PART;                    // PART 1: the outputs have the impurity of star 0 occupied
     const int nimp = __popc(ib);
-    const double dg0 = dgbase + ent->eo + __ldg(A.xtab + impd * 32u + (uint32_t)ib) + A.cst.pair_e * (double)(nimp * (nimp - 1) / 2);
-    const double dg1 = dgbase + ent->eo + __ldg(A.xtab + impd * 32u + (uint32_t)(ib | 1)) + A.cst.pair_e * (double)((nimp + 1) * nimp / 2);
-    const double sig = ent->neg ? -1.0 : 1.0;
+    const double dg = dgbase + F.eo() + __ldg(A.xtab + impd * 32u + (uint32_t)ib) + A.cst.pair_e * (double)(nimp * (nimp - 1) / 2);
+    const double sig = F.neg() ? -1.0 : 1.0;
     double *yE = yband + (oE >> 3), *yO = yband + (oO >> 3);
-    double carry = 0.0;
-    fiber_up_phase<NL, M0, HS, 0>(A, img + oE, img + oO, sE, sO, amp, dg0, sig, yE, yO, carry);
-    fiber_up_phase<NL, M0, HS, 1>(A, img + oE, img + oO, sE, sO, amp, dg1, sig, yE, yO, carry);
+    fiber_up_phase<NL, M0, HS, PART>(A, img + oE, img + oO, sE, sO, amp, dg, sig, yE, yO);
+}
+
+// consumers: copy the outer table of block `B` into shared memory (amplitudes resolved); named barrier 1 = consumers only
+template <int NC>
+__device__ __forceinline__ bool load_stab(const FibArgs &A, const FibBlockDev &B, uint32_t stab0, int tid)
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");                  // nobody still reads the previous table
+    const bool fits = B.hsmax <= kStabHS && (size_t)B.nouter * sizeof(SOuter) <= (size_t)kStab;
+    if (fits) {
+        for (int o = tid; o < B.nouter; o += NC) {
+            const OuterEnt *e = A.outer + B.tab + o;
+            const uint32_t d = stab0 + (uint32_t)o * (uint32_t)sizeof(SOuter);
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(d), "d"(e->eo) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 8u), "r"(e->impbits), "r"(e->nslot) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 16u), "r"(e->neg), "r"(0) : "memory");
+#pragma unroll
+            for (int q = 0; q < kStabHS; q++) {
+                const bool on = q < e->nslot;
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + 24u + 4u * q), "r"(on ? e->delta[q] : 0) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(d + 56u + 8u * q), "d"(on ? __ldg(A.amps + e->code[q]) : 0.0) : "memory");
+            }
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    return fits;
 }
 
 template <int NL>
@@ -609,6 +697,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     __shared__ uint64_t s_bar[4];
     const int tid = threadIdx.x;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t stab0 = slot0 + 2u * kSlot;
     const uint32_t bfull = (uint32_t)__cvta_generic_to_shared(s_bar), bempty = bfull + 16u;
     if (tid == 0) {
         fmbar_init(bfull, 1); fmbar_init(bfull + 8, 1);
@@ -619,13 +708,15 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid >= NC) {
         if (tid == NC) {
-            int use[2] = {0, 0}, pos = 0;
+            // ne[s]: tiles that have occupied the memory of slot s so far (= phases its empty barrier must have completed);
+            // a two-slot tile occupies both
+            int ne[2] = {0, 0}, pos = 0;
             for (int i = 0; i < myn; i++) {
                 const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
                 const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
-                if (use[s] > 0) fmbar_wait(bempty + 8 * s, (uint32_t)(use[s] - 1) & 1u);
-                if (two && use[1] > 0) fmbar_wait(bempty + 8, (uint32_t)(use[1] - 1) & 1u);
+                if (ne[s] > 0) fmbar_wait_backoff(bempty + 8 * s, (uint32_t)(ne[s] - 1) & 1u);
+                if (two && ne[1] > 0) fmbar_wait_backoff(bempty + 8, (uint32_t)(ne[1] - 1) & 1u);
                 fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
                 const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
                 const char *src = reinterpret_cast<const char *>(A.x + t.off);
@@ -633,36 +724,75 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                     const int n = t.bytes - ofs < 32768 ? t.bytes - ofs : 32768;
                     fbulk_g2s(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s);
                 }
-                use[s]++;
-                if (!two) pos ^= 1;
+                ne[s]++;
+                if (two) ne[1]++;
+                else pos ^= 1;
+                // the tile after next cannot be loaded before a buffer frees: pull it into L2 meanwhile
+                if (i + 1 < myn) {
+                    const FibTile tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
+                    const bool need = two || tn.bytes > A.slot || i + 2 < myn;
+                    const FibTile tp = (two || tn.bytes > A.slot || i + 2 >= myn) ? tn : A.tiles[blockIdx.x + (size_t)(i + 2) * gridDim.x];
+                    if (need) {
+                        const char *ps = reinterpret_cast<const char *>(A.x + tp.off);
+                        for (int ofs = 0; ofs < tp.bytes; ofs += 32768)
+                            fbulk_prefetch_l2(ps + ofs, (uint32_t)(tp.bytes - ofs < 32768 ? tp.bytes - ofs : 32768));
+                    }
+                }
             }
         }
         return;
     }
-    int cuse[2] = {0, 0}, pos = 0;
+    int nfill[2] = {0, 0}, pos = 0, cur_blk = -1;
+    bool stab = false;
     for (int i = 0; i < myn; i++) {
         const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
         const bool two = t.bytes > A.slot;
         const int s = two ? 0 : pos;
-        fmbar_wait(bfull + 8 * s, (uint32_t)cuse[s] & 1u);
         const FibBlockDev BU = A.blk_f[t.blk];
         const PairDev pd = A.pairs[t.pair];
         const FibBlockDev BD = A.blk_o[pd.bi];
-        const int noE = (BU.nouter + 1) & ~1, nf = 4 * noE, nfib = t.b * nf;
+        if (t.blk != cur_blk) { stab = load_stab<NC>(A, BU, stab0, tid); cur_blk = t.blk; }
+        // work units of a tile: [band g][phase][fiber], a warp takes 32 fibers of ONE phase (lanes = 4 rows x 8 outer indices,
+        // a quarter-warp = 4 rows x 2 neighbouring outer indices: conflict-free LDS.128)
+        const int noE = (BU.nouter + 1) & ~1, nwf = (4 * noE + 31) >> 5, nwu = 2 * nwf * t.b;
         const uint32_t band_bytes = (uint32_t)BU.C4 * 128u;
-        for (int f0 = 0; f0 < nfib; f0 += NC) {
-            const int f = f0 + tid;
-            const int g = f / nf, fb = f - g * nf;
-            const int r4 = fb & 3, o = 2 * (fb >> 3) + ((fb >> 2) & 1);
+        const int warp = tid >> 5, lane = tid & 31;
+        auto decode = [&](int wu, int &g, int &part, int &r4, int &o) {
+            g = wu / (2 * nwf);
+            const int rem = wu - g * 2 * nwf;
+            part = rem / nwf;
+            const int fb = (rem - part * nwf) * 32 + lane;
+            r4 = fb & 3; o = 2 * (fb >> 3) + ((fb >> 2) & 1);
+        };
+        // per-row terms of the first unit, issued before the wait for the image
+        double dg_first = 0.0;
+        uint32_t impd_first = 0;
+        if (warp < nwu) {
+            int g, part, r4, o;
+            decode(warp, g, part, r4, o);
             const int rp = (t.a + g) * 4 + r4;
             const int od = rp / BD.d0r, kd = rp - od * BD.d0r;
-            const bool active = f < nfib && o < BU.nouter && od < BD.nouter && kd < BD.D0;
-            const OuterEnt *ent = A.outer + BU.tab + (active ? o : 0);
-            const int nslot = active ? ent->nslot : 0;
+            if (od < BD.nouter && kd < BD.D0) {
+                const int id = BD.off + od * BD.D0 + kd;
+                dg_first = __ldg(A.e_dw + id);
+                impd_first = __ldg(A.cfg_dw + id) & A.impmask;
+            }
+        }
+        fmbar_wait_warp(bfull + 8 * s, (uint32_t)nfill[s] & 1u);
+        for (int wu = warp; wu < ((A.dbg & 1) ? 0 : nwu); wu += NC / 32) {
+            int g, part, r4, o;
+            decode(wu, g, part, r4, o);
+            const int rp = (t.a + g) * 4 + r4;
+            const int od = rp / BD.d0r, kd = rp - od * BD.d0r;
+            const bool active = o < BU.nouter && od < BD.nouter && kd < BD.D0;
+            FiberMeta F;
+            F.stab = stab ? stab0 + (uint32_t)(active ? o : 0) * (uint32_t)sizeof(SOuter) : 0u;
+            F.ent = A.outer + BU.tab + (active ? o : 0);
+            const int nslot = active ? F.nslot() : 0;
             const int wmax = __reduce_max_sync(0xffffffffu, nslot);
-            double dgbase = 0.0;
-            uint32_t impd = 0;
-            if (active) {
+            double dgbase = dg_first;
+            uint32_t impd = impd_first;
+            if (wu != warp && active) {
                 const int id = BD.off + od * BD.D0 + kd;
                 dgbase = __ldg(A.e_dw + id);
                 impd = __ldg(A.cfg_dw + id) & A.impmask;
@@ -672,23 +802,28 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             fib::static_for<NL - 1>([&](auto mm) {
                 constexpr int M0 = decltype(mm)::value + 1;
                 if (BU.m0 == M0) {
-                    if (wmax <= 4) fiber_up<NL, M0, 4>(A, ent, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
-                    else if (NL >= 7 || wmax <= 7) fiber_up<NL, M0, 7>(A, ent, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
-                    else if constexpr (NL < 7) fiber_up<NL, M0, kHS>(A, ent, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                    if (part == 0) {
+                        if (wmax <= 4) fiber_up<NL, M0, 4, 0>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                        else if (NL >= 7 || wmax <= 7) fiber_up<NL, M0, 7, 0>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                        else if constexpr (NL < 7) fiber_up<NL, M0, kHS, 0>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                    } else {
+                        if (wmax <= 4) fiber_up<NL, M0, 4, 1>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                        else if (NL >= 7 || wmax <= 7) fiber_up<NL, M0, 7, 1>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                        else if constexpr (NL < 7) fiber_up<NL, M0, kHS, 1>(A, F, nslot, active, img, r4, o, BU.d0p, dgbase, impd, yband);
+                    }
                 }
             });
         }
         __syncwarp();
         if ((tid & 31) == 0) { fmbar_arrive(bempty + 8 * s); if (two) fmbar_arrive(bempty + 8); }
-        cuse[s]++;
-        if (two) cuse[1]++;
+        nfill[s]++;
         if (!two) pos ^= 1;
     }
 }
 
 // ---- pass 2: one column (c4 of the strip) of the fiber (outer index o) of the down spin; PART 0: outputs with imp=0 ----
 template <int NL, int M0, int HS, int PART>
-__device__ __forceinline__ void fiber_dw(const FibArgs &A, const OuterEnt *__restrict__ ent, int nslot, bool active, uint32_t img, int c4, int o,
+__device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, int nslot, bool active, uint32_t img, int c4, int o,
                                          int d0r, double *ystrip, int64_t bstride, double &dsum)
 {
     constexpr int NB = NL - 1, D0 = fib::cbinom(NL, M0), A0 = fib::cbinom(NB, M0), B0 = D0 - A0;
@@ -696,22 +831,12 @@ __device__ __forceinline__ void fiber_dw(const FibArgs &A, const OuterEnt *__res
     if (!active) return;
     if constexpr (NIN > 0 && NOUT > 0) {
         const int r0 = o * d0r;
-        const uint32_t base = img + (uint32_t)r0 * 32u + (uint32_t)c4 * 8u;
-        double in[NIN];
-        fib::static_for<NIN>([&](auto jj) { constexpr int J = decltype(jj)::value; in[J] = flds64(base + (uint32_t)(IN0 + J) * 32u); });
-        uint32_t sb[HS];
-        double amp[HS];
-#pragma unroll
-        for (int s = 0; s < HS; s++) {
-            const bool on = s < nslot;
-            sb[s] = img + (uint32_t)((o + (on ? ent->delta[s] : 0)) * d0r) * 32u + (uint32_t)c4 * 8u;
-            amp[s] = on ? __ldg(A.amps + ent->code[s]) : 0.0;
-        }
         // global rows of the outputs: row r0 + k lies in band (r0+k)/4 at sub-row (r0+k)%4; Q[j] serves k == j (mod 4)
         double *Q[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) Q[j] = ystrip + (int64_t)((r0 + j) >> 2) * bstride + ((r0 + j) & 3) * 4 + c4;
-        // y of the outputs, prefetched chunk by chunk (double buffered in registers: CH loads in flight per thread)
+        // y of the outputs, prefetched chunk by chunk (double buffered in registers: CH loads in flight per thread);
+        // the producer has pulled the y tile into L2 together with the x image
         constexpr int CH = 9, NCH = (NOUT + CH - 1) / CH;
         double yv[2][CH];
         auto prefetch = [&](auto cc) {
@@ -722,7 +847,18 @@ __device__ __forceinline__ void fiber_dw(const FibArgs &A, const OuterEnt *__res
             });
         };
         prefetch(std::integral_constant<int, 0>{});
-        const double sig = ent->neg ? -1.0 : 1.0;
+        const uint32_t base = img + (uint32_t)r0 * 32u + (uint32_t)c4 * 8u;
+        double in[NIN];
+        fib::static_for<NIN>([&](auto jj) { constexpr int J = decltype(jj)::value; in[J] = flds64(base + (uint32_t)(IN0 + J) * 32u); });
+        uint32_t sb[HS];
+        double amp[HS];
+#pragma unroll
+        for (int s = 0; s < HS; s++) {
+            const bool on = s < nslot;
+            sb[s] = img + (uint32_t)((o + (on ? F.delta(s) : 0)) * d0r) * 32u + (uint32_t)c4 * 8u;
+            amp[s] = on ? F.amp(s, A.amps) : 0.0;
+        }
+        const double sig = F.neg() ? -1.0 : 1.0;
         fib::static_for<NCH>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             prefetch(std::integral_constant<int, c + 1>{});
@@ -751,6 +887,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
     __shared__ double s_dot[NC / 32];
     const int tid = threadIdx.x;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t stab0 = slot0 + 2u * kSlot;
     const uint32_t bfull = (uint32_t)__cvta_generic_to_shared(s_bar), bempty = bfull + 16u;
     if (tid == 0) {
         fmbar_init(bfull, 1); fmbar_init(bfull + 8, 1);
@@ -761,48 +898,69 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
     const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid >= NC) {
         if (tid == NC) {
-            int use[2] = {0, 0}, pos = 0;
+            int ne[2] = {0, 0}, pos = 0;
+            auto boxes = [&](const FibTile &t, const FibBlockDev &BD, auto &&fn) {
+                for (int g = 0; g < t.b; g++)
+                    for (int b = 0; b < BD.nbox; b++) fn(g, b);
+            };
             for (int i = 0; i < myn; i++) {
                 const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
                 const FibBlockDev BD = A.blk_f[t.blk];
                 const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
-                if (use[s] > 0) fmbar_wait(bempty + 8 * s, (uint32_t)(use[s] - 1) & 1u);
-                if (two && use[1] > 0) fmbar_wait(bempty + 8, (uint32_t)(use[1] - 1) & 1u);
+                if (ne[s] > 0) fmbar_wait_backoff(bempty + 8 * s, (uint32_t)(ne[s] - 1) & 1u);
+                if (two && ne[1] > 0) fmbar_wait_backoff(bempty + 8, (uint32_t)(ne[1] - 1) & 1u);
                 fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
                 const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
                 const uint32_t sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * 128u;
-                for (int g = 0; g < t.b; g++)
-                    for (int b = 0; b < BD.nbox; b++)
-                        ftma_load_3d(dst + (uint32_t)g * sbytes + (uint32_t)b * (uint32_t)BD.BR * 128u, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s);
-                use[s]++;
-                if (!two) pos ^= 1;
+                boxes(t, BD, [&](int g, int b) {
+                    ftma_load_3d(dst + (uint32_t)g * sbytes + (uint32_t)b * (uint32_t)BD.BR * 128u, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s);
+                });
+                // the read-modify-write operand of THIS tile goes to L2 while its x image lands ...
+                boxes(t, BD, [&](int g, int b) { ftma_prefetch_3d(A.tmaps_y + t.pair, 0, t.a + g, b * BD.BR); });
+                ne[s]++;
+                if (two) ne[1]++;
+                else pos ^= 1;
+                // ... and so does the x image of the tile that cannot be loaded yet
+                if (i + 1 < myn) {
+                    const FibTile tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
+                    const bool nextwaits = two || tn.bytes > A.slot;
+                    if (nextwaits || i + 2 < myn) {
+                        const FibTile tp = nextwaits ? tn : A.tiles[blockIdx.x + (size_t)(i + 2) * gridDim.x];
+                        const FibBlockDev BP = A.blk_f[tp.blk];
+                        boxes(tp, BP, [&](int g, int b) { ftma_prefetch_3d(A.tmaps + tp.pair, 0, tp.a + g, b * BP.BR); });
+                    }
+                }
             }
         }
         return;
     }
     double dsum = 0.0;
-    int cuse[2] = {0, 0}, pos = 0;
+    int nfill[2] = {0, 0}, pos = 0, cur_blk = -1;
+    bool stab = false;
     const int warp = tid >> 5, lane = tid & 31;
     for (int i = 0; i < myn; i++) {
         const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
         const bool two = t.bytes > A.slot;
         const int s = two ? 0 : pos;
-        fmbar_wait(bfull + 8 * s, (uint32_t)cuse[s] & 1u);
         const FibBlockDev BD = A.blk_f[t.blk];
         const PairDev pd = A.pairs[t.pair];
         const int C4 = A.blk_o[pd.bj].C4;
+        if (t.blk != cur_blk) { stab = load_stab<NC>(A, BD, stab0, tid); cur_blk = t.blk; }
+        fmbar_wait_warp(bfull + 8 * s, (uint32_t)nfill[s] & 1u);
         const int64_t bstride = (int64_t)C4 * 16;
         const uint32_t sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * 128u;
         // warp-fibers of a strip: [part][8 outer indices per warp]; lanes = (c4 = lane & 3, o = 8*ow + lane/4)
         const int now = (BD.nouter + 7) >> 3, nwf = 2 * now * t.b;
-        for (int wf = warp; wf < nwf; wf += NC / 32) {
+        for (int wf = warp; wf < ((A.dbg & 1) ? 0 : nwf); wf += NC / 32) {
             const int g = wf / (2 * now), rem = wf - g * 2 * now;
             const int part = rem / now, ow = rem - part * now;
             const int c4 = lane & 3, o = 8 * ow + (lane >> 2);
             const bool active = o < BD.nouter;
-            const OuterEnt *ent = A.outer + BD.tab + (active ? o : 0);
-            const int nslot = active ? ent->nslot : 0;
+            FiberMeta F;
+            F.stab = stab ? stab0 + (uint32_t)(active ? o : 0) * (uint32_t)sizeof(SOuter) : 0u;
+            F.ent = A.outer + BD.tab + (active ? o : 0);
+            const int nslot = active ? F.nslot() : 0;
             const int wmax = __reduce_max_sync(0xffffffffu, nslot);
             const uint32_t img = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * sbytes;
             double *ystrip = A.y + pd.base + (int64_t)(t.a + g) * 16;
@@ -810,21 +968,20 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_dw(const __grid_constant
                 constexpr int M0 = decltype(mm)::value + 1;
                 if (BD.m0 == M0) {
                     if (part == 0) {
-                        if (wmax <= 4) fiber_dw<NL, M0, 4, 0>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
-                        else if (NL >= 7 || wmax <= 7) fiber_dw<NL, M0, 7, 0>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
-                        else if constexpr (NL < 7) fiber_dw<NL, M0, kHS, 0>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        if (wmax <= 4) fiber_dw<NL, M0, 4, 0>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        else if (NL >= 7 || wmax <= 7) fiber_dw<NL, M0, 7, 0>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        else if constexpr (NL < 7) fiber_dw<NL, M0, kHS, 0>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
                     } else {
-                        if (wmax <= 4) fiber_dw<NL, M0, 4, 1>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
-                        else if (NL >= 7 || wmax <= 7) fiber_dw<NL, M0, 7, 1>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
-                        else if constexpr (NL < 7) fiber_dw<NL, M0, kHS, 1>(A, ent, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        if (wmax <= 4) fiber_dw<NL, M0, 4, 1>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        else if (NL >= 7 || wmax <= 7) fiber_dw<NL, M0, 7, 1>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
+                        else if constexpr (NL < 7) fiber_dw<NL, M0, kHS, 1>(A, F, nslot, active, img, c4, o, BD.d0r, ystrip, bstride, dsum);
                     }
                 }
             });
         }
         __syncwarp();
         if (lane == 0) { fmbar_arrive(bempty + 8 * s); if (two) fmbar_arrive(bempty + 8); }
-        cuse[s]++;
-        if (two) cuse[1]++;
+        nfill[s]++;
         if (!two) pos ^= 1;
     }
     if (A.dot_out) {
@@ -991,11 +1148,11 @@ static int launch_fiber(edgpu_sector *s, const double *x, double *y, double *dot
     edgpu_ctx *ctx = s->ctx;
     PairLayout &P = *s->pl;
     const FibSpin &FU = *s->up->fib, &FD = *s->dw->fib;
-    const size_t smem = 2 * (size_t)kSlot;
+    const size_t smem = 2 * (size_t)kSlot + kStab;
     int nd = 0;
     FibArgs A;
     memset(&A, 0, sizeof(A));
-    A.pairs = P.d_pairs; A.x = x; A.y = y; A.impmask = (1u << ctx->ham.norb) - 1u; A.slot = P.slot;
+    A.pairs = P.d_pairs; A.x = x; A.y = y; A.impmask = (1u << ctx->ham.norb) - 1u; A.slot = P.slot; A.dbg = (ctx->par.reserved[0] >> 13) & 3;
     A.e_dw = s->dw->ediag; A.cfg_dw = s->dw->cfg; A.xtab = ctx->d_xtab;
     PairGenArgs G{};
     G.pairs = P.d_pairs; G.blk_u = FU.d_blocks; G.blk_d = FD.d_blocks; G.va = sector_vaddr(s);
@@ -1018,10 +1175,11 @@ static int launch_fiber(edgpu_sector *s, const double *x, double *y, double *dot
     // ---- pass 2 ----
     if (P.n2 > 0) {
         if (int rc = fib_ensure_smem(ctx, (const void *)k_fib_dw<NL>, smem)) return rc;
-        const CUtensorMap *tm = nullptr;
+        const CUtensorMap *tm = nullptr, *tmy = nullptr;
         if (int rc = fib_tensor_maps(s, x, &tm)) return rc;
+        if (int rc = fib_tensor_maps(s, y, &tmy)) return rc;
         A.cst = FD.cst; A.blk_f = FD.d_blocks; A.blk_o = FU.d_blocks; A.outer = FD.d_outer; A.amps = FD.d_amps;
-        A.tiles = P.d_t2; A.ntiles = P.n2; A.tmaps = tm;
+        A.tiles = P.d_t2; A.ntiles = P.n2; A.tmaps = tm; A.tmaps_y = tmy;
         const int grid = std::min(ctx->sm_count, P.n2);
         A.dot_out = dot ? dot + nd : nullptr;
         k_fib_dw<NL><<<grid, FibCfg<NL>::NT, smem, ctx->stream>>>(A);
@@ -1045,11 +1203,13 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
 {
     if (!s->pl) return edgpu_fail(s->ctx, "hxv_fiber: the sector is not in the pair-tile layout");
     switch (s->pl->nl) {
+#ifndef EDGPU_FIB_ONLY_NL8                     // (development switch: compile one instantiation only)
         case 3: return launch_fiber<3>(s, x, y, dot, ndot);
         case 4: return launch_fiber<4>(s, x, y, dot, ndot);
         case 5: return launch_fiber<5>(s, x, y, dot, ndot);
         case 6: return launch_fiber<6>(s, x, y, dot, ndot);
         case 7: return launch_fiber<7>(s, x, y, dot, ndot);
+#endif
         case 8: return launch_fiber<8>(s, x, y, dot, ndot);
     }
     return edgpu_fail(s->ctx, "hxv_fiber: %d levels per star are not instantiated", s->pl->nl);

@@ -116,3 +116,67 @@ int hxv_generic(edgpu_sector *s, const double *x, double *y)
     CUDA_TRY(ctx, cudaGetLastError());
     return hxv_jxjp(s, x, y);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Dense Hmat of a small sector in ONE launch (build_Hv_sector(isector,Hmat), ED_HAMILTONIAN.f90:75-79; used for the
+// LAPACK sectors of ED_DIAG.f90:188-193).  One thread per reference row i = ru + rd*DimUp: the row of H is sparse, its
+// entries are the diagonal and the gather-form hop terms of the two spins.  Column-major output in the reference order.
+// (Replaces dim products H e_j with a synchronisation each: the sector scan of ed_solve was bound by those.)
+__global__ void k_invert_perm(int64_t n, const uint32_t *__restrict__ r2i, uint32_t *__restrict__ i2r)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) i2r[r2i ? r2i[r] : r] = (uint32_t)r;
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_rows(int64_t dim_up, int64_t dim_dw, int norb,
+             const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw,
+             const uint32_t *__restrict__ i2r_up, const uint32_t *__restrict__ i2r_dw,
+             const uint32_t *__restrict__ cfg_up, const uint32_t *__restrict__ cfg_dw,
+             const double *__restrict__ e_up, const double *__restrict__ e_dw, const double *__restrict__ xtab,
+             const uint32_t *__restrict__ hop_up, const uint8_t *__restrict__ nhop_up, const double *__restrict__ amp_up,
+             const uint32_t *__restrict__ hop_dw, const uint8_t *__restrict__ nhop_dw, const double *__restrict__ amp_dw,
+             double *__restrict__ H)
+{
+    const int64_t dim = dim_up * dim_dw;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim) return;
+    const int64_t ru = i % dim_up, rd = i / dim_up;
+    const int64_t iu = r2i_up ? r2i_up[ru] : ru, id = r2i_dw ? r2i_dw[rd] : rd;
+    const uint32_t impmask = (1u << norb) - 1u;
+    H[i + dim * i] += e_up[iu] + e_dw[id] + xtab[(cfg_dw[id] & impmask) * 32u + (cfg_up[iu] & impmask)];
+    const int nu = nhop_up[iu];
+    for (int j = 0; j < nu; j++) {
+        const uint32_t h = hop_up[(int64_t)j * dim_up + iu];
+        const int64_t col = (int64_t)i2r_up[h >> 8] + rd * dim_up;
+        H[i + dim * col] += amp_up[h & 255u];
+    }
+    const int nd = nhop_dw[id];
+    for (int j = 0; j < nd; j++) {
+        const uint32_t h = hop_dw[(int64_t)j * dim_dw + id];
+        const int64_t col = ru + (int64_t)i2r_dw[h >> 8] * dim_up;
+        H[i + dim * col] += amp_dw[h & 255u];
+    }
+}
+
+// d_H: dim x dim device buffer (zeroed here).  Returns 1 (without an error message) when the sector needs the
+// two-spin Jx/Jp terms: the caller falls back to products with unit vectors.
+int dense_rows(edgpu_sector *s, double *d_H)
+{
+    edgpu_ctx *ctx = s->ctx;
+    if (ctx->ham.jhflag) return 1;
+    const int64_t dim = s->dim;
+    uint32_t *i2r = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&i2r, sizeof(uint32_t) * (size_t)(s->dim_up + s->dim_dw)));
+    cudaStream_t st = ctx->stream;
+    k_invert_perm<<<(unsigned)((s->dim_up + 255) / 256), 256, 0, st>>>(s->dim_up, s->up->ref2int, i2r);
+    k_invert_perm<<<(unsigned)((s->dim_dw + 255) / 256), 256, 0, st>>>(s->dim_dw, s->dw->ref2int, i2r + s->dim_up);
+    CUDA_TRY(ctx, cudaMemsetAsync(d_H, 0, sizeof(double) * (size_t)dim * (size_t)dim, st));
+    k_dense_rows<<<(unsigned)((dim + 255) / 256), 256, 0, st>>>(s->dim_up, s->dim_dw, ctx->ham.norb, s->up->ref2int, s->dw->ref2int, i2r, i2r + s->dim_up,
+                                                                s->up->cfg, s->dw->cfg, s->up->ediag, s->dw->ediag, ctx->d_xtab,
+                                                                s->up->hop, s->up->nhop, s->up->amp, s->dw->hop, s->dw->nhop, s->dw->amp, d_H);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    cudaFree(i2r);
+    return 0;
+}

@@ -58,6 +58,14 @@ int32_t ed_get_bath_dimension(const ed_input *in);
 int ed_init_solver(const ed_input *in, int device, void *stream, double *bath, int32_t bath_len,
                    const double *hloc_cplx, ed_solver **solver);
 int ed_finalize_solver(ed_solver *solver);
+/* MPI build of the reference (ED_MAIN.f90:62-71 ed_set_MpiComm + ED_MAIN.f90:598-636): one process per GPU.  Rank 0 obtains
+ * the 128-byte id with ed_comm_unique_id, the host broadcasts it, every rank calls ed_set_comm.  ed_solve then deals the
+ * sectors of the scan (ED_DIAG.f90:71-75) round-robin over the ranks, every rank builds the Green's-function /
+ * susceptibility chains and observables of the ground states IT found (ED_GF_NORMAL.f90:150-253), and the results are
+ * summed over the ranks, so that every getter returns the global answer on every rank (ed_get_state* list the local
+ * states only). */
+int ed_comm_unique_id(ed_solver *solver, unsigned char id[128]);
+int ed_set_comm(ed_solver *solver, const unsigned char id[128], int32_t rank, int32_t nranks);
 const char *ed_last_error(const ed_solver *solver);
 
 /* ed_solve(bath[,Hloc]) (ED_MAIN.f90:253-282): set_dmft_bath, diagonalize_impurity, buildgf_impurity,

@@ -78,6 +78,10 @@ int edgpu_sector_build_shard(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int32_t r
 int edgpu_comm_unique_id(edgpu_ctx *ctx, unsigned char id[128]);
 int edgpu_comm_init(edgpu_ctx *ctx, const unsigned char id[128], int32_t rank, int32_t nranks);
 int edgpu_comm_finalize(edgpu_ctx *ctx);
+int edgpu_comm_info(const edgpu_ctx *ctx, int32_t *rank, int32_t *nranks);
+/* host[0..n) <- reduction over the ranks, in place (op 0: sum, 1: min, 2: max): what MPI_Allreduce does for the reference's
+ * MPI build (e.g. the sums over the states of the distributed ed_solve, host/ed_main.cpp) */
+int edgpu_comm_allreduce_host(edgpu_ctx *ctx, double *host, int64_t n, int32_t op);
 /* layout_kind: 0 = one Dimdw x ld tile, 3 = pair tiles; nalloc: doubles stored per vector on this rank */
 int edgpu_sector_info(const edgpu_sector *s, int32_t *layout_kind, int64_t *nalloc, int32_t *shard_rank, int32_t *shard_nranks);
 int edgpu_sector_dim(const edgpu_sector *s, int64_t *dim, int64_t *dim_up, int64_t *dim_dw);

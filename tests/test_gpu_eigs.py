@@ -35,22 +35,27 @@ def test_lanczos_eigs_lowest_pairs(oracle, edb, kernel):
 
 
 def test_ed_solve_reference_default_arpack_six_states(oracle, edb):
-    """Orbital-degenerate two-band model away from half filling: the ground state is degenerate INSIDE a
-    (nup,ndw) sector; the reference default (arpack, 6 states per sector) keeps every member (ED_DIAG.f90:224-235)."""
-    kw = dict(Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, xmu=-1.2, lanc_dim_threshold=32,
-              lanc_method="arpack", lanc_nstates_sector=6)
-    p, ref, sol = run_pair(oracle, edb, **kw)
-    states, zeta, egs = sol.states()
-    assert zeta == ref.zeta and len(states) == len(ref.states)
-    compare(p, ref, sol, tol_obs=1e-8, tol_g=1e-8)
-    # the same model with one state per sector would lose members whenever a sector holds a degenerate level
+    """Orbital-degenerate two-band model away from half filling: the ground level is doubly degenerate INSIDE
+    the (2,3) and (3,2) sectors; the reference default (arpack, 6 states per sector) keeps every member
+    (ED_DIAG.f90:224-235).  Expected values: the oracle with LAPACK in every sector (lanc_dim_threshold above the largest
+    sector), whose eigenvectors are orthonormal.  (ARPACK -- the oracle's eigsh branch, like the reference -- returns the
+    two copies of a degenerate level with an overlap of ~5e-3, which moves the densities by 1e-3; the device solver
+    locks converged vectors and re-runs in their complement, so its basis of the level is orthonormal.)"""
+    kw = dict(Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, xmu=-1.2, lanc_method="arpack", lanc_nstates_sector=6)
+    base = dict(Lmats=128, Lreal=128, beta=100.0)
+    pref = oracle.Params(lanc_dim_threshold=1024, **kw, **base)
+    ref = oracle.ed_solve(pref, oracle.init_bath(pref))
     per_sector = {}
     for st in ref.states:
         per_sector[(st.nup, st.ndw)] = per_sector.get((st.nup, st.ndw), 0) + 1
+    assert max(per_sector.values()) > 1
+    p, _, sol = run_pair(oracle, edb, lanc_dim_threshold=32, **kw)            # the 300- and 400-state sectors go through eigs.cu
+    states, zeta, egs = sol.states()
+    assert zeta == ref.zeta and len(states) == len(ref.states)
+    compare(p, ref, sol, tol_obs=1e-8, tol_g=1e-8)
+    assert sol.sector_nlanc(2, 3) > 0                                          # that sector really took the Lanczos path
     sol.close()
-    assert max(per_sector.values()) > 1                     # xmu=-1.2: (2,3) and (3,2) each hold a doubly degenerate ground level
-    if True:
-        kw1 = dict(kw, lanc_method="lanczos", lanc_nstates_sector=1)
-        p1, ref1, sol1 = run_pair(oracle, edb, **kw1)
-        assert len(sol1.states()[0]) < len(states)
-        sol1.close()
+    # one state per sector loses members of the level
+    p1, ref1, sol1 = run_pair(oracle, edb, lanc_dim_threshold=32, **dict(kw, lanc_method="lanczos", lanc_nstates_sector=1))
+    assert len(sol1.states()[0]) < len(states)
+    sol1.close()
