@@ -4,14 +4,14 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu comm.cu eigs.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
+SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu fib_nl3.cu fib_nl4.cu fib_nl5.cu fib_nl6.cu fib_nl7.cu fib_nl8.cu comm.cu eigs.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
 mkdir -p ../build
 OBJS=""
 PIDS=""
 for f in $SRCS; do
   [ -f "$f" ] || continue
   o=../build/$(basename ${f%.*}).o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ edgpu_internal.h -nt "$o" ] || [ ../../include/edgpu.h -nt "$o" ] || [ star_info.h -nt "$o" ] || [ -f host/ed_host.h -a host/ed_host.h -nt "$o" ] || [ ../../include/ed_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ edgpu_internal.h -nt "$o" ] || [ ../../include/edgpu.h -nt "$o" ] || [ star_info.h -nt "$o" ] || [ fiber_common.h -nt "$o" ] || { case "$f" in fib_nl*) [ fiber_kernels.cuh -nt "$o" ];; *) false;; esac; } || [ -f host/ed_host.h -a host/ed_host.h -nt "$o" ] || [ ../../include/ed_b200.h -nt "$o" ]; then
     echo "nvcc $f"
     rm -f "$o"
     $NVCC $FLAGS ${EXTRA_FLAGS} -x cu -c "$f" -o "$o" &
