@@ -578,7 +578,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the ed_solve wall-time section")
-    ap.add_argument("--solve-cfg3", action="store_true", help="also time a full ed_solve of BASELINE config 3 (Ns=14, 225 sectors)")
+    ap.add_argument("--no-solve-cfg3", action="store_true", help="skip the full ed_solve of BASELINE config 3 (Ns=14, 225 sectors)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mode", default="auto", choices=["auto", "pairs", "strips", "chains"],
                     help="N>1: 'pairs' (default) = one sector vector sharded by conserved occupation pairs, no exchange; 'strips' = "
@@ -678,7 +678,9 @@ def main():
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get(args.workload)
+            tjd = json.load(open(tj))
+            # per-H*v DRAM bytes from an ncu capture; only valid for the kernel version it was taken at
+            traffic = tjd.get(args.workload) if tjd.get("edgpu_version") == edb.lib().edgpu_version() else None
         except Exception:
             traffic = None
 
@@ -717,24 +719,41 @@ def main():
                "ms_per_lanczos_step": (te - max(tup)) / nlanc * 1e3}
 
     # ---- ed_solve wall time (BASELINE metric, second half): full sector scan + GF + Sigma + observables ------------
+    # cfg1 / cfg2 / cfg3 on the GPU; beside them the CPU oracle's ed_solve (rank 0, same inputs): the full scan for cfg1, and
+    # for cfg2 the half-filling window of 7 sectors (ED_SECTORS) on BOTH sides -- the oracle's full Ns=10 scan takes
+    # ~4.5 minutes, which does not fit a bench run.
     solve = None
     if rank == 0 and world == 1 and not args.no_solve:
         solve = {}
-        cases = [("cfg1", dict(Norb=1, Nbath=4)), ("cfg2", dict(Norb=1, Nbath=9))]
-        if args.solve_cfg3:
-            cases.append(("cfg3", dict(Norb=2, Nbath=6, uloc=[2.0, 2.0])))
-        for name, kw in cases:
+        win2 = [(5, 5), (4, 5), (5, 4), (6, 5), (5, 6), (4, 4), (6, 6)]
+        cases = [("cfg1", dict(Norb=1, Nbath=4), None), ("cfg2", dict(Norb=1, Nbath=9), None), ("cfg2_window", dict(Norb=1, Nbath=9), win2)]
+        if not args.no_solve_cfg3:
+            cases.append(("cfg3", dict(Norb=2, Nbath=6, uloc=[2.0, 2.0]), None))
+        for name, kw, secs in cases:
             si = edb.default_input(lanc_method="lanczos", lanc_nstates_sector=1, ed_sparse_H=0, Lmats=1024, Lreal=1024, **kw)
             so = edb.Solver(si, device=local, stream=stream)
+            if secs:
+                so.set_sectors(secs)
             so.solve()                                    # warm-up (table builds, allocator)
             t0 = time.perf_counter()
             so.solve()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             st, zeta, egs = so.states()
-            solve[name] = {"wall_s": dt, "phases_s": so.timings(), "egs": egs, "n_gs": len(st),
-                           "sectors": (si.Nbath * si.Norb + si.Norb + 1) ** 2, "scan": "all sectors, lanc_method=lanczos, direct H*v"}
+            nsec = len(secs) if secs else (si.Nbath * si.Norb + si.Norb + 1) ** 2
+            solve[name] = {"wall_s": dt, "phases_s": so.timings(), "egs": egs, "n_gs": len(st), "sectors": nsec,
+                           "scan": "lanc_method=lanczos, direct H*v" + ("" if not secs else ", half-filling window")}
             so.close()
+            if not args.no_cpu and name in ("cfg1", "cfg2_window"):
+                from oracle import ed_oracle as O
+                O.build()
+                po = O.Params(lanc_method="lanczos", lanc_nstates_sector=1, Lmats=1024, Lreal=1024,
+                              **{k: (tuple(v) if isinstance(v, list) else v) for k, v in kw.items()})
+                t0 = time.perf_counter()
+                ro = O.ed_solve(po, O.init_bath(po), sectors=secs)
+                solve[name]["cpu_oracle_wall_s"] = time.perf_counter() - t0
+                solve[name]["cpu_oracle_egs"] = ro.egs
+                solve[name]["cpu_kind"] = "port, 1 thread (numpy + C oracle)"
 
     # ---- parity of the timed product against the oracle (rank 0, N=1): sampled reference rows -------------------------
     parity = None

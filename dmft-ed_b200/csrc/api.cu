@@ -38,6 +38,53 @@ int edgpu_fail(edgpu_ctx *ctx, const char *fmt, ...)
     return 1;
 }
 
+// ---- pooled device buffers ----------------------------------------------------------------------------------
+int pool_alloc(edgpu_ctx *ctx, size_t bytes, void **p)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    auto it = ctx->pool_free.lower_bound(bytes);
+    if (it != ctx->pool_free.end() && it->first <= bytes + bytes / 4) {          // at most 25 % larger than asked
+        *p = it->second;
+        ctx->pool_held -= it->first;
+        ctx->pool_free.erase(it);
+        return 0;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {                                                      // give the cached buffers back and retry
+        cudaGetLastError();
+        pool_trim(ctx, 0);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) return edgpu_fail(ctx, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    ctx->pool_size[*p] = bytes;
+    return 0;
+}
+
+void pool_release(edgpu_ctx *ctx, void *p)
+{
+    if (!p) return;
+    auto it = ctx->pool_size.find(p);
+    if (it == ctx->pool_size.end()) { cudaFree(p); return; }
+    ctx->pool_free.emplace(it->second, p);
+    ctx->pool_held += it->second;
+    const size_t cap = ctx->mem_bytes > 0 ? (size_t)ctx->mem_bytes / 3 : ((size_t)32 << 30);
+    if (ctx->pool_held > cap) pool_trim(ctx, cap / 2);
+}
+
+void pool_trim(edgpu_ctx *ctx, size_t keep_bytes)
+{
+    if (ctx->pool_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    while (!ctx->pool_free.empty() && ctx->pool_held > keep_bytes) {
+        auto it = std::prev(ctx->pool_free.end());                               // largest first
+        cudaFree(it->second);
+        ctx->pool_size.erase(it->second);
+        ctx->pool_held -= it->first;
+        ctx->pool_free.erase(it);
+    }
+}
+
 CsrMatrix::~CsrMatrix() { cudaFree(rowptr); cudaFree(cols); cudaFree(rowlen); cudaFree(vals); }
 
 extern "C" const char *edgpu_last_error(const edgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_null_err.c_str(); }
@@ -93,6 +140,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     edgpu_comm_finalize(ctx);
+    pool_trim(ctx, 0);
     ctx->bases.clear();
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -209,7 +257,7 @@ extern "C" int edgpu_sector_free(edgpu_sector *s)
 {
     if (!s) return 0;
     cudaStreamSynchronize(s->ctx->stream);
-    for (int i = 0; i < 3; i++) cudaFree(s->work[i]);
+    for (int i = 0; i < 3; i++) pool_release(s->ctx, s->work[i]);
     delete s;
     return 0;
 }
@@ -264,8 +312,7 @@ extern "C" int edgpu_vec_alloc(edgpu_sector *s, edgpu_vec **out)
     edgpu_ctx *ctx = s->ctx;
     auto v = new edgpu_vec();
     v->s = s;
-    cudaError_t e = cudaMalloc(&v->d, sizeof(double) * (size_t)s->nalloc);
-    if (e != cudaSuccess) { delete v; return edgpu_fail(ctx, "edgpu_vec_alloc: cudaMalloc of %lld doubles failed: %s", (long long)s->nalloc, cudaGetErrorString(e)); }
+    if (int rc = pool_alloc(ctx, sizeof(double) * (size_t)s->nalloc, (void **)&v->d)) { delete v; return rc; }
     CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)s->nalloc, ctx->stream));
     *out = v;
     return 0;
@@ -274,9 +321,7 @@ extern "C" int edgpu_vec_alloc(edgpu_sector *s, edgpu_vec **out)
 extern "C" int edgpu_vec_free(edgpu_vec *v)
 {
     if (!v) return 0;
-    cudaStreamSynchronize(v->s->ctx->stream);
-    pair_layout_forget(v->s, v->d);
-    cudaFree(v->d);
+    pool_release(v->s->ctx, v->d);              // stream-ordered reuse: no synchronisation needed
     delete v;
     return 0;
 }
@@ -284,9 +329,7 @@ extern "C" int edgpu_vec_free(edgpu_vec *v)
 // Staging buffer in the reference order (real or interleaved complex), then a conversion kernel.
 static int stage_alloc(edgpu_ctx *ctx, size_t bytes, double **p)
 {
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess) return edgpu_fail(ctx, "staging cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    return 0;
+    return pool_alloc(ctx, bytes, (void **)p);
 }
 
 extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cplx)
@@ -356,7 +399,7 @@ extern "C" int edgpu_vec_download(const edgpu_vec *v, double *host, int32_t is_c
         if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_vec_download: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
+    pool_release(ctx, stage);
     return rc;
 }
 
@@ -377,7 +420,7 @@ extern "C" int edgpu_vec_download_rows(const edgpu_vec *v, int64_t rd0, int64_t 
         if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_vec_download_rows: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
+    pool_release(ctx, stage);
     return rc;
 }
 
@@ -472,7 +515,7 @@ extern "C" int edgpu_hxv(edgpu_sector *s, int64_t nloc, const double *v_cplx, do
         if (cudaMemcpyAsync(hv_cplx, stage, cb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = edgpu_fail(ctx, "edgpu_hxv: D2H failed"); break; }
     } while (0);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
+    pool_release(ctx, stage);
     if (!rc && e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_hxv: %s", cudaGetErrorString(e));
     return rc;
 }
@@ -486,15 +529,15 @@ extern "C" int edgpu_sector_dense(edgpu_sector *s, double *hmat)
     {
         // one launch: every thread writes the (sparse) row of its reference state into the dense matrix
         double *d_H = nullptr;
-        CUDA_TRY(ctx, cudaMalloc(&d_H, sizeof(double) * (size_t)n * (size_t)n));
+        if (int rc0 = pool_alloc(ctx, sizeof(double) * (size_t)n * (size_t)n, (void **)&d_H)) return rc0;
         const int rc = dense_rows(s, d_H);
         if (rc == 0) {
             cudaError_t e = cudaMemcpy(hmat, d_H, sizeof(double) * (size_t)n * (size_t)n, cudaMemcpyDeviceToHost);
-            cudaFree(d_H);
+            pool_release(ctx, d_H);
             if (e != cudaSuccess) return edgpu_fail(ctx, "edgpu_sector_dense: %s", cudaGetErrorString(e));
             return 0;
         }
-        cudaFree(d_H);
+        pool_release(ctx, d_H);
         if (!ctx->ham.jhflag) return rc;          // a real error; with Jx/Jp fall through to H applied to unit vectors
     }
     double *x, *y, *yr;

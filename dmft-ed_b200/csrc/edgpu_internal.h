@@ -9,7 +9,7 @@
 #include <vector>
 #include "../../include/edgpu.h"
 
-#define EDGPU_VERSION 100
+#define EDGPU_VERSION 200
 
 // ---- error plumbing: every C-ABI call returns int; message kept in the context (the reference `stop`s) ----
 struct edgpu_ctx;
@@ -133,7 +133,16 @@ struct edgpu_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     EdComm *comm = nullptr;            // set by edgpu_comm_init: reductions of sharded sectors are summed over the ranks
+    // stream-ordered pool of the large device buffers (sector vectors, Lanczos workspaces, staging): an ed_solve scan builds
+    // and frees hundreds of sectors, and cudaMalloc / cudaFree of ~100 MB buffers (10-50 ms each, device-synchronising)
+    // dominated its wall time.  Every user of a pooled buffer works on ctx->stream, so reuse is ordered by the stream.
+    std::multimap<size_t, void *> pool_free;
+    std::map<void *, size_t> pool_size;
+    size_t pool_held = 0;
 };
+int pool_alloc(edgpu_ctx *ctx, size_t bytes, void **p);
+void pool_release(edgpu_ctx *ctx, void *p);
+void pool_trim(edgpu_ctx *ctx, size_t keep_bytes);
 
 struct edgpu_sector {
     edgpu_ctx *ctx = nullptr;

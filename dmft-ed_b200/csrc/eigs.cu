@@ -125,9 +125,8 @@ extern "C" int edgpu_lanczos_eigs(edgpu_sector *s, int32_t neigen, int32_t ncv, 
     if (maxrestart < 1) maxrestart = 300;
     const int nvtot = maxlock + m + 1;
     double *V = nullptr, *d_part = nullptr, *d_h = nullptr, *d_S = nullptr;
-    cudaError_t ce = cudaMalloc(&V, sizeof(double) * (size_t)n * (size_t)nvtot);
-    if (ce != cudaSuccess) return edgpu_fail(ctx, "edgpu_lanczos_eigs: cudaMalloc of %d basis vectors (%lld doubles each) failed: %s", nvtot, (long long)n, cudaGetErrorString(ce));
-    auto cleanup = [&]() { cudaFree(V); cudaFree(d_part); cudaFree(d_h); cudaFree(d_S); };
+    if (int rc0 = pool_alloc(ctx, sizeof(double) * (size_t)n * (size_t)nvtot, (void **)&V)) return rc0;
+    auto cleanup = [&]() { pool_release(ctx, V); cudaFree(d_part); cudaFree(d_h); cudaFree(d_S); };
     if (cudaMalloc(&d_part, sizeof(double) * (size_t)kMdBlocks * kMaxBasis) != cudaSuccess || cudaMalloc(&d_h, sizeof(double) * 2 * kMaxBasis) != cudaSuccess ||
         cudaMalloc(&d_S, sizeof(double) * (size_t)kMaxBasis * kMaxBasis) != cudaSuccess) { cleanup(); return edgpu_fail(ctx, "edgpu_lanczos_eigs: scratch allocation failed"); }
     cudaStream_t st = ctx->stream;

@@ -150,6 +150,10 @@ struct PairLayout {
     FibTile *d_t1 = nullptr, *d_t2 = nullptr;
     int n1 = 0, n2 = 0;
     int *d_g1 = nullptr, *d_g2 = nullptr;      // pair ids for the generic up / down kernels
+    // tables of the memory-order pair kernels: inverse position maps (padded position -> internal index, -1 = pad) per
+    // block, concatenated (start of block b at *_start[b]), and hop tables whose targets are POSITIONS inside the block
+    int *d_idx_of_cp = nullptr, *d_idx_of_rp = nullptr, *d_cp_start = nullptr, *d_rp_start = nullptr;
+    uint32_t *d_poshop_c = nullptr, *d_poshop_r = nullptr;
     int ng1 = 0, ng2 = 0;
     int64_t g1_elems = 0, g2_elems = 0;
     int nl = 0;
@@ -160,6 +164,7 @@ struct PairLayout {
     {
         cudaFree(d_rowinfo); cudaFree(d_colinfo); cudaFree(d_pbase); cudaFree(d_c4); cudaFree(d_pairs); cudaFree(d_t1); cudaFree(d_t2);
         cudaFree(d_g1); cudaFree(d_g2);
+        cudaFree(d_idx_of_cp); cudaFree(d_idx_of_rp); cudaFree(d_cp_start); cudaFree(d_rp_start); cudaFree(d_poshop_c); cudaFree(d_poshop_r);
         for (auto &kv : tmaps) cudaFree(kv.second);
     }
 };

@@ -28,6 +28,7 @@
 #include <cstring>
 
 uint64_t edgpu_binom(int n, int k);
+__global__ void k_poshop(int64_t dim, int maxhop, const uint32_t *__restrict__ hop, const int2 *__restrict__ info, uint32_t *__restrict__ out);
 
 static int colex_rank_host(uint32_t w)
 {
@@ -200,7 +201,7 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     }
     const int slot = P->slot;
     // ownership: LPT over pair COSTS (deterministic: ties by pair index).  cost = stored elements, weighted by the pass
-    // kernels the pair will get: a pass through the thread-per-element kernels is ~16x slower per element than a fiber pass
+    // kernels the pair will get: a pass through the memory-order pair kernels is ~6x slower per element than a fiber pass (measured on Ns=18)
     std::vector<int64_t> psize((size_t)nbd * nbu), pcost((size_t)nbd * nbu);
     std::vector<int> order((size_t)nbd * nbu), owner((size_t)nbd * nbu, 0);
     for (int i = 0; i < nbd; i++)
@@ -209,7 +210,7 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
             const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock);
             const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock);
             psize[(size_t)i * nbu + j] = (int64_t)BD.R4 * BU.C4 * 16;
-            pcost[(size_t)i * nbu + j] = psize[(size_t)i * nbu + j] * ((fu ? 1 : 16) + (fd ? 1 : 16));
+            pcost[(size_t)i * nbu + j] = psize[(size_t)i * nbu + j] * ((fu ? 1 : 6) + (fd ? 1 : 6));
             order[(size_t)i * nbu + j] = i * nbu + j;
         }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pcost[a] > pcost[b]; });
@@ -303,6 +304,31 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     CUDA_TRY(ctx, up(&P->d_t2, t2));
     CUDA_TRY(ctx, up(&P->d_g1, g1));
     CUDA_TRY(ctx, up(&P->d_g2, g2));
+    if (!g1.empty() || !g2.empty()) {
+        // memory-order pair kernels: inverse position maps per block and position-resolved hop tables
+        std::vector<int> cps(nbu + 1, 0), rps(nbd + 1, 0);
+        for (int j = 0; j < nbu; j++) cps[j + 1] = cps[j] + FU.blocks[j].C;
+        for (int i = 0; i < nbd; i++) rps[i + 1] = rps[i] + FD.blocks[i].R;
+        std::vector<int> icp((size_t)cps[nbu], -1), irp((size_t)rps[nbd], -1);
+        for (int j = 0; j < nbu; j++) {
+            const FibBlockDev &B = FU.blocks[j];
+            for (int e = 0; e < B.size; e++) icp[(size_t)cps[j] + (e / B.D0) * B.d0p + e % B.D0] = B.off + e;
+        }
+        for (int i = 0; i < nbd; i++) {
+            const FibBlockDev &B = FD.blocks[i];
+            for (int e = 0; e < B.size; e++) irp[(size_t)rps[i] + (e / B.D0) * B.d0r + e % B.D0] = B.off + e;
+        }
+        CUDA_TRY(ctx, up(&P->d_idx_of_cp, icp));
+        CUDA_TRY(ctx, up(&P->d_idx_of_rp, irp));
+        CUDA_TRY(ctx, up(&P->d_cp_start, cps));
+        CUDA_TRY(ctx, up(&P->d_rp_start, rps));
+        const int mhu = std::max(1, s->up->maxhop), mhd = std::max(1, s->dw->maxhop);
+        CUDA_TRY(ctx, cudaMalloc(&P->d_poshop_c, sizeof(uint32_t) * (size_t)s->dim_up * mhu));
+        CUDA_TRY(ctx, cudaMalloc(&P->d_poshop_r, sizeof(uint32_t) * (size_t)s->dim_dw * mhd));
+        k_poshop<<<(unsigned)((s->dim_up + 255) / 256), 256, 0, st>>>(s->dim_up, s->up->maxhop, s->up->hop, P->d_colinfo, P->d_poshop_c);
+        k_poshop<<<(unsigned)((s->dim_dw + 255) / 256), 256, 0, st>>>(s->dim_dw, s->dw->maxhop, s->dw->hop, P->d_rowinfo, P->d_poshop_r);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     s->pl = P;
     return 0;
@@ -314,14 +340,27 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
 struct PairGenArgs {
     const PairDev *pairs; const int *list; int nlist;
     const FibBlockDev *blk_u, *blk_d;
-    VAddr va;
+    const int *idx_of_cp, *idx_of_rp, *cp_start, *rp_start;
     const uint32_t *cfg_up, *cfg_dw; const double *e_up, *e_dw, *xtab;
-    const uint32_t *hop; const uint8_t *nhop; const double *amp; int64_t hop_ld;     // of the spin that is applied
+    const uint32_t *poshop; const uint8_t *nhop; const double *amp; int64_t hop_ld;     // of the spin that is applied
     uint32_t impmask;
     const double *x; double *y; double *dot_out;
 };
 
-// y = H_dw x on the listed pairs (first pass: every element of the pair is written)
+// Hop table with positions as targets: out[j*dim + i] = (position of target(in[j*dim + i]) << 8) | amplitude code
+__global__ void k_poshop(int64_t dim, int maxhop, const uint32_t *__restrict__ hop, const int2 *__restrict__ info, uint32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim) return;
+    for (int j = 0; j < maxhop; j++) {
+        const uint32_t h = hop[(int64_t)j * dim + i];
+        out[(int64_t)j * dim + i] = ((uint32_t)info[h >> 8].y << 8) | (h & 255u);
+    }
+}
+
+// The two kernels walk a pair in MEMORY order (thread = one element of a micro-tile: coalesced own accesses); the hop
+// sources are gathered through L2 inside the same band (up) / the same strip (down).
+// y = H_dw x on the listed pairs (first pass: every element of the pair is written; pads receive zero)
 __global__ void __launch_bounds__(256) k_pair_dw(const PairGenArgs A)
 {
     __shared__ double s_amp[256];
@@ -330,16 +369,23 @@ __global__ void __launch_bounds__(256) k_pair_dw(const PairGenArgs A)
     for (int q = blockIdx.y; q < A.nlist; q += gridDim.y) {
         const PairDev pd = A.pairs[A.list[q]];
         const FibBlockDev BD = A.blk_d[pd.bi], BU = A.blk_u[pd.bj];
-        const int64_t total = (int64_t)BD.size * BU.size;
-        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t id = BD.off + e / BU.size, iu = BU.off + e % BU.size;
+        const int *irp = A.idx_of_rp + A.rp_start[pd.bi];
+        const int64_t C4 = BU.C4, ntile = (int64_t)BD.R4 * C4;
+        for (int64_t tile = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); tile < ntile; tile += (int64_t)gridDim.x * 16) {
+            const int within = threadIdx.x & 15, r4 = within >> 2, c4 = within & 3;
+            const int64_t band = tile / C4, ct = tile - band * C4;
+            const int rp = (int)band * 4 + r4;
+            const int id = rp < BD.R ? irp[rp] : -1;
             double acc = 0.0;
-            const int nd = A.nhop[id];
-            for (int j = 0; j < nd; j++) {
-                const uint32_t h = A.hop[(int64_t)j * A.hop_ld + id];
-                acc += s_amp[h & 255u] * A.x[A.va(h >> 8, iu)];
+            if (id >= 0) {
+                const int nd = A.nhop[id];
+                for (int j = 0; j < nd; j++) {
+                    const uint32_t h = A.poshop[(int64_t)j * A.hop_ld + id];
+                    const int rp2 = (int)(h >> 8);
+                    acc += s_amp[h & 255u] * A.x[pd.base + ((int64_t)(rp2 >> 2) * C4 + ct) * 16 + (rp2 & 3) * 4 + c4];
+                }
             }
-            A.y[A.va(id, iu)] = acc;
+            A.y[pd.base + tile * 16 + within] = acc;
         }
     }
 }
@@ -354,16 +400,22 @@ __global__ void __launch_bounds__(256) k_pair_up(const PairGenArgs A)
     for (int q = blockIdx.y; q < A.nlist; q += gridDim.y) {
         const PairDev pd = A.pairs[A.list[q]];
         const FibBlockDev BD = A.blk_d[pd.bi], BU = A.blk_u[pd.bj];
-        const int64_t total = (int64_t)BD.size * BU.size;
-        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t id = BD.off + e / BU.size, iu = BU.off + e % BU.size;
-            const int64_t a = A.va(id, iu);
+        const int *irp = A.idx_of_rp + A.rp_start[pd.bi], *icp = A.idx_of_cp + A.cp_start[pd.bj];
+        const int64_t C4 = BU.C4, ntile = (int64_t)BD.R4 * C4;
+        for (int64_t tile = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); tile < ntile; tile += (int64_t)gridDim.x * 16) {
+            const int within = threadIdx.x & 15, r4 = within >> 2, c4 = within & 3;
+            const int64_t band = tile / C4, ct = tile - band * C4;
+            const int rp = (int)band * 4 + r4, cp = (int)ct * 4 + c4;
+            const int id = rp < BD.R ? irp[rp] : -1, iu = cp < BU.C ? icp[cp] : -1;
+            if (id < 0 || iu < 0) continue;
+            const int64_t a = pd.base + tile * 16 + within, rowb = pd.base + band * C4 * 16 + r4 * 4;
             const double xo = A.x[a];
             double acc = A.y[a] + (A.e_up[iu] + A.e_dw[id] + A.xtab[(A.cfg_dw[id] & A.impmask) * 32u + (A.cfg_up[iu] & A.impmask)]) * xo;
             const int nu = A.nhop[iu];
             for (int j = 0; j < nu; j++) {
-                const uint32_t h = A.hop[(int64_t)j * A.hop_ld + iu];
-                acc += s_amp[h & 255u] * A.x[A.va(id, h >> 8)];
+                const uint32_t h = A.poshop[(int64_t)j * A.hop_ld + iu];
+                const int cp2 = (int)(h >> 8);
+                acc += s_amp[h & 255u] * A.x[rowb + (int64_t)(cp2 >> 2) * 16 + (cp2 & 3)];
             }
             A.y[a] = acc;
             dsum = fma(xo, acc, dsum);
@@ -478,7 +530,8 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
     A.dbg = (ctx->par.reserved[0] >> 13) & 3;
     A.e_dw = s->dw->ediag; A.cfg_dw = s->dw->cfg; A.xtab = ctx->d_xtab;
     PairGenArgs G{};
-    G.pairs = P.d_pairs; G.blk_u = FU.d_blocks; G.blk_d = FD.d_blocks; G.va = sector_vaddr(s);
+    G.pairs = P.d_pairs; G.blk_u = FU.d_blocks; G.blk_d = FD.d_blocks;
+    G.idx_of_cp = P.d_idx_of_cp; G.idx_of_rp = P.d_idx_of_rp; G.cp_start = P.d_cp_start; G.rp_start = P.d_rp_start;
     G.cfg_up = s->up->cfg; G.cfg_dw = s->dw->cfg; G.e_up = s->up->ediag; G.e_dw = s->dw->ediag; G.xtab = ctx->d_xtab;
     G.impmask = A.impmask; G.x = x; G.y = y;
     // ---- first pass: y = H_dw x (strips of 4 columns; write-only) ----
@@ -490,9 +543,9 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
         if (int rc = fib_launch_any(ctx, P.nl, 2, A, std::min(ctx->sm_count, P.n2))) return rc;
     }
     if (P.ng2 > 0) {
-        G.list = P.d_g2; G.nlist = P.ng2; G.hop = s->dw->hop; G.nhop = s->dw->nhop; G.amp = s->dw->amp; G.hop_ld = s->dw->dim; G.dot_out = nullptr;
+        G.list = P.d_g2; G.nlist = P.ng2; G.poshop = P.d_poshop_r; G.nhop = s->dw->nhop; G.amp = s->dw->amp; G.hop_ld = s->dw->dim; G.dot_out = nullptr;
         const int64_t per = P.g2_elems / P.ng2 + 1;
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (per + 255) / 256)), (unsigned)std::min(P.ng2, 4096));
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), (unsigned)std::min(P.ng2, 2048));
         k_pair_dw<<<grid, 256, 0, ctx->stream>>>(G);
     }
     // ---- second pass: y += (diag + H_up) x (bands of 4 rows; read-modify-write, partial <x, y>) ----
@@ -505,9 +558,10 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
         if (dot) nd += grid;
     }
     if (P.ng1 > 0) {
-        G.list = P.d_g1; G.nlist = P.ng1; G.hop = s->up->hop; G.nhop = s->up->nhop; G.amp = s->up->amp; G.hop_ld = s->up->dim;
+        G.list = P.d_g1; G.nlist = P.ng1; G.poshop = P.d_poshop_c; G.nhop = s->up->nhop; G.amp = s->up->amp; G.hop_ld = s->up->dim;
         const int64_t per = P.g1_elems / P.ng1 + 1;
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (per + 255) / 256)), (unsigned)std::min(P.ng1, 128));
+        const unsigned gy = (unsigned)std::min(P.ng1, 32);
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), gy);
         G.dot_out = dot ? dot + nd : nullptr;
         k_pair_up<<<grid, 256, 0, ctx->stream>>>(G);
         if (dot) nd += (int)(grid.x * grid.y);

@@ -167,7 +167,7 @@ int dense_rows(edgpu_sector *s, double *d_H)
     if (ctx->ham.jhflag) return 1;
     const int64_t dim = s->dim;
     uint32_t *i2r = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&i2r, sizeof(uint32_t) * (size_t)(s->dim_up + s->dim_dw)));
+    if (int rc = pool_alloc(ctx, sizeof(uint32_t) * (size_t)(s->dim_up + s->dim_dw), (void **)&i2r)) return rc;
     cudaStream_t st = ctx->stream;
     k_invert_perm<<<(unsigned)((s->dim_up + 255) / 256), 256, 0, st>>>(s->dim_up, s->up->ref2int, i2r);
     k_invert_perm<<<(unsigned)((s->dim_dw + 255) / 256), 256, 0, st>>>(s->dim_dw, s->dw->ref2int, i2r + s->dim_up);
@@ -177,6 +177,6 @@ int dense_rows(edgpu_sector *s, double *d_H)
                                                                 s->up->hop, s->up->nhop, s->up->amp, s->dw->hop, s->dw->nhop, s->dw->amp, d_H);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    cudaFree(i2r);
+    pool_release(ctx, i2r);
     return 0;
 }

@@ -149,7 +149,7 @@ int vec_axpy(edgpu_ctx *ctx, double *acc, const double *v, double z, int64_t n)
 int sector_work(edgpu_sector *s, int i, double **p)
 {
     if (!s->work[i]) {
-        CUDA_TRY(s->ctx, cudaMalloc(&s->work[i], sizeof(double) * (size_t)s->nalloc));
+        if (int rc = pool_alloc(s->ctx, sizeof(double) * (size_t)s->nalloc, (void **)&s->work[i])) return rc;
         CUDA_TRY(s->ctx, cudaMemsetAsync(s->work[i], 0, sizeof(double) * (size_t)s->nalloc, s->ctx->stream));
     }
     *p = s->work[i];
