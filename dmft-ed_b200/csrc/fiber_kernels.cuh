@@ -8,6 +8,7 @@
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fmbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void fmbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void fmbar_expect_tx_only(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void fmbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void fmbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -266,6 +267,25 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
     }
 }
 
+// Tile descriptors travel from the producer thread to the consumers through a 4-entry ring in shared memory (entry i+1 is
+// written before the arrive on full(i), read after full(i) was observed).  Together with volatile re-reads of the few fields a
+// work unit needs, this keeps the state that is live across the (huge, fully unrolled) fiber bodies small: the first build kept
+// the descriptor in registers, which ptxas spilled -- ~30 local-memory reloads per unit, each an L2 round trip next to 226 KB
+// of shared memory (26 % of the stall samples sat at the head of a unit, another 13 % at its tail and at the tile head).
+struct UpRing {                 // 64 bytes
+    int off_lo, off_hi, bytes, blk;
+    int a, b, q0, q1;
+    int q2, q3, m0, d0p;
+    int nouter, C4, tab, nwf;
+};
+#define UPR(field) ((uint32_t)offsetof(UpRing, field))
+__device__ __forceinline__ int ring_ld(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int NL>
 __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant__ FibArgs A)
 {
@@ -273,29 +293,43 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[4];
     __shared__ double s_dot[NW];
+    __shared__ __align__(16) UpRing s_ring[4];
     const int tid = threadIdx.x;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t stab0 = slot0 + 2u * kSlot;
     const uint32_t bfull = (uint32_t)__cvta_generic_to_shared(s_bar), bempty = bfull + 16u;
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring);
+    const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto ring_put = [&](int i, const FibTile &t) {
+        const FibBlockDev BU = A.blk_f[t.blk];
+        const uint32_t d = ring0 + (uint32_t)(i & 3) * (uint32_t)sizeof(UpRing);
+        const int nwf = (4 * ((BU.nouter + 1) & ~1) + 31) >> 5;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"((int)(uint32_t)(t.off & 0xffffffffll)), "r"((int)(t.off >> 32)), "r"(t.bytes), "r"(t.blk) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 16u), "r"(t.a), "r"(t.b), "r"(t.q0), "r"(t.q1) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 32u), "r"(t.q2), "r"(t.q3), "r"(BU.m0), "r"(BU.d0p) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 48u), "r"(BU.nouter), "r"(BU.C4), "r"(BU.tab), "r"(nwf) : "memory");
+    };
     if (tid == 0) {
         fmbar_init(bfull, 1); fmbar_init(bfull + 8, 1);
         fmbar_init(bempty, NW); fmbar_init(bempty + 8, NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid == NC && myn > 0) ring_put(0, A.tiles[blockIdx.x]);
     __syncthreads();
-    const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid >= NC) {
         if (tid == NC) {
             // ne[s]: tiles that have occupied the memory of slot s so far (= phases its empty barrier must have completed);
             // a two-slot tile occupies both
             int ne[2] = {0, 0}, pos = 0;
+            FibTile t = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
             for (int i = 0; i < myn; i++) {
-                const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
+                FibTile tn = t;
+                if (i + 1 < myn) tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
                 const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
                 if (ne[s] > 0) fmbar_wait_backoff(bempty + 8 * s, (uint32_t)(ne[s] - 1) & 1u);
                 if (two && ne[1] > 0) fmbar_wait_backoff(bempty + 8, (uint32_t)(ne[1] - 1) & 1u);
-                fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
+                fmbar_expect_tx_only(bfull + 8 * s, (uint32_t)t.bytes);
                 const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
                 const char *src = reinterpret_cast<const char *>(A.x + t.off);
                 for (int ofs = 0; ofs < t.bytes; ofs += 32768) {
@@ -308,9 +342,14 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                     for (int ofs = 0; ofs < t.bytes; ofs += 32768)
                         fbulk_prefetch_l2(py + ofs, (uint32_t)(t.bytes - ofs < 32768 ? t.bytes - ofs : 32768));
                 }
+                // every consumer has finished tile i-2 (or later) here: ring entry (i+1) & 3 = (i-3) & 3 is free.  The entry is
+                // written while the copies fly and published by the (release) arrive that lets full(i) complete.
+                if (i + 1 < myn) ring_put(i + 1, tn);
+                fmbar_arrive(bfull + 8 * s);
                 ne[s]++;
                 if (two) ne[1]++;
                 else pos ^= 1;
+                t = tn;
             }
         }
         return;
@@ -319,50 +358,57 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     double dsum = 0.0;
     int nfill[2] = {0, 0}, pos = 0, cur_blk = -1;
     bool stab = false;
-    // block data, refreshed when the block changes (tiles are sorted by size, then block: long runs)
-    int b_m0 = 0, b_d0p = 0, b_nouter = 0, b_C4 = 0, b_tab = 0, nwf = 1;
     for (int i = 0; i < myn; i++) {
-        const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
-        const bool two = t.bytes > A.slot;
+        const uint32_t re = ring0 + (uint32_t)(i & 3) * (uint32_t)sizeof(UpRing);
+        const bool two = ring_ld(re + UPR(bytes)) > A.slot;
         const int s = two ? 0 : pos;
-        if (t.blk != cur_blk) {
-            const FibBlockDev BU = A.blk_f[t.blk];
-            stab = load_stab<NC, 1>(A, BU, stab0, tid);
-            cur_blk = t.blk;
-            b_m0 = BU.m0; b_d0p = BU.d0p; b_nouter = BU.nouter; b_C4 = BU.C4; b_tab = BU.tab;
-            nwf = (4 * ((BU.nouter + 1) & ~1) + 31) >> 5;
+        {
+            const int blk = ring_ld(re + UPR(blk));
+            if (blk != cur_blk) {
+                const FibBlockDev BU = A.blk_f[blk];
+                stab = load_stab<NC, 1>(A, BU, stab0, tid);
+                cur_blk = blk;
+            }
         }
         // work units of a tile: [band g][phase][32 fibers]; lanes = 4 rows x 8 outer indices, a quarter-warp = 4 rows x 2
         // neighbouring outer indices (conflict-free LDS.128).  A thread keeps its row r4 = lane & 3 in every unit, so the
-        // per-row terms are loaded once per band -- for band 0 before the wait for the image.
-        const int nwu = 2 * nwf * t.b;
-        const uint32_t band_bytes = (uint32_t)b_C4 * 128u;
+        // per-row terms change with the band only: they are fetched one unit ahead (for band 0 before the wait for the image).
         auto rowterms = [&](int g, double &dg, uint32_t &impd) -> bool {
-            const int rp = (t.a + g) * 4 + r4;
-            const int od = rp / t.q0, kd = rp - od * t.q0;
-            if (od >= t.q1 || kd >= t.q2) return false;
-            const int id = t.q3 + od * t.q2 + kd;
+            const int q0 = ring_ld(re + UPR(q0)), q2 = ring_ld(re + UPR(q2));
+            const int rp = (ring_ld(re + UPR(a)) + g) * 4 + r4;
+            const int od = rp / q0, kd = rp - od * q0;
+            if (od >= ring_ld(re + UPR(q1)) || kd >= q2) return false;
+            const int id = ring_ld(re + UPR(q3)) + od * q2 + kd;
             dg = __ldg(A.e_dw + id);
             impd = __ldg(A.cfg_dw + id) & A.impmask;
             return true;
         };
+        const int nb = (A.dbg & 1) ? 0 : ring_ld(re + UPR(b));
+        const int nwf2 = 2 * ring_ld(re + UPR(nwf));
+        int g = 0, rem = warp;
+        while (rem >= nwf2) { rem -= nwf2; g++; }
         double dgb = 0.0;
         uint32_t impd = 0;
-        int g_cur = 0;
-        bool rowok = rowterms(0, dgb, impd);
+        bool rowok = g < nb ? rowterms(g, dgb, impd) : false;
         fmbar_wait_warp(bfull + 8 * s, (uint32_t)nfill[s] & 1u);
-        for (int wu = warp; wu < ((A.dbg & 1) ? 0 : nwu); wu += NW) {
-            int g = 0, rem = wu;
-            if (t.b > 1) { g = wu / (2 * nwf); rem = wu - g * 2 * nwf; }
-            if (g != g_cur) { rowok = rowterms(g, dgb, impd); g_cur = g; }
+        const uint32_t img0 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)r4 * 32u;
+        while (g < nb) {
+            // the next unit of this warp; its row terms are requested now if it lies in another band
+            int gn = g, remn = rem + NW;
+            while (remn >= nwf2) { remn -= nwf2; gn++; }
+            double dgn = dgb;
+            uint32_t impn = impd;
+            bool okn = rowok;
+            if (gn != g && gn < nb) okn = rowterms(gn, dgn, impn);
+            const int nwf = nwf2 >> 1;
             const int part = rem >= nwf ? 1 : 0;
             const int fb = (rem - part * nwf) * 32 + lane;
             const int o = 2 * (fb >> 3) + ((fb >> 2) & 1);
-            const bool active = rowok && o < b_nouter;
+            const bool active = rowok && o < ring_ld(re + UPR(nouter));
             FiberMeta F;
             F.stab = stab ? stab0 + (uint32_t)(active ? o : 0) * (uint32_t)kSOuterBytes : 0u;
-            F.ent = A.outer + b_tab + (active ? o : 0);
-            F.o = o; F.stride = b_d0p;
+            F.ent = A.outer + ring_ld(re + UPR(tab)) + (active ? o : 0);
+            F.o = o; F.stride = ring_ld(re + UPR(d0p));
             double eo; int impbits, nslot, neg;
             F.head(eo, impbits, nslot, neg);
             if (!active) nslot = 0;
@@ -370,21 +416,25 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             if (active) {
                 const int ib = impbits | part;
                 const double xt = stab ? flds64(stab0 + (uint32_t)kStabXtab + 8u * (impd * (1u << A.norb) + (uint32_t)ib)) : __ldg(A.xtab + impd * 32u + (uint32_t)ib);
-                const uint32_t img4 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * band_bytes + (uint32_t)r4 * 32u;
-                double *yband4 = A.y + t.off + (int64_t)g * b_C4 * 16 + r4 * 4;
+                const int C4 = ring_ld(re + UPR(C4));
+                const uint32_t img4 = img0 + (uint32_t)g * (uint32_t)C4 * 128u;
+                const int64_t toff = (int64_t)(((uint64_t)(uint32_t)ring_ld(re + UPR(off_hi)) << 32) | (uint64_t)(uint32_t)ring_ld(re + UPR(off_lo)));
+                double *yband4 = A.y + toff + (int64_t)g * C4 * 16 + r4 * 4;
+                const int m0 = ring_ld(re + UPR(m0));
                 fib::static_for<NL - 1>([&](auto mm) {
                     constexpr int M0 = decltype(mm)::value + 1;
-                    if (b_m0 == M0) {
+                    if (m0 == M0) {
                         fib::static_for<FibHS<NL>::n>([&](auto hh) {
                             constexpr int H = fib_hs<NL>(decltype(hh)::value), HP = decltype(hh)::value == 0 ? 0 : fib_hs<NL>(decltype(hh)::value - 1);
                             if (wmax <= H && (decltype(hh)::value == 0 || wmax > HP)) {
-                                if (part == 0) fiber_up<NL, M0, H, 0>(A, F, nslot, eo, impbits, neg, img4, o, b_d0p, dgb, xt, yband4, dsum);
-                                else fiber_up<NL, M0, H, 1>(A, F, nslot, eo, impbits, neg, img4, o, b_d0p, dgb, xt, yband4, dsum);
+                                if (part == 0) fiber_up<NL, M0, H, 0>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
+                                else fiber_up<NL, M0, H, 1>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
                             }
                         });
                     }
                 });
             }
+            g = gn; rem = remn; dgb = dgn; impd = impn; rowok = okn;
         }
         __syncwarp();
         if (lane == 0) { fmbar_arrive(bempty + 8 * s); if (two) fmbar_arrive(bempty + 8); }
