@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libedgpu.so")
+LIB_PATH = os.environ.get("EDGPU_LIB_PATH") or os.path.join(_HERE, "libedgpu.so")   # override: kernel-variant experiments
 _lib = None
 
 dp = C.POINTER(C.c_double)

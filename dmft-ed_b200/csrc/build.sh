@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall"
-SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu fib_nl3.cu fib_nl4.cu fib_nl5.cu fib_nl6.cu fib_nl7.cu fib_nl8.cu comm.cu eigs.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
+SRCS="api.cu tables.cu hxv_generic.cu hxv_star.cu hxv_fiber.cu fib_nl8.cu fib_nl8h.cu fib_nl7.cu fib_nl7h.cu fib_nl6.cu fib_nl6h.cu fib_nl5.cu fib_nl5h.cu fib_nl4.cu fib_nl4h.cu fib_nl3.cu fib_nl3h.cu comm.cu eigs.cu lanczos.cu ops.cu csr.cu host/ed_main.cpp host/ed_capi.cpp"
 mkdir -p ../build
 OBJS=""
 PIDS=""

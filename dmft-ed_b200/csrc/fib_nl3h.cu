@@ -1,0 +1,3 @@
+// fib_nl3h.cu -- fiber kernels for stars of 3 levels (Nbath = 2), half tiles; see hxv_fiber.cu / fiber_kernels.cuh
+#include "fiber_kernels.cuh"
+int fib_launch_nl3h(int pass, cudaStream_t st, const FibArgs &A, int grid) { return fib_launch<3, true>(pass, st, A, grid); }

@@ -1,0 +1,3 @@
+// fib_nl5h.cu -- fiber kernels for stars of 5 levels (Nbath = 4), half tiles; see hxv_fiber.cu / fiber_kernels.cuh
+#include "fiber_kernels.cuh"
+int fib_launch_nl5h(int pass, cudaStream_t st, const FibArgs &A, int grid) { return fib_launch<5, true>(pass, st, A, grid); }

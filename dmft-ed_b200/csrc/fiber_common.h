@@ -92,6 +92,7 @@ struct FibBlockDev {
     int fiber;                  // fiber kernels apply (else the generic pair kernels)
     int BR, nbox;               // down pass: bands per tensor box, boxes per strip
     int hsmax;                  // largest slot count of a fiber of the block
+    int hbox, hnbox;            // up pass, half bands (2 rows): micro-tile columns per tensor box, boxes per half band
 };
 
 struct __align__(16) OuterEnt {  // one value of the outer index o (stars 1..) of a block; 128 bytes
@@ -135,7 +136,7 @@ struct FibTile {                // pass 1: bands [a, a+b) of the pair ; pass 2: 
     int pair, blk, a, b;
     int bytes;
     int q0, q1, q2, q3;         // pass 1: d0r, nouter, D0, off of the DOWN block (rows of the pair) ; pass 2: q0 = C4 of the up block
-    int pad;
+    int half;                   // 0: full band / strip (4 rows / columns); 1, 2: its first / second half (half-tile kernels)
 };
 static_assert(sizeof(FibTile) == 48, "FibTile must be 48 bytes");
 
@@ -149,6 +150,10 @@ struct PairLayout {
     PairDev *d_pairs = nullptr;
     FibTile *d_t1 = nullptr, *d_t2 = nullptr;
     int n1 = 0, n2 = 0;
+    // half tiles (2 rows of a band / 2 columns of a strip): blocks whose full image does not fit ONE pipeline slot -- halved, the
+    // image double-buffers (4900 configurations of Ns=16) or fits the two slots at all (8000 configurations of Ns=18)
+    FibTile *d_t1h = nullptr, *d_t2h = nullptr;
+    int n1h = 0, n2h = 0;
     int *d_g1 = nullptr, *d_g2 = nullptr;      // pair ids for the generic up / down kernels
     // tables of the memory-order pair kernels: inverse position maps (padded position -> internal index, -1 = pad) per
     // block, concatenated (start of block b at *_start[b]), and hop tables whose targets are POSITIONS inside the block
@@ -159,10 +164,12 @@ struct PairLayout {
     int nl = 0;
     int slot = kSlot;                                      // pipeline slot size the tile schedules were built for
     int skip1 = 0, skip2 = 0;                              // test hooks: leave a pass to the thread-per-element kernels
-    std::map<const double *, CUtensorMap *> tmaps;         // per source pointer: one 3-D map per pair (device array)
+    // per source pointer, a device array of 3 maps per pair: [p] strips (3-D, box 16 x 1 x BR), [np + p] half strips (4-D,
+    // box 2 x 4 x 1 x BR), [2 np + p] half bands (3-D, box 8 x hbox x 1)
+    std::map<const double *, CUtensorMap *> tmaps;
     ~PairLayout()
     {
-        cudaFree(d_rowinfo); cudaFree(d_colinfo); cudaFree(d_pbase); cudaFree(d_c4); cudaFree(d_pairs); cudaFree(d_t1); cudaFree(d_t2);
+        cudaFree(d_rowinfo); cudaFree(d_colinfo); cudaFree(d_pbase); cudaFree(d_c4); cudaFree(d_pairs); cudaFree(d_t1); cudaFree(d_t2); cudaFree(d_t1h); cudaFree(d_t2h);
         cudaFree(d_g1); cudaFree(d_g2);
         cudaFree(d_idx_of_cp); cudaFree(d_idx_of_rp); cudaFree(d_cp_start); cudaFree(d_rp_start); cudaFree(d_poshop_c); cudaFree(d_poshop_r);
         for (auto &kv : tmaps) cudaFree(kv.second);
@@ -187,7 +194,7 @@ struct FibArgs {
     const double *e_dw;                 // pass 1: per-row diagonal energy and configuration word of the down spin
     const uint32_t *cfg_dw;
     const double *xtab;
-    const CUtensorMap *tmaps;           // pass 2: one 3-D tensor map per pair over x
-    const CUtensorMap *tmaps_y;         // pass 2: the same over y (L2 prefetch of the read-modify-write operand)
+    const CUtensorMap *tmaps;           // one tensor map per pair over x, of the kind the kernel loads with (see PairLayout::tmaps)
+    const CUtensorMap *tmaps_y;         // half-band up pass: the same over y (L2 prefetch of the read-modify-write operand)
     double *dot_out;                    // pass 2: per-CTA partial <x, y> (nullptr: not wanted)
 };

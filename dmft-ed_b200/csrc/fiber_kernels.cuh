@@ -55,6 +55,11 @@ __device__ __forceinline__ void ftma_load_3d(uint32_t dst, const CUtensorMap *tm
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void ftma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ double2 flds128(uint32_t addr)
 {
     double2 v;
@@ -93,6 +98,9 @@ __device__ __forceinline__ double fldg64(const double *p)
 // Long fibers (7-8 levels per star): 8 warps (7 consumers + producer) = 2 per scheduler -> 255 registers per thread and NO
 // spills (local memory has no L1 to live in next to 226 KB of shared memory: every spill reload is an L2 round trip, which
 // made the 12-warp / 168-register build latency-bound); short fibers: 16 warps, 128 registers.
+#ifndef EDGPU_FIB_YW
+#define EDGPU_FIB_YW 0            // y loads in flight per unit (0 = all of them up front)
+#endif
 #ifndef EDGPU_FIB_NC_BIG
 #define EDGPU_FIB_NC_BIG 224
 #endif
@@ -112,11 +120,12 @@ template <int NL> __device__ __forceinline__ constexpr int fib_hs(int i)
 
 // ------------------------------------------------------------------------------------------------------------
 // Shared-memory copy of the outer table of the block a CTA is working on (consumers only; named barrier 1).
-// PASS 1: offsets in the micro-tiled band image; PASS 2: row offsets in the strip image.  Blocks whose table does not
-// fit (more than 70 outer indices or more than 7 slots: only Norb = 3) use the global table (slower set-up).
+// PASS 1: offsets in the micro-tiled band image (mt = bytes per micro-tile of the image: 128, half bands 64); PASS 2: row
+// offsets in the strip image (mt = bytes per row: 32, half strips 16).  Blocks whose table does not fit (more than 70 outer
+// indices or more than 7 slots: only Norb = 3) use the global table (slower set-up).
 // ------------------------------------------------------------------------------------------------------------
 template <int NC, int PASS>
-__device__ __forceinline__ bool load_stab(const FibArgs &A, const FibBlockDev &B, uint32_t stab0, int tid)
+__device__ __forceinline__ bool load_stab(const FibArgs &A, const FibBlockDev &B, uint32_t stab0, int tid, int mt)
 {
     asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");                  // nobody still reads the previous table
     const bool fits = B.hsmax <= kStabHS && B.nouter * kSOuterBytes <= kStabXtab;
@@ -134,10 +143,10 @@ __device__ __forceinline__ bool load_stab(const FibArgs &A, const FibBlockDev &B
                 int relE, relO;
                 if (PASS == 1) {
                     const int c = o2 * B.d0p;
-                    const int T = (c >> 2) * 128;
+                    const int T = (c >> 2) * mt;
                     relE = (c & 3) ? T + 16 : T;
-                    relO = (c & 3) ? T + 128 : T + 16;
-                } else { relE = o2 * B.d0r * 32; relO = 0; }
+                    relO = (c & 3) ? T + mt : T + 16;
+                } else { relE = o2 * B.d0r * mt; relO = 0; }
                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 16u + 16u * q), "r"(relE), "r"(relO) : "memory");
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(d + 24u + 16u * q), "d"(on ? __ldg(A.amps + e->code[q]) : 0.0) : "memory");
             }
@@ -156,7 +165,7 @@ __device__ __forceinline__ bool load_stab(const FibArgs &A, const FibBlockDev &B
 struct FiberMeta {
     uint32_t stab;                    // shared address of the entry, 0 = use `ent`
     const OuterEnt *ent;
-    int o, stride;                    // global path: outer index and d0p (pass 1) / d0r (pass 2)
+    int o, stride, mt;                // global path: outer index, d0p (pass 1) / d0r (pass 2), image stride (see load_stab)
     __device__ __forceinline__ void head(double &eo, int &impbits, int &nslot, int &neg) const
     {
         if (stab) {
@@ -175,10 +184,10 @@ struct FiberMeta {
         } else {
             const int o2 = o + (on ? ent->delta[s2] : 0);
             if (PASS == 1) {
-                const int c = o2 * stride, T = (c >> 2) * 128;
+                const int c = o2 * stride, T = (c >> 2) * mt;
                 relE = (c & 3) ? T + 16 : T;
-                relO = (c & 3) ? T + 128 : T + 16;
-            } else { relE = o2 * stride * 32; relO = 0; }
+                relO = (c & 3) ? T + mt : T + 16;
+            } else { relE = o2 * stride * mt; relO = 0; }
             amp = on ? __ldg(amps + ent->code[s2]) : 0.0;
         }
     }
@@ -187,7 +196,8 @@ struct FiberMeta {
 // ---- up pass (runs SECOND: y += (diag + H_up) x, fused <x,y>): one PHASE of one fiber (row r4 of the band, outer index o) ----
 // PART 0 holds the imp=1 half of the fiber in registers and produces the imp=0 outputs, PART 1 the other way round (only half
 // of a <= 70-element fiber lives in registers at a time); the own element (diagonal term) is re-read with the gathers.
-template <int NL, int M0, int HS, int PART>
+// MT: bytes per micro-tile of the IMAGE (128: bands of 4 rows; 64: half bands of 2 rows); y is always in 128-byte micro-tiles.
+template <int NL, int M0, int HS, int PART, int MT>
 __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, int nslot, double eo, int impbits, int neg, uint32_t img4 /* image + r4*32 */,
                                          int o, int d0p, double dgbase, double xt, double *yband4 /* band + r4*4 */, double &dsum)
 {
@@ -197,15 +207,15 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
     if constexpr (NIN > 0 && OUT_HI > OUT_LO) {
         // element k of the fiber sits at column c = o*d0p + k; c0 = o*d0p is 0 or 2 (mod 4)
         const int c0 = o * d0p;
-        const uint32_t T = (uint32_t)(c0 >> 2) * 128u;
+        const uint32_t T = (uint32_t)(c0 >> 2) * (uint32_t)MT, Ty = (uint32_t)(c0 >> 2) * 16u;
         const bool q2 = (c0 & 3) != 0;
-        const uint32_t oE = q2 ? T + 16u : T, oO = q2 ? T + 128u : T + 16u;      // k == 0 / 2 (mod 4); plus (k/4)*128
+        const uint32_t oE = q2 ? T + 16u : T, oO = q2 ? T + (uint32_t)MT : T + 16u;      // k == 0 / 2 (mod 4); plus (k/4)*MT
         const uint32_t own = img4 + oE, ownO = img4 + oO;
-        double *yE = yband4 + (oE >> 3), *yO = yband4 + (oO >> 3);
+        double *yE = yband4 + (q2 ? Ty + 2u : Ty), *yO = yband4 + (q2 ? Ty + 16u : Ty + 2u);
         constexpr int P_LO = OUT_LO / 2, P_HI = (OUT_HI + 1) / 2, NPR = P_HI - P_LO;
         // y += ... : the pass-1 result (H_dw x) of the unit's pairs comes through a rolling window of W loads in flight
         // (the producer has pulled the y band into L2 together with the x image)
-        constexpr int W = NPR;
+        constexpr int W = (EDGPU_FIB_YW) > 0 && (EDGPU_FIB_YW) < NPR ? (EDGPU_FIB_YW) : NPR;
         double2 yw[W];
         auto yaddr = [&](auto kk) -> double * {
             constexpr int K = decltype(kk)::value;
@@ -218,7 +228,7 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         double in[NIN];
         fib::static_for<NIN / 2>([&](auto jj) {
             constexpr int K = IN_LO + 2 * decltype(jj)::value;
-            const double2 v = flds128(((K & 3) == 0 ? own : ownO) + (uint32_t)(K >> 2) * 128u);
+            const double2 v = flds128(((K & 3) == 0 ? own : ownO) + (uint32_t)(K >> 2) * (uint32_t)MT);
             in[K - IN_LO] = v.x; in[K - IN_LO + 1] = v.y;
         });
         uint32_t sE[HS], sO[HS];
@@ -235,7 +245,7 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         fib::static_for<NPR>([&](auto jj) {
             constexpr int J = decltype(jj)::value, K = 2 * (P_LO + J);
             constexpr bool do0 = K >= OUT_LO && K < OUT_HI, do1 = K + 1 >= OUT_LO && K + 1 < OUT_HI;
-            const uint32_t rel = (uint32_t)(K >> 2) * 128u;
+            const uint32_t rel = (uint32_t)(K >> 2) * (uint32_t)MT;
             const double2 xo = flds128(((K & 3) == 0 ? own : ownO) + rel);
             double g0 = 0.0, g1 = 0.0;
 #pragma unroll
@@ -275,7 +285,7 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
 struct UpRing {                 // 64 bytes
     int off_lo, off_hi, bytes, blk;
     int a, b, q0, q1;
-    int q2, q3, m0, d0p;
+    int q2, q3, m0, d0p;        // m0 | half << 8
     int nouter, C4, tab, nwf;
 };
 #define UPR(field) ((uint32_t)offsetof(UpRing, field))
@@ -286,10 +296,13 @@ __device__ __forceinline__ int ring_ld(uint32_t addr)
     return v;
 }
 
-template <int NL>
+// HALF: the tiles are half bands (rows 0-1 or 2-3 of a band): lanes = 2 rows x 16 outer indices, image in 64-byte half micro-tiles
+// fetched through a tensor map (64-byte runs); a quarter-warp = 2 rows x 4 consecutive outer indices is conflict free for
+// d0p == 2 (mod 4) as well.
+template <int NL, bool HALF>
 __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant__ FibArgs A)
 {
-    constexpr int NC = FibCfg<NL>::NC, NW = NC / 32;
+    constexpr int NC = FibCfg<NL>::NC, NW = NC / 32, MT = HALF ? 64 : 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[4];
     __shared__ double s_dot[NW];
@@ -300,13 +313,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
     const uint32_t bfull = (uint32_t)__cvta_generic_to_shared(s_bar), bempty = bfull + 16u;
     const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring);
     const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    auto ring_put = [&](int i, const FibTile &t) {
-        const FibBlockDev BU = A.blk_f[t.blk];
+    auto ring_put = [&](int i, const FibTile &t, const FibBlockDev &BU) {
         const uint32_t d = ring0 + (uint32_t)(i & 3) * (uint32_t)sizeof(UpRing);
-        const int nwf = (4 * ((BU.nouter + 1) & ~1) + 31) >> 5;
+        const int nwf = HALF ? (BU.nouter + 15) >> 4 : (4 * ((BU.nouter + 1) & ~1) + 31) >> 5;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"((int)(uint32_t)(t.off & 0xffffffffll)), "r"((int)(t.off >> 32)), "r"(t.bytes), "r"(t.blk) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 16u), "r"(t.a), "r"(t.b), "r"(t.q0), "r"(t.q1) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 32u), "r"(t.q2), "r"(t.q3), "r"(BU.m0), "r"(BU.d0p) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 32u), "r"(t.q2), "r"(t.q3), "r"(BU.m0 | (t.half << 8)), "r"(BU.d0p) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 48u), "r"(BU.nouter), "r"(BU.C4), "r"(BU.tab), "r"(nwf) : "memory");
     };
     if (tid == 0) {
@@ -314,14 +326,18 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
         fmbar_init(bempty, NW); fmbar_init(bempty + 8, NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == NC && myn > 0) ring_put(0, A.tiles[blockIdx.x]);
+    if (tid == NC && myn > 0) {
+        const FibTile t0 = A.tiles[blockIdx.x];
+        ring_put(0, t0, A.blk_f[t0.blk]);
+    }
     __syncthreads();
     if (tid >= NC) {
         if (tid == NC) {
             // ne[s]: tiles that have occupied the memory of slot s so far (= phases its empty barrier must have completed);
             // a two-slot tile occupies both
-            int ne[2] = {0, 0}, pos = 0;
+            int ne[2] = {0, 0}, nfb[2] = {0, 0}, pos = 0;        // nfb[s]: completed uses of full barrier s
             FibTile t = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
+            FibBlockDev bt = A.blk_f[t.blk];
             for (int i = 0; i < myn; i++) {
                 FibTile tn = t;
                 if (i + 1 < myn) tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
@@ -331,32 +347,49 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                 if (two && ne[1] > 0) fmbar_wait_backoff(bempty + 8, (uint32_t)(ne[1] - 1) & 1u);
                 fmbar_expect_tx_only(bfull + 8 * s, (uint32_t)t.bytes);
                 const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
-                const char *src = reinterpret_cast<const char *>(A.x + t.off);
-                for (int ofs = 0; ofs < t.bytes; ofs += 32768) {
-                    const int n = t.bytes - ofs < 32768 ? t.bytes - ofs : 32768;
-                    fbulk_g2s(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s);
-                }
                 // the read-modify-write operand of THIS tile (the same band of y) goes to L2 while the x image lands
-                {
+                if (HALF) {
+                    const int c0 = 8 * (t.half - 1);
+                    for (int k = 0; k < bt.hnbox; k++)
+                        ftma_load_3d(dst + (uint32_t)k * (uint32_t)bt.hbox * 64u, A.tmaps + t.pair, c0, k * bt.hbox, t.a, bfull + 8 * s);
+                    for (int k = 0; k < bt.hnbox; k++) ftma_prefetch_3d(A.tmaps_y + t.pair, c0, k * bt.hbox, t.a);
+                } else {
+                    const char *src = reinterpret_cast<const char *>(A.x + t.off);
+                    for (int ofs = 0; ofs < t.bytes; ofs += 32768) {
+                        const int n = t.bytes - ofs < 32768 ? t.bytes - ofs : 32768;
+                        fbulk_g2s(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s);
+                    }
                     const char *py = reinterpret_cast<const char *>(A.y + t.off);
                     for (int ofs = 0; ofs < t.bytes; ofs += 32768)
                         fbulk_prefetch_l2(py + ofs, (uint32_t)(t.bytes - ofs < 32768 ? t.bytes - ofs : 32768));
                 }
                 // every consumer has finished tile i-2 (or later) here: ring entry (i+1) & 3 = (i-3) & 3 is free.  The entry is
                 // written while the copies fly and published by the (release) arrive that lets full(i) complete.
-                if (i + 1 < myn) ring_put(i + 1, tn);
+                FibBlockDev bn = bt;
+                if (i + 1 < myn) {
+                    if (tn.blk != t.blk) bn = A.blk_f[tn.blk];
+                    ring_put(i + 1, tn, bn);
+                }
                 fmbar_arrive(bfull + 8 * s);
-                ne[s]++;
+                // a two-slot tile cannot be loaded while its predecessor is computed on: at least pull it into L2 meanwhile
+                // (once the own image has landed, so that the two do not compete), the exposed fill then runs at L2 speed
+                if (!HALF && i + 1 < myn && tn.bytes > A.slot && !(A.dbg & 2)) {
+                    fmbar_wait_backoff(bfull + 8 * s, (uint32_t)nfb[s] & 1u);
+                    const char *px = reinterpret_cast<const char *>(A.x + tn.off);
+                    for (int ofs = 0; ofs < tn.bytes; ofs += 32768)
+                        fbulk_prefetch_l2(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768));
+                }
+                ne[s]++; nfb[s]++;
                 if (two) ne[1]++;
                 else pos ^= 1;
-                t = tn;
+                t = tn; bt = bn;
             }
         }
         return;
     }
-    const int warp = tid >> 5, lane = tid & 31, r4 = lane & 3;
+    const int warp = tid >> 5, lane = tid & 31, rl = HALF ? (lane & 1) : (lane & 3);       // row of the image
     double dsum = 0.0;
-    int nfill[2] = {0, 0}, pos = 0, cur_blk = -1;
+    int nfill0 = 0, nfill1 = 0, pos = 0, cur_blk = -1;
     bool stab = false;
     for (int i = 0; i < myn; i++) {
         const uint32_t re = ring0 + (uint32_t)(i & 3) * (uint32_t)sizeof(UpRing);
@@ -366,10 +399,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             const int blk = ring_ld(re + UPR(blk));
             if (blk != cur_blk) {
                 const FibBlockDev BU = A.blk_f[blk];
-                stab = load_stab<NC, 1>(A, BU, stab0, tid);
+                stab = load_stab<NC, 1>(A, BU, stab0, tid, MT);
                 cur_blk = blk;
             }
         }
+        const int m0h = ring_ld(re + UPR(m0));
+        const int r4 = HALF ? 2 * ((m0h >> 8) - 1) + rl : rl;                                // row of the band
         // work units of a tile: [band g][phase][32 fibers]; lanes = 4 rows x 8 outer indices, a quarter-warp = 4 rows x 2
         // neighbouring outer indices (conflict-free LDS.128).  A thread keeps its row r4 = lane & 3 in every unit, so the
         // per-row terms change with the band only: they are fetched one unit ahead (for band 0 before the wait for the image).
@@ -390,8 +425,8 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
         double dgb = 0.0;
         uint32_t impd = 0;
         bool rowok = g < nb ? rowterms(g, dgb, impd) : false;
-        fmbar_wait_warp(bfull + 8 * s, (uint32_t)nfill[s] & 1u);
-        const uint32_t img0 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)r4 * 32u;
+        fmbar_wait_warp(bfull + 8 * s, (uint32_t)(s ? nfill1 : nfill0) & 1u);
+        const uint32_t img0 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)rl * 32u;
         while (g < nb) {
             // the next unit of this warp; its row terms are requested now if it lies in another band
             int gn = g, remn = rem + NW;
@@ -403,12 +438,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             const int nwf = nwf2 >> 1;
             const int part = rem >= nwf ? 1 : 0;
             const int fb = (rem - part * nwf) * 32 + lane;
-            const int o = 2 * (fb >> 3) + ((fb >> 2) & 1);
+            const int o = HALF ? (fb >> 1) : 2 * (fb >> 3) + ((fb >> 2) & 1);
             const bool active = rowok && o < ring_ld(re + UPR(nouter));
             FiberMeta F;
             F.stab = stab ? stab0 + (uint32_t)(active ? o : 0) * (uint32_t)kSOuterBytes : 0u;
             F.ent = A.outer + ring_ld(re + UPR(tab)) + (active ? o : 0);
-            F.o = o; F.stride = ring_ld(re + UPR(d0p));
+            F.o = o; F.stride = ring_ld(re + UPR(d0p)); F.mt = MT;
             double eo; int impbits, nslot, neg;
             F.head(eo, impbits, nslot, neg);
             if (!active) nslot = 0;
@@ -417,18 +452,18 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                 const int ib = impbits | part;
                 const double xt = stab ? flds64(stab0 + (uint32_t)kStabXtab + 8u * (impd * (1u << A.norb) + (uint32_t)ib)) : __ldg(A.xtab + impd * 32u + (uint32_t)ib);
                 const int C4 = ring_ld(re + UPR(C4));
-                const uint32_t img4 = img0 + (uint32_t)g * (uint32_t)C4 * 128u;
+                const uint32_t img4 = img0 + (uint32_t)g * (uint32_t)C4 * (uint32_t)MT;
                 const int64_t toff = (int64_t)(((uint64_t)(uint32_t)ring_ld(re + UPR(off_hi)) << 32) | (uint64_t)(uint32_t)ring_ld(re + UPR(off_lo)));
                 double *yband4 = A.y + toff + (int64_t)g * C4 * 16 + r4 * 4;
-                const int m0 = ring_ld(re + UPR(m0));
+                const int m0 = m0h & 255;
                 fib::static_for<NL - 1>([&](auto mm) {
                     constexpr int M0 = decltype(mm)::value + 1;
                     if (m0 == M0) {
                         fib::static_for<FibHS<NL>::n>([&](auto hh) {
                             constexpr int H = fib_hs<NL>(decltype(hh)::value), HP = decltype(hh)::value == 0 ? 0 : fib_hs<NL>(decltype(hh)::value - 1);
                             if (wmax <= H && (decltype(hh)::value == 0 || wmax > HP)) {
-                                if (part == 0) fiber_up<NL, M0, H, 0>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
-                                else fiber_up<NL, M0, H, 1>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
+                                if (part == 0) fiber_up<NL, M0, H, 0, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
+                                else fiber_up<NL, M0, H, 1, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
                             }
                         });
                     }
@@ -438,7 +473,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
         }
         __syncwarp();
         if (lane == 0) { fmbar_arrive(bempty + 8 * s); if (two) fmbar_arrive(bempty + 8); }
-        nfill[s]++;
+        if (s) nfill1++; else nfill0++;
         if (!two) pos ^= 1;
     }
     if (A.dot_out) {
@@ -456,7 +491,8 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
 
 // ---- down pass (runs FIRST: y = H_dw x, write-only): one column (c4 of the strip) of the fiber (outer index o) of the down
 // spin; PART 0: outputs with imp=0 ----
-template <int NL, int M0, int HS, int PART>
+// RS: bytes per row of the image (32: strips of 4 columns; 16: half strips of 2 columns)
+template <int NL, int M0, int HS, int PART, int RS>
 __device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, int nslot, int neg, uint32_t img8 /* image + c4*8 */, int o,
                                          int d0r, double *ystrip4 /* strip + c4 */, int64_t bstride)
 {
@@ -468,9 +504,9 @@ __device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, i
         double *Q[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) Q[j] = ystrip4 + (int64_t)((r0 + j) >> 2) * bstride + ((r0 + j) & 3) * 4;
-        const uint32_t base = img8 + (uint32_t)r0 * 32u;
+        const uint32_t base = img8 + (uint32_t)r0 * (uint32_t)RS;
         double in[NIN];
-        fib::static_for<NIN>([&](auto jj) { constexpr int J = decltype(jj)::value; in[J] = flds64(base + (uint32_t)(IN0 + J) * 32u); });
+        fib::static_for<NIN>([&](auto jj) { constexpr int J = decltype(jj)::value; in[J] = flds64(base + (uint32_t)(IN0 + J) * (uint32_t)RS); });
         uint32_t sb[HS];
         double amp[HS];
 #pragma unroll
@@ -484,17 +520,19 @@ __device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, i
             constexpr int K = OUT0 + decltype(kk)::value;
             double g = 0.0;
 #pragma unroll
-            for (int s = 0; s < HS; s++) g = fma(amp[s], flds64(sb[s] + (uint32_t)K * 32u), g);
+            for (int s = 0; s < HS; s++) g = fma(amp[s], flds64(sb[s] + (uint32_t)K * (uint32_t)RS), g);
             const double inr = fib::out<NB, M0, K, IN0>(in, A.cst.v0);
             Q[K & 3][(int64_t)(K >> 2) * bstride] = fma(sig, inr, PART == 0 ? g : -g);
         });
     }
 }
 
-template <int NL>
+// HALF: the tiles are half strips (columns 0-1 or 2-3 of a strip): lanes = 2 columns x 16 outer indices, image rows of 16 bytes
+// fetched through a 4-D tensor map (box 2 x 4 x 1 x BR: 16-byte runs)
+template <int NL, bool HALF>
 __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_constant__ FibArgs A)
 {
-    constexpr int NC = FibCfgDw<NL>::NC, NW = NC / 32;
+    constexpr int NC = FibCfgDw<NL>::NC, NW = NC / 32, RS = HALF ? 16 : 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[4];
     const int tid = threadIdx.x;
@@ -510,13 +548,15 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
     const int myn = (int)blockIdx.x < A.ntiles ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid >= NC) {
         if (tid == NC) {
-            int ne[2] = {0, 0}, pos = 0;
+            int ne[2] = {0, 0}, nfb[2] = {0, 0}, pos = 0;        // nfb[s]: completed uses of full barrier s
             auto boxes = [&](const FibTile &t, const FibBlockDev &BD, auto &&fn) {
                 for (int g = 0; g < t.b; g++)
                     for (int b = 0; b < BD.nbox; b++) fn(g, b);
             };
+            FibTile t = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
             for (int i = 0; i < myn; i++) {
-                const FibTile t = A.tiles[blockIdx.x + (size_t)i * gridDim.x];
+                FibTile tn = t;
+                if (i + 1 < myn) tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
                 const FibBlockDev BD = A.blk_f[t.blk];
                 const bool two = t.bytes > A.slot;
                 const int s = two ? 0 : pos;
@@ -524,20 +564,30 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
                 if (two && ne[1] > 0) fmbar_wait_backoff(bempty + 8, (uint32_t)(ne[1] - 1) & 1u);
                 fmbar_expect_tx(bfull + 8 * s, (uint32_t)t.bytes);
                 const uint32_t dst = slot0 + (uint32_t)s * (uint32_t)A.slot;
-                const uint32_t sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * 128u;
+                const uint32_t sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * (uint32_t)(RS * 4);
                 boxes(t, BD, [&](int g, int b) {
-                    ftma_load_3d(dst + (uint32_t)g * sbytes + (uint32_t)b * (uint32_t)BD.BR * 128u, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s);
+                    const uint32_t d = dst + (uint32_t)g * sbytes + (uint32_t)b * (uint32_t)BD.BR * (uint32_t)(RS * 4);
+                    if (HALF) ftma_load_4d(d, A.tmaps + t.pair, 2 * (t.half - 1), 0, t.a + g, b * BD.BR, bfull + 8 * s);
+                    else ftma_load_3d(d, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s);
                 });
-                ne[s]++;
+                // see the up pass: the next two-slot strip goes to L2 while this one is computed on
+                if (!HALF && i + 1 < myn && tn.bytes > A.slot && !(A.dbg & 2)) {
+                    fmbar_wait_backoff(bfull + 8 * s, (uint32_t)nfb[s] & 1u);
+                    const FibBlockDev BN = tn.blk == t.blk ? BD : A.blk_f[tn.blk];
+                    for (int g = 0; g < tn.b; g++)
+                        for (int b = 0; b < BN.nbox; b++) ftma_prefetch_3d(A.tmaps + tn.pair, 0, tn.a + g, b * BN.BR);
+                }
+                ne[s]++; nfb[s]++;
                 if (two) ne[1]++;
                 else pos ^= 1;
+                t = tn;
             }
         }
         return;
     }
-    int nfill[2] = {0, 0}, pos = 0, cur_blk = -1;
+    int nfill0 = 0, nfill1 = 0, pos = 0, cur_blk = -1;
     bool stab = false;
-    const int warp = tid >> 5, lane = tid & 31, c4 = lane & 3;
+    const int warp = tid >> 5, lane = tid & 31, cl = HALF ? (lane & 1) : (lane & 3);         // column of the image
     int b_m0 = 0, b_d0r = 0, b_nouter = 0, b_tab = 0, now = 1;
     uint32_t sbytes = 0;
     FibTile tnext = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
@@ -548,41 +598,42 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
         const int s = two ? 0 : pos;
         if (t.blk != cur_blk) {
             const FibBlockDev BD = A.blk_f[t.blk];
-            stab = load_stab<NC, 2>(A, BD, stab0, tid);
+            stab = load_stab<NC, 2>(A, BD, stab0, tid, RS);
             cur_blk = t.blk;
             b_m0 = BD.m0; b_d0r = BD.d0r; b_nouter = BD.nouter; b_tab = BD.tab;
-            now = (BD.nouter + 7) >> 3;
-            sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * 128u;
+            now = HALF ? (BD.nouter + 15) >> 4 : (BD.nouter + 7) >> 3;
+            sbytes = (uint32_t)BD.nbox * (uint32_t)BD.BR * (uint32_t)(RS * 4);
         }
-        fmbar_wait_warp(bfull + 8 * s, (uint32_t)nfill[s] & 1u);
+        fmbar_wait_warp(bfull + 8 * s, (uint32_t)(s ? nfill1 : nfill0) & 1u);
         const int64_t bstride = (int64_t)t.q0 * 16;
         // warp-fibers of a strip: [part][8 outer indices per warp]; lanes = (c4 = lane & 3, o = 8*ow + lane/4)
+        // (half strips: 16 outer indices per warp, lanes = (lane & 1, o = 16*ow + lane/2))
         const int nwf = 2 * now * t.b;
         for (int wf = warp; wf < ((A.dbg & 1) ? 0 : nwf); wf += NW) {
             int g = 0, rem = wf;
             if (t.b > 1) { g = wf / (2 * now); rem = wf - g * 2 * now; }
             const int part = rem >= now ? 1 : 0, ow = rem - part * now;
-            const int o = 8 * ow + (lane >> 2);
+            const int o = HALF ? 16 * ow + (lane >> 1) : 8 * ow + (lane >> 2);
             const bool active = o < b_nouter;
             FiberMeta F;
             F.stab = stab ? stab0 + (uint32_t)(active ? o : 0) * (uint32_t)kSOuterBytes : 0u;
             F.ent = A.outer + b_tab + (active ? o : 0);
-            F.o = o; F.stride = b_d0r;
+            F.o = o; F.stride = b_d0r; F.mt = RS;
             double eo; int impbits, nslot, neg;
             F.head(eo, impbits, nslot, neg);
             if (!active) nslot = 0;
             const int wmax = __reduce_max_sync(0xffffffffu, nslot);
             if (active) {
-                const uint32_t img8 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * sbytes + (uint32_t)c4 * 8u;
-                double *ystrip4 = A.y + t.off + (int64_t)(t.a + g) * 16 + c4;
+                const uint32_t img8 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)g * sbytes + (uint32_t)cl * 8u;
+                double *ystrip4 = A.y + t.off + (int64_t)(t.a + g) * 16 + (HALF ? 2 * (t.half - 1) : 0) + cl;
                 fib::static_for<NL - 1>([&](auto mm) {
                     constexpr int M0 = decltype(mm)::value + 1;
                     if (b_m0 == M0) {
                         fib::static_for<FibHS<NL>::n>([&](auto hh) {
                             constexpr int H = fib_hs<NL>(decltype(hh)::value), HP = decltype(hh)::value == 0 ? 0 : fib_hs<NL>(decltype(hh)::value - 1);
                             if (wmax <= H && (decltype(hh)::value == 0 || wmax > HP)) {
-                                if (part == 0) fiber_dw<NL, M0, H, 0>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
-                                else fiber_dw<NL, M0, H, 1>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
+                                if (part == 0) fiber_dw<NL, M0, H, 0, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
+                                else fiber_dw<NL, M0, H, 1, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
                             }
                         });
                     }
@@ -591,24 +642,24 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
         }
         __syncwarp();
         if (lane == 0) { fmbar_arrive(bempty + 8 * s); if (two) fmbar_arrive(bempty + 8); }
-        nfill[s]++;
+        if (s) nfill1++; else nfill0++;
         if (!two) pos ^= 1;
     }
 }
 
-// host entry of one translation unit: pass 1 or 2 of the fiber kernels for NL levels per star
-template <int NL>
+// host entry of one translation unit: pass 1 or 2 of the fiber kernels for NL levels per star, full or half tiles
+template <int NL, bool HALF>
 static int fib_launch(int pass, cudaStream_t st, const FibArgs &A, int grid)
 {
     static bool attr[2] = {false, false};
     const size_t smem = 2 * (size_t)kSlot + kStab;
     if (!attr[pass - 1]) {
-        cudaError_t e = pass == 1 ? cudaFuncSetAttribute((const void *)k_fib_up<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                  : cudaFuncSetAttribute((const void *)k_fib_dw<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pass == 1 ? cudaFuncSetAttribute((const void *)k_fib_up<NL, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute((const void *)k_fib_dw<NL, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr[pass - 1] = true;
     }
-    if (pass == 1) k_fib_up<NL><<<grid, FibCfg<NL>::NT, smem, st>>>(A);
-    else k_fib_dw<NL><<<grid, FibCfgDw<NL>::NT, smem, st>>>(A);
+    if (pass == 1) k_fib_up<NL, HALF><<<grid, FibCfg<NL>::NT, smem, st>>>(A);
+    else k_fib_dw<NL, HALF><<<grid, FibCfgDw<NL>::NT, smem, st>>>(A);
     return (int)cudaGetLastError();
 }

@@ -100,7 +100,9 @@ static int build_fib_spin(edgpu_ctx *ctx, SpinBasis *b)
         fb.R = fb.nouter * fb.d0r; fb.R4 = (fb.R + 3) / 4;
         fb.C = fb.nouter * fb.d0p; fb.C4 = (fb.C + 3) / 4;
         fb.nbox = (fb.R4 + 255) / 256;
-        fb.BR = (fb.R4 + fb.nbox - 1) / fb.nbox;
+        fb.BR = ((fb.R4 + fb.nbox - 1) / fb.nbox + 1) & ~1;       // even: a half-strip box (BR x 64 bytes) keeps the 128-byte alignment
+        fb.hnbox = (fb.C4 + 255) / 256;
+        fb.hbox = ((fb.C4 + fb.hnbox - 1) / fb.hnbox + 1) & ~1;   // even, for the same reason (hbox x 64 bytes per box)
         fb.tab = (int)outer.size();
         int hsmax = 0;
         // outer index o: mixed radix over stars 1.., star 1 fastest
@@ -140,8 +142,9 @@ static int build_fib_spin(edgpu_ctx *ctx, SpinBasis *b)
             hsmax = std::max(hsmax, ns);
             outer.push_back(e);
         }
-        // fiber kernels: star 0 must have hops (1 <= m0 <= nl-1), the images must fit, the block must be worth a tile
-        const int64_t band_bytes = (int64_t)fb.C4 * 128, strip_bytes = (int64_t)fb.nbox * fb.BR * 128;
+        // fiber kernels: star 0 must have hops (1 <= m0 <= nl-1), the images must fit (as half tiles at least), the block
+        // must be worth a tile
+        const int64_t band_bytes = (int64_t)fb.hnbox * fb.hbox * 64, strip_bytes = (int64_t)fb.nbox * fb.BR * 64;
         fb.fiber = (nl >= 3 && nl <= 8 && norb >= 2 && fb.m0 >= 1 && fb.m0 <= nl - 1 && band_bytes <= 2 * kSlot && strip_bytes <= 2 * kSlot &&
                     hsmax <= (nl >= 7 ? 7 : kHS)) ? 1 : 0;
         fb.hsmax = hsmax;
@@ -192,11 +195,12 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     const bool force_fiber = (ctx->par.reserved[0] & 16) != 0, force_generic = (ctx->par.reserved[0] & 4) != 0;
     const bool gen1 = force_generic || (ctx->par.reserved[0] & 1024) != 0, gen2 = force_generic || (ctx->par.reserved[0] & 2048) != 0;
     if (ctx->par.reserved[0] & 4096) {
-        // test hook: shrink the pipeline slot so that the largest image of this sector needs BOTH slots (the two-slot
-        // path that only the 4900-configuration blocks of Ns=16 take in production)
+        // test hook: shrink the pipeline slot so that the largest HALF image of this sector needs BOTH slots (the path that
+        // only the 8000-configuration blocks of Ns=18 take in production); the blocks below it run as two-slot full tiles
+        // (the 4900-configuration blocks of Ns=16) or as one-slot tiles
         int64_t big = 0;
-        for (const FibBlockDev &B : FU.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.C4 * 128);
-        for (const FibBlockDev &B : FD.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.nbox * B.BR * 128);
+        for (const FibBlockDev &B : FU.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.hnbox * B.hbox * 64);
+        for (const FibBlockDev &B : FD.blocks) if (B.fiber) big = std::max<int64_t>(big, (int64_t)B.nbox * B.BR * 64);
         if (big > 256) P->slot = (int)std::min<int64_t>(kSlot, ((big / 2 + 127) / 128) * 128);
     }
     const int slot = P->slot;
@@ -207,8 +211,8 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     for (int i = 0; i < nbd; i++)
         for (int j = 0; j < nbu; j++) {
             const FibBlockDev &BD = FD.blocks[i], &BU = FU.blocks[j];
-            const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock);
-            const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock);
+            const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock) && (int64_t)BU.hnbox * BU.hbox * 64 <= 2 * (int64_t)slot;
+            const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock) && (int64_t)BD.nbox * BD.BR * 64 <= 2 * (int64_t)slot;
             psize[(size_t)i * nbu + j] = (int64_t)BD.R4 * BU.C4 * 16;
             pcost[(size_t)i * nbu + j] = psize[(size_t)i * nbu + j] * ((fu ? 1 : 6) + (fd ? 1 : 6));
             order[(size_t)i * nbu + j] = i * nbu + j;
@@ -249,35 +253,45 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
         for (int e = 0; e < B.size; e++) colinfo[(size_t)B.off + e] = make_int2(j, (e / B.D0) * B.d0p + e % B.D0);
     }
     // tile schedules
-    std::vector<FibTile> t1, t2;
+    std::vector<FibTile> t1, t2, t1h, t2h;
     std::vector<int> g1, g2;
     for (int p = 0; p < (int)P->pairs.size(); p++) {
         const PairDev &pd = P->pairs[p];
         const FibBlockDev &BD = FD.blocks[pd.bi], &BU = FU.blocks[pd.bj];
-        const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock);
-        const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock);
+        const bool fu = !gen1 && BU.fiber && (force_fiber || BU.size >= kFibMinBlock) && (int64_t)BU.hnbox * BU.hbox * 64 <= 2 * (int64_t)slot;
+        const bool fd = !gen2 && BD.fiber && (force_fiber || BD.size >= kFibMinBlock) && (int64_t)BD.nbox * BD.BR * 64 <= 2 * (int64_t)slot;
         if (fu) {
             const int64_t bb = (int64_t)BU.C4 * 128;
+            // a band does not fit the two slots: two half bands (rows 0-1, 2-3) per band.  (Bands between one and two slots stay
+            // whole and take both slots: halving them so that they double-buffer was measured SLOWER on the 4900-configuration
+            // blocks of Ns=16 -- 64-byte runs, 87 % lane use, a second launch: 0.55 ms against 0.40 ms for their share.)
+            const bool halves = bb > 2 * (int64_t)slot || (ctx->par.reserved[0] & 32768) != 0 && bb > slot;
             int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, slot / bb));
+            if (halves) G = 1;
             for (int a = 0; a < BD.R4; a += G) {
                 FibTile t; memset(&t, 0, sizeof(t));
                 t.pair = p; t.blk = pd.bj; t.a = a; t.b = std::min(G, BD.R4 - a);
                 t.q0 = BD.d0r; t.q1 = BD.nouter; t.q2 = BD.D0; t.q3 = BD.off;
                 t.off = pd.base + (int64_t)a * BU.C4 * 16;
-                t.bytes = (int)(bb * t.b);
-                t1.push_back(t);
+                if (!halves) { t.bytes = (int)(bb * t.b); t1.push_back(t); continue; }
+                t.bytes = BU.hnbox * BU.hbox * 64;
+                for (int h = 1; h <= 2; h++) { t.half = h; t1h.push_back(t); }
             }
         } else { g1.push_back(p); P->g1_elems += (int64_t)BD.size * BU.size; }
         if (fd) {
             const int64_t sb = (int64_t)BD.nbox * BD.BR * 128;
+            // a strip does not fit the two slots: two half strips (columns 0-1, 2-3); see above
+            const bool halves = sb > 2 * (int64_t)slot || (ctx->par.reserved[0] & 32768) != 0 && sb > slot;
             int G = (int)std::max<int64_t>(1, std::min<int64_t>(8, slot / sb));
+            if (halves) G = 1;
             for (int a = 0; a < BU.C4; a += G) {
                 FibTile t; memset(&t, 0, sizeof(t));
                 t.pair = p; t.blk = pd.bi; t.a = a; t.b = std::min(G, BU.C4 - a);
                 t.q0 = BU.C4;
                 t.off = pd.base;
-                t.bytes = (int)(sb * t.b);
-                t2.push_back(t);
+                if (!halves) { t.bytes = (int)(sb * t.b); t2.push_back(t); continue; }
+                t.bytes = (int)(sb / 2);
+                for (int h = 1; h <= 2; h++) { t.half = h; t2h.push_back(t); }
             }
         } else { g2.push_back(p); P->g2_elems += (int64_t)BD.size * BU.size; }
     }
@@ -286,7 +300,10 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     auto bysize = [](const FibTile &a, const FibTile &b) { return a.bytes != b.bytes ? a.bytes > b.bytes : a.blk < b.blk; };
     std::stable_sort(t1.begin(), t1.end(), bysize);
     std::stable_sort(t2.begin(), t2.end(), bysize);
+    std::stable_sort(t1h.begin(), t1h.end(), bysize);
+    std::stable_sort(t2h.begin(), t2h.end(), bysize);
     P->n1 = (int)t1.size(); P->n2 = (int)t2.size(); P->ng1 = (int)g1.size(); P->ng2 = (int)g2.size();
+    P->n1h = (int)t1h.size(); P->n2h = (int)t2h.size();
     cudaStream_t st = ctx->stream;
     auto up = [&](auto **dptr, const auto &vec) -> cudaError_t {
         using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -302,6 +319,8 @@ int pair_layout_build(edgpu_sector *s, int rank, int nranks)
     CUDA_TRY(ctx, up(&P->d_pairs, P->pairs));
     CUDA_TRY(ctx, up(&P->d_t1, t1));
     CUDA_TRY(ctx, up(&P->d_t2, t2));
+    CUDA_TRY(ctx, up(&P->d_t1h, t1h));
+    CUDA_TRY(ctx, up(&P->d_t2h, t2h));
     CUDA_TRY(ctx, up(&P->d_g1, g1));
     CUDA_TRY(ctx, up(&P->d_g2, g2));
     if (!g1.empty() || !g2.empty()) {
@@ -436,7 +455,9 @@ __global__ void __launch_bounds__(256) k_pair_up(const PairGenArgs A)
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-// one 3-D tensor map per pair over the vector at `x`: dims (16 doubles of a micro-tile, C4 strips, R4 bands)
+// tensor maps per pair over the vector at `x` (see PairLayout::tmaps): strips = dims (16 doubles of a micro-tile, C4, R4) with
+// box 16 x 1 x BR; half bands = the same dims with box 8 x hbox x 1; half strips = dims (4 columns, 4 rows, C4, R4) with box
+// 2 x 4 x 1 x BR
 static int fib_tensor_maps(edgpu_sector *s, const double *x, const CUtensorMap **out)
 {
     edgpu_ctx *ctx = s->ctx;
@@ -455,19 +476,37 @@ static int fib_tensor_maps(edgpu_sector *s, const double *x, const CUtensorMap *
         fn = reinterpret_cast<EncodeFn>(p);
     }
     const FibSpin &FU = *s->up->fib, &FD = *s->dw->fib;
-    std::vector<CUtensorMap> maps(std::max<size_t>(1, P.pairs.size()));
+    const size_t np = std::max<size_t>(1, P.pairs.size());
+    std::vector<CUtensorMap> maps(3 * np);
     memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
     for (size_t p = 0; p < P.pairs.size(); p++) {
         const PairDev &pd = P.pairs[p];
         const FibBlockDev &BD = FD.blocks[pd.bi], &BU = FU.blocks[pd.bj];
-        if (!BD.fiber) continue;
-        const cuuint64_t gdim[3] = {16, (cuuint64_t)BU.C4, (cuuint64_t)BD.R4};
-        const cuuint64_t gstr[2] = {128, (cuuint64_t)BU.C4 * 128};
-        const cuuint32_t box[3] = {16, 1, (cuuint32_t)BD.BR};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = fn(&maps[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(x + pd.base), gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return edgpu_fail(ctx, "cuTensorMapEncodeTiled failed (%d) for pair (%d,%d): C4=%d R4=%d BR=%d", (int)r, pd.bi, pd.bj, BU.C4, BD.R4, BD.BR);
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        void *base = const_cast<double *>(x + pd.base);
+        CUresult r = CUDA_SUCCESS;
+        if (BD.fiber) {
+            const cuuint64_t gdim[3] = {16, (cuuint64_t)BU.C4, (cuuint64_t)BD.R4};
+            const cuuint64_t gstr[2] = {128, (cuuint64_t)BU.C4 * 128};
+            const cuuint32_t box[3] = {16, 1, (cuuint32_t)BD.BR};
+            r = fn(&maps[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS && P.n2h > 0) {
+                const cuuint64_t gdim4[4] = {4, 4, (cuuint64_t)BU.C4, (cuuint64_t)BD.R4};
+                const cuuint64_t gstr4[3] = {32, 128, (cuuint64_t)BU.C4 * 128};
+                const cuuint32_t box4[4] = {2, 4, 1, (cuuint32_t)BD.BR};
+                r = fn(&maps[np + p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, gdim4, gstr4, box4, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+        }
+        if (r == CUDA_SUCCESS && BU.fiber && P.n1h > 0) {
+            const cuuint64_t gdim[3] = {16, (cuuint64_t)BU.C4, (cuuint64_t)BD.R4};
+            const cuuint64_t gstr[2] = {128, (cuuint64_t)BU.C4 * 128};
+            const cuuint32_t box[3] = {8, (cuuint32_t)BU.hbox, 1};
+            r = fn(&maps[2 * np + p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) return edgpu_fail(ctx, "cuTensorMapEncodeTiled failed (%d) for pair (%d,%d): C4=%d R4=%d BR=%d hbox=%d", (int)r, pd.bi, pd.bj, BU.C4, BD.R4, BD.BR, BU.hbox);
     }
     if (P.tmaps.size() > 64) {                       // bounded cache: a sector sees only a handful of vector buffers
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -494,26 +533,20 @@ void pair_layout_forget(edgpu_sector *s, const double *x)
     s->pl->tmaps.erase(it);
 }
 
-int fib_launch_nl3(int pass, cudaStream_t st, const FibArgs &A, int grid);
-int fib_launch_nl4(int pass, cudaStream_t st, const FibArgs &A, int grid);
-int fib_launch_nl5(int pass, cudaStream_t st, const FibArgs &A, int grid);
-int fib_launch_nl6(int pass, cudaStream_t st, const FibArgs &A, int grid);
-int fib_launch_nl7(int pass, cudaStream_t st, const FibArgs &A, int grid);
-int fib_launch_nl8(int pass, cudaStream_t st, const FibArgs &A, int grid);
+#define FIB_DECL(n) int fib_launch_nl##n(int pass, cudaStream_t st, const FibArgs &A, int grid); int fib_launch_nl##n##h(int pass, cudaStream_t st, const FibArgs &A, int grid);
+FIB_DECL(3) FIB_DECL(4) FIB_DECL(5) FIB_DECL(6) FIB_DECL(7) FIB_DECL(8)
+#undef FIB_DECL
 
-static int fib_launch_any(edgpu_ctx *ctx, int nl, int pass, const FibArgs &A, int grid)
+static int fib_launch_any(edgpu_ctx *ctx, int nl, int pass, bool half, const FibArgs &A, int grid)
 {
     int e = (int)cudaErrorInvalidValue;
     switch (nl) {
-        case 3: e = fib_launch_nl3(pass, ctx->stream, A, grid); break;
-        case 4: e = fib_launch_nl4(pass, ctx->stream, A, grid); break;
-        case 5: e = fib_launch_nl5(pass, ctx->stream, A, grid); break;
-        case 6: e = fib_launch_nl6(pass, ctx->stream, A, grid); break;
-        case 7: e = fib_launch_nl7(pass, ctx->stream, A, grid); break;
-        case 8: e = fib_launch_nl8(pass, ctx->stream, A, grid); break;
+#define FIB_CASE(n) case n: e = half ? fib_launch_nl##n##h(pass, ctx->stream, A, grid) : fib_launch_nl##n(pass, ctx->stream, A, grid); break;
+        FIB_CASE(3) FIB_CASE(4) FIB_CASE(5) FIB_CASE(6) FIB_CASE(7) FIB_CASE(8)
+#undef FIB_CASE
         default: return edgpu_fail(ctx, "hxv_fiber: %d levels per star are not instantiated", nl);
     }
-    if (e != 0) return edgpu_fail(ctx, "fiber kernel launch (NL=%d, pass %d): %s", nl, pass, cudaGetErrorString((cudaError_t)e));
+    if (e != 0) return edgpu_fail(ctx, "fiber kernel launch (NL=%d, pass %d%s): %s", nl, pass, half ? ", half tiles" : "", cudaGetErrorString((cudaError_t)e));
     return 0;
 }
 
@@ -535,12 +568,21 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
     G.cfg_up = s->up->cfg; G.cfg_dw = s->dw->cfg; G.e_up = s->up->ediag; G.e_dw = s->dw->ediag; G.xtab = ctx->d_xtab;
     G.impmask = A.impmask; G.x = x; G.y = y;
     // ---- first pass: y = H_dw x (strips of 4 columns; write-only) ----
-    if (P.n2 > 0) {
-        const CUtensorMap *tm = nullptr;
+    const size_t np = std::max<size_t>(1, P.pairs.size());
+    const CUtensorMap *tm = nullptr, *tmy = nullptr;
+    if (P.n2 + P.n2h + P.n1h > 0)
         if (int rc = fib_tensor_maps(s, x, &tm)) return rc;
-        A.cst = FD.cst; A.blk_f = FD.d_blocks; A.blk_o = FU.d_blocks; A.outer = FD.d_outer; A.amps = FD.d_amps;
-        A.tiles = P.d_t2; A.ntiles = P.n2; A.tmaps = tm; A.tmaps_y = nullptr; A.dot_out = nullptr;
-        if (int rc = fib_launch_any(ctx, P.nl, 2, A, std::min(ctx->sm_count, P.n2))) return rc;
+    if (P.n1h > 0)
+        if (int rc = fib_tensor_maps(s, y, &tmy)) return rc;
+    A.cst = FD.cst; A.blk_f = FD.d_blocks; A.blk_o = FU.d_blocks; A.outer = FD.d_outer; A.amps = FD.d_amps;
+    A.tmaps_y = nullptr; A.dot_out = nullptr;
+    if (P.n2 > 0) {
+        A.tiles = P.d_t2; A.ntiles = P.n2; A.tmaps = tm;
+        if (int rc = fib_launch_any(ctx, P.nl, 2, false, A, std::min(ctx->sm_count, P.n2))) return rc;
+    }
+    if (P.n2h > 0) {
+        A.tiles = P.d_t2h; A.ntiles = P.n2h; A.tmaps = tm + np;
+        if (int rc = fib_launch_any(ctx, P.nl, 2, true, A, std::min(ctx->sm_count, P.n2h))) return rc;
     }
     if (P.ng2 > 0) {
         G.list = P.d_g2; G.nlist = P.ng2; G.poshop = P.d_poshop_r; G.nhop = s->dw->nhop; G.amp = s->dw->amp; G.hop_ld = s->dw->dim; G.dot_out = nullptr;
@@ -549,12 +591,19 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
         k_pair_dw<<<grid, 256, 0, ctx->stream>>>(G);
     }
     // ---- second pass: y += (diag + H_up) x (bands of 4 rows; read-modify-write, partial <x, y>) ----
+    A.cst = FU.cst; A.blk_f = FU.d_blocks; A.blk_o = FD.d_blocks; A.outer = FU.d_outer; A.amps = FU.d_amps;
     if (P.n1 > 0) {
-        A.cst = FU.cst; A.blk_f = FU.d_blocks; A.blk_o = FD.d_blocks; A.outer = FU.d_outer; A.amps = FU.d_amps;
         A.tiles = P.d_t1; A.ntiles = P.n1; A.tmaps = nullptr; A.tmaps_y = nullptr;
         const int grid = std::min(ctx->sm_count, P.n1);
         A.dot_out = dot ? dot + nd : nullptr;
-        if (int rc = fib_launch_any(ctx, P.nl, 1, A, grid)) return rc;
+        if (int rc = fib_launch_any(ctx, P.nl, 1, false, A, grid)) return rc;
+        if (dot) nd += grid;
+    }
+    if (P.n1h > 0) {
+        A.tiles = P.d_t1h; A.ntiles = P.n1h; A.tmaps = tm + 2 * np; A.tmaps_y = tmy + 2 * np;
+        const int grid = std::min(ctx->sm_count, P.n1h);
+        A.dot_out = dot ? dot + nd : nullptr;
+        if (int rc = fib_launch_any(ctx, P.nl, 1, true, A, grid)) return rc;
         if (dot) nd += grid;
     }
     if (P.ng1 > 0) {
@@ -575,5 +624,5 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
 int hxv_fiber_launches(const edgpu_sector *s)
 {
     if (!s->pl) return 0;
-    return (s->pl->n1 > 0) + (s->pl->ng1 > 0) + (s->pl->n2 > 0) + (s->pl->ng2 > 0);
+    return (s->pl->n1 > 0) + (s->pl->n1h > 0) + (s->pl->ng1 > 0) + (s->pl->n2 > 0) + (s->pl->n2h > 0) + (s->pl->ng2 > 0);
 }
