@@ -49,7 +49,7 @@ class ed_input(C.Structure):
 
 # every symbol declared in include/edgpu.h and include/ed_b200.h (checked by tests/test_abi.py)
 EDGPU_SYMBOLS = [
-    "edgpu_init", "edgpu_finalize", "edgpu_last_error", "edgpu_version", "edgpu_ns", "edgpu_set_hamiltonian",
+    "edgpu_init", "edgpu_finalize", "edgpu_bind_thread", "edgpu_sector_context", "edgpu_last_error", "edgpu_version", "edgpu_ns", "edgpu_set_hamiltonian",
     "edgpu_sector_build", "edgpu_sector_build_shard", "edgpu_sector_info", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize", "edgpu_comm_info", "edgpu_comm_allreduce_host", "edgpu_vec_download_rows", "edgpu_sector_free", "edgpu_sector_dim", "edgpu_sector_map", "edgpu_sector_map_check",
     "edgpu_vec_alloc", "edgpu_vec_free", "edgpu_vec_upload", "edgpu_vec_download", "edgpu_vec_fill_normal", "edgpu_vec_fill_uniform",
     "edgpu_vec_copy", "edgpu_vec_dot", "edgpu_vec_scale", "edgpu_hxv", "edgpu_hxv_dev",

@@ -108,6 +108,11 @@ extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: cudaSetDevice(%d) failed", device); }
     ctx->stream = (cudaStream_t)stream;
+    if (p->reserved[2] & 1) {
+        // worker context of a multi-threaded host (ed_solve): a stream of its own that does not synchronise with stream 0
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: cudaStreamCreate failed"); }
+        ctx->own_stream = true;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: cudaGetDeviceProperties failed"); }
     if (prop.major < 10) { delete ctx; return edgpu_fail(nullptr, "edgpu_init: device sm_%d%d is not Blackwell (sm_100a build)", prop.major, prop.minor); }
@@ -134,6 +139,15 @@ extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu
     return 0;
 }
 
+extern "C" edgpu_ctx *edgpu_sector_context(const edgpu_sector *s) { return s ? s->ctx : nullptr; }
+
+extern "C" int edgpu_bind_thread(edgpu_ctx *ctx)
+{
+    if (!ctx) return edgpu_fail(nullptr, "edgpu_bind_thread: null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
+
 extern "C" int edgpu_finalize(edgpu_ctx *ctx)
 {
     if (!ctx) return 0;
@@ -144,6 +158,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     ctx->bases.clear();
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
     delete ctx;
     return 0;

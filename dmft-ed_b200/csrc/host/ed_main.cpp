@@ -19,9 +19,11 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 int host_tql2(int n, double *d, double *e, double *z);
@@ -33,6 +35,7 @@ struct EdState {
     int nup = 0, ndw = 0;
     edgpu_sector *sec = nullptr;
     edgpu_vec *vec = nullptr;
+    int worker = 0;                 // index of the worker context that owns sec / vec
 };
 
 struct EdChain {
@@ -66,6 +69,10 @@ struct ed_solver {
     std::vector<cplx> densChi_iv, densChi_w, densChi_tot_iv, densChi_tot_w;
     double timings[4] = {0, 0, 0, 0};
     int rank = 0, nranks = 1;                 // ed_set_comm: sectors / states dealt over the ranks
+    // work-unit parallelism on ONE GPU: the sectors of the scan and the GF chains are independent (the reference deals them
+    // over MPI ranks, ED_MAIN.f90:598-636); here host threads drive worker contexts with streams of their own, so that the
+    // launch latency and the host-side algebra of the many small sectors overlap.  wctx[0] == ctx.
+    std::vector<edgpu_ctx *> wctx;
 };
 
 static int fail(ed_solver *s, const char *fmt, ...)
@@ -164,6 +171,21 @@ extern "C" int ed_init_solver(const ed_input *in, int device, void *stream, doub
         delete s;
         return 1;
     }
+    s->wctx.push_back(s->ctx);
+    int nworkers = in->reserved[2] > 0 ? in->reserved[2] : 4;
+    if (const char *e = getenv("ED_B200_WORKERS")) nworkers = std::max(1, atoi(e));
+    nworkers = std::min(nworkers, 16);
+    p.reserved[2] = 1;                                // worker contexts own a non-blocking stream
+    for (int w = 1; w < nworkers; w++) {
+        edgpu_ctx *c = nullptr;
+        if (edgpu_init(&p, device, nullptr, &c) != 0) {
+            fprintf(stderr, "ed_init_solver: %s\n", edgpu_last_error(nullptr));
+            for (auto *q : s->wctx) edgpu_finalize(q);
+            delete s;
+            return 1;
+        }
+        s->wctx.push_back(c);
+    }
     const size_t nh = (size_t)in->Nspin * in->Nspin * in->Norb * in->Norb;
     s->hloc.assign(2 * nh, 0.0);
     if (hloc_cplx) memcpy(s->hloc.data(), hloc_cplx, sizeof(double) * 2 * nh);
@@ -207,6 +229,7 @@ extern "C" int ed_finalize_solver(ed_solver *s)
 {
     if (!s) return 0;
     free_states(s);
+    for (size_t w = s->wctx.size(); w-- > 1;) edgpu_finalize(s->wctx[w]);
     edgpu_finalize(s->ctx);
     delete s;
     return 0;
@@ -316,22 +339,34 @@ static void insert_state(std::vector<EdState> &list, const EdState &st)
     list.insert(list.begin() + pos, st);
 }
 
-static int ed_diag(ed_solver *s)
+// ED_B200_TRACE=1: per-sector / per-chain wall times on stderr (where does a solve spend its time)
+static bool trace_on()
+{
+    static const bool on = getenv("ED_B200_TRACE") != nullptr;
+    return on;
+}
+
+// One worker's share of the scan: the reference's loop body (ED_DIAG.f90:86-240) over `secs` with a LOCAL running minimum.
+struct DiagLocal {
+    std::vector<EdState> states;
+    std::map<std::pair<int, int>, double> sector_e;
+    std::map<std::pair<int, int>, int> sector_nlanc;
+    std::string err;
+};
+
+static int diag_sectors(ed_solver *s, int worker, const std::vector<std::pair<int, int>> &secs, DiagLocal &L)
 {
     const ed_input &in = s->in;
-    const int Ns = s->Ns;
-    free_states(s);
-    s->sector_e.clear();
-    s->sector_nlanc.clear();
+    edgpu_ctx *ctx = s->wctx[worker];
+    auto bad = [&](const char *what) { L.err = std::string(what) + ": " + edgpu_last_error(ctx); return 1; };
+    if (edgpu_bind_thread(ctx)) return bad("ed_diag");
     double oldzero = 1000.0;
-    int isec = -1;
-    for (int nup = 0; nup <= Ns; nup++)
-        for (int ndw = 0; ndw <= Ns; ndw++) {                                  // isector order, ED_SETUP.f90:382-393
-            if (!s->mask.empty() && std::find(s->mask.begin(), s->mask.end(), std::make_pair(nup, ndw)) == s->mask.end()) continue;
-            isec++;
-            if (s->nranks > 1 && isec % s->nranks != s->rank) continue;        // distributed scan: this sector belongs to another rank
+    for (const auto &nn : secs) {
+            const int nup = nn.first, ndw = nn.second;
             edgpu_sector *sec = nullptr;
-            GPU_TRY(s, edgpu_sector_build(s->ctx, nup, ndw, &sec));
+            const double tr0 = now_s();
+            if (edgpu_sector_build(ctx, nup, ndw, &sec)) return bad("ed_diag");
+            const double tr1 = now_s();
             int64_t dim = 0;
             edgpu_sector_dim(sec, &dim, nullptr, nullptr);
             int64_t neigen, nitermax;
@@ -367,75 +402,125 @@ static int ed_diag(ed_solver *s)
                     std::vector<edgpu_vec *> vv(neigen, nullptr);
                     int nconv = 0, nmv = 0;
                     rc = edgpu_lanczos_eigs(sec, (int)neigen, ncv, std::max(1, in.lanc_niter), in.lanc_tolerance, 1234567ull, ev.data(), vv.data(), &nconv, &nmv);
-                    if (rc) { for (auto *q : vv) if (q) edgpu_vec_free(q); edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
+                    if (rc) { bad("ed_diag"); for (auto *q : vv) if (q) edgpu_vec_free(q); edgpu_sector_free(sec); return 1; }
                     for (int64_t i = 0; i < neigen; i++) { evals.push_back(ev[i]); evecs.push_back(vv[i]); }
-                    s->sector_nlanc[{nup, ndw}] = nmv;
+                    L.sector_nlanc[{nup, ndw}] = nmv;
                 } else {
-                if (!rc) rc = edgpu_lanczos_gs(sec, v, (int)nitermax, in.lanc_tolerance, 10, &e0, &nl, nullptr, nullptr);
-                if (rc) { if (v) edgpu_vec_free(v); edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
-                // lanc_nstates_sector = 1 (or lanc_method=lanczos): the lowest pair by plain Lanczos (sp_lanc_eigh, :173-181)
-                evals.push_back(e0);
-                evecs.push_back(v);
-                s->sector_nlanc[{nup, ndw}] = nl;
+                    if (!rc) rc = edgpu_lanczos_gs(sec, v, (int)nitermax, in.lanc_tolerance, 10, &e0, &nl, nullptr, nullptr);
+                    if (rc) { bad("ed_diag"); if (v) edgpu_vec_free(v); edgpu_sector_free(sec); return 1; }
+                    // lanc_nstates_sector = 1 (or lanc_method=lanczos): the lowest pair by plain Lanczos (sp_lanc_eigh, :173-181)
+                    evals.push_back(e0);
+                    evecs.push_back(v);
+                    L.sector_nlanc[{nup, ndw}] = nl;
                 }
                 if (in.ed_sparse_H) edgpu_sector_drop_csr(sec);
             } else {
                 H.assign((size_t)dim * dim, 0.0);
                 std::vector<double> w(dim);
                 rc = edgpu_sector_dense(sec, H.data());                                                   // :188-193
-                if (rc) { edgpu_sector_free(sec); return fail(s, "%s", edgpu_last_error(s->ctx)); }
-                if (ed_host_eigh((int)dim, H.data(), w.data())) { edgpu_sector_free(sec); return fail(s, "ed_diag: dense eigh failed"); }
+                if (rc) { bad("ed_diag"); edgpu_sector_free(sec); return 1; }
+                if (ed_host_eigh((int)dim, H.data(), w.data())) { L.err = "ed_diag: dense eigh failed"; edgpu_sector_free(sec); return 1; }
                 for (int64_t i = 0; i < neigen; i++) { evals.push_back(w[i]); evecs.push_back(nullptr); }   // uploaded on demand
             }
-            s->sector_e[{nup, ndw}] = evals.empty() ? 0.0 : evals[0];
+            L.sector_e[{nup, ndw}] = evals.empty() ? 0.0 : evals[0];
+            const double tr2 = now_s();
             bool used = false;
             for (size_t i = 0; i < evals.size(); i++) {                                                   // :224-235
                 const double enemin = evals[i];
                 EdState st;
-                st.e = enemin; st.nup = nup; st.ndw = ndw; st.sec = sec;
+                st.e = enemin; st.nup = nup; st.ndw = ndw; st.sec = sec; st.worker = worker;
                 const bool lower = enemin < oldzero - 10.0 * in.gs_threshold;
                 const bool degen = !lower && std::fabs(enemin - oldzero) <= in.gs_threshold;
-                if ((lower || degen) && need_vec(i)) return fail(s, "ed_diag: %s", edgpu_last_error(s->ctx));
+                if ((lower || degen) && need_vec(i)) return bad("ed_diag");
                 st.vec = evecs[i];
                 if (lower) {
                     oldzero = enemin;
                     // es_free_espace: drop every stored state
-                    std::vector<edgpu_sector *> secs;
-                    for (auto &o : s->states) {
+                    std::vector<edgpu_sector *> old;
+                    for (auto &o : L.states) {
                         if (o.vec) edgpu_vec_free(o.vec);
-                        if (o.sec != sec && std::find(secs.begin(), secs.end(), o.sec) == secs.end()) secs.push_back(o.sec);
+                        if (o.sec != sec && std::find(old.begin(), old.end(), o.sec) == old.end()) old.push_back(o.sec);
                     }
-                    for (auto *q : secs) edgpu_sector_free(q);
-                    s->states.clear();
-                    if (!st.vec) return fail(s, "ed_diag: internal error (missing eigenvector)");
-                    insert_state(s->states, st);
+                    for (auto *q : old) edgpu_sector_free(q);
+                    L.states.clear();
+                    if (!st.vec) { L.err = "ed_diag: internal error (missing eigenvector)"; return 1; }
+                    insert_state(L.states, st);
                     used = true;
                 } else if (degen) {
                     oldzero = std::min(oldzero, enemin);
-                    if (!st.vec) return fail(s, "ed_diag: internal error (missing eigenvector)");
-                    insert_state(s->states, st);
+                    if (!st.vec) { L.err = "ed_diag: internal error (missing eigenvector)"; return 1; }
+                    insert_state(L.states, st);
                     used = true;
                 } else if (st.vec) {
                     edgpu_vec_free(st.vec);
                 }
             }
             if (!used) edgpu_sector_free(sec);
+            if (trace_on())
+                fprintf(stderr, "[ed_diag w%d] (%d,%d) dim %lld %s build %.2f ms solve %.2f ms (nlanc %d) keep/free %.2f ms\n", worker, nup, ndw, (long long)dim,
+                        lanc_solve ? "lanczos" : "dense", (tr1 - tr0) * 1e3, (tr2 - tr1) * 1e3, lanc_solve ? L.sector_nlanc[{nup, ndw}] : 0, (now_s() - tr2) * 1e3);
+    }
+    return 0;
+}
+
+// Keeps, of the states the workers (and ranks) found with their local running minima, those within gs_threshold of `emin`.
+static void keep_ground_states(ed_solver *s, std::vector<EdState> &all, double emin)
+{
+    std::vector<EdState> keep;
+    std::vector<edgpu_sector *> used, drop;
+    for (auto &st : all) {
+        if (std::fabs(st.e - emin) <= s->in.gs_threshold) { keep.push_back(st); used.push_back(st.sec); }
+        else { if (st.vec) edgpu_vec_free(st.vec); drop.push_back(st.sec); }
+    }
+    for (auto *q : drop)
+        if (std::find(used.begin(), used.end(), q) == used.end()) { edgpu_sector_free(q); used.push_back(q); }
+    // the list order of the serial scan: insertion in sector order (ties keep the reference's "new entry first" rule)
+    std::stable_sort(keep.begin(), keep.end(), [](const EdState &a, const EdState &b) { return a.nup != b.nup ? a.nup < b.nup : a.ndw < b.ndw; });
+    s->states.clear();
+    for (auto &st : keep) insert_state(s->states, st);
+}
+
+static int ed_diag(ed_solver *s)
+{
+    const int Ns = s->Ns;
+    free_states(s);
+    s->sector_e.clear();
+    s->sector_nlanc.clear();
+    // sectors of this rank in the reference's isector order (ED_SETUP.f90:382-393), dealt round-robin to the workers
+    const int nw = (int)s->wctx.size();
+    std::vector<std::vector<std::pair<int, int>>> mine(nw);
+    int isec = -1, cnt = 0;
+    for (int nup = 0; nup <= Ns; nup++)
+        for (int ndw = 0; ndw <= Ns; ndw++) {
+            if (!s->mask.empty() && std::find(s->mask.begin(), s->mask.end(), std::make_pair(nup, ndw)) == s->mask.end()) continue;
+            isec++;
+            if (s->nranks > 1 && isec % s->nranks != s->rank) continue;        // distributed scan: this sector belongs to another rank
+            mine[cnt++ % nw].push_back({nup, ndw});
         }
+    std::vector<DiagLocal> loc(nw);
+    std::vector<int> rcs(nw, 0);
+    {
+        std::vector<std::thread> th;
+        for (int w = 1; w < nw; w++) th.emplace_back([&, w] { rcs[w] = diag_sectors(s, w, mine[w], loc[w]); });
+        rcs[0] = diag_sectors(s, 0, mine[0], loc[0]);
+        for (auto &t : th) t.join();
+    }
+    std::vector<EdState> all;
+    int bad = -1;
+    for (int w = 0; w < nw; w++) {
+        if (rcs[w] && bad < 0) bad = w;
+        for (auto &st : loc[w].states) all.push_back(st);
+        for (auto &kv : loc[w].sector_e) s->sector_e[kv.first] = kv.second;
+        for (auto &kv : loc[w].sector_nlanc) s->sector_nlanc[kv.first] = kv.second;
+    }
+    if (bad >= 0) { s->states = all; free_states(s); return fail(s, "%s", loc[bad].err.c_str()); }
+    double emin = 1e300;
+    for (auto &st : all) emin = std::min(emin, st.e);
     if (s->nranks > 1) {
         // the running minimum of :224-235 was local: agree on the global ground energy, keep the local states within
         // gs_threshold of it, and share the sector energies
-        double emin = 1e300;
-        for (auto &st : s->states) emin = std::min(emin, st.e);
         GPU_TRY(s, edgpu_comm_allreduce_host(s->ctx, &emin, 1, 1));
-        std::vector<EdState> keep;
-        std::vector<edgpu_sector *> used, drop;
-        for (auto &st : s->states) {
-            if (std::fabs(st.e - emin) <= in.gs_threshold) { keep.push_back(st); used.push_back(st.sec); }
-            else { if (st.vec) edgpu_vec_free(st.vec); drop.push_back(st.sec); }
-        }
-        for (auto *q : drop)
-            if (std::find(used.begin(), used.end(), q) == used.end()) { edgpu_sector_free(q); used.push_back(q); }
-        s->states.swap(keep);
+        keep_ground_states(s, all, emin);
         double cnt = (double)s->states.size();
         GPU_TRY(s, edgpu_comm_allreduce_host(s->ctx, &cnt, 1, 0));
         const int nsec = (Ns + 1) * (Ns + 1);
@@ -450,6 +535,7 @@ static int ed_diag(ed_solver *s)
         s->zeta = cnt;
         return 0;
     }
+    keep_ground_states(s, all, emin);
     if (s->states.empty()) return fail(s, "ed_diag: no state found");
     // ed_post_diag (ED_DIAG.f90:403-416), T=0
     s->egs = s->states[0].e;
@@ -467,7 +553,7 @@ static inline size_t gidx(const ed_input &in, int ispin, int jspin, int iorb, in
     return (size_t)ispin + in.Nspin * ((size_t)jspin + in.Nspin * ((size_t)iorb + in.Norb * ((size_t)jorb + (size_t)in.Norb * i)));
 }
 
-static void add_to_lanczos_gf(ed_solver *s, double vnorm2, double Ei, const std::vector<double> &alanc,
+static void add_to_lanczos_gf(const ed_solver *s, std::vector<cplx> &Gm, std::vector<cplx> &Gr, double vnorm2, double Ei, const std::vector<double> &alanc,
                               const std::vector<double> &blanc, int isign, int iorb, int jorb, int ispin)
 {
     // add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:580-632), T=0: pesoBZ = vnorm2/zeta_function
@@ -481,16 +567,62 @@ static void add_to_lanczos_gf(ed_solver *s, double vnorm2, double Ei, const std:
         const double peso = pesoBZ * Z[(size_t)nlanc * j] * Z[(size_t)nlanc * j];      // Z(1,j)^2
         if (peso == 0.0) continue;
         for (int i = 0; i < in.Lmats; i++)
-            s->Gmats[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(0.0, s->wm[i]) - (double)isign * de);
+            Gm[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(0.0, s->wm[i]) - (double)isign * de);
         for (int i = 0; i < in.Lreal; i++)
-            s->Greal[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(s->wr[i], in.eps) - (double)isign * de);
+            Gr[gidx(in, ispin, ispin, iorb, jorb, i)] += peso / (cplx(s->wr[i], in.eps) - (double)isign * de);
     }
+}
+
+// one GF chain: seed c / c^dagger |state>, tridiagonalise in the target sector, add the poles (ED_GF_NORMAL.f90:116-260)
+struct GfUnit { int ispin, iorb, istate, pass; };
+
+static int gf_unit(ed_solver *s, const GfUnit &u, EdChain &ch, std::vector<cplx> &Gm, std::vector<cplx> &Gr, std::string &err)
+{
+    const ed_input &in = s->in;
+    const int Ns = s->Ns;
+    const int ispin = u.ispin, iorb = u.iorb;
+    EdState &st = s->states[u.istate];
+    edgpu_ctx *ctx = s->wctx[st.worker];
+    const int isite = (ispin == 0) ? iorb + 1 : iorb + 1 + Ns;                // impIndex, ED_SETUP.f90:443-446
+    const int dagger = u.pass == 0 ? 1 : 0, isign = u.pass == 0 ? 1 : -1;     // :150 cdg first, :203 c
+    const int jup = st.nup + (ispin == 0 ? (dagger ? 1 : -1) : 0);
+    const int jdw = st.ndw + (ispin == 1 ? (dagger ? 1 : -1) : 0);
+    ch.iorb = iorb; ch.ispin = ispin; ch.isign = isign; ch.istate = u.istate; ch.norm2 = 0; ch.nlanc = 0; ch.nused = -1;
+    if (jup < 0 || jup > Ns || jdw < 0 || jdw > Ns) return 0;                 // getCDGsector/getCsector == 0: no chain
+    edgpu_sector *sj = nullptr;
+    edgpu_vec *vv = nullptr;
+    const double tr0 = now_s();
+    if (edgpu_sector_build(ctx, jup, jdw, &sj)) { err = edgpu_last_error(ctx); return 1; }
+    const double tr1 = now_s();
+    int64_t jdim = 0;
+    edgpu_sector_dim(sj, &jdim, nullptr, nullptr);
+    int rc = edgpu_vec_alloc(sj, &vv);
+    double norm2 = 0;
+    if (!rc) rc = edgpu_apply_c(st.sec, sj, isite, dagger, st.vec, vv, 1, &norm2);     // :159-174
+    ch.norm2 = norm2;
+    ch.nlanc = (int)std::min<int64_t>(jdim, in.lanc_ngfiter);                           // :177
+    ch.alfa.assign(ch.nlanc, 0.0);
+    ch.beta.assign(ch.nlanc, 0.0);
+    ch.nused = 0;
+    if (!rc && in.ed_sparse_H && jdim > 1) rc = edgpu_sector_build_csr(sj);              // build_Hv_sector :180
+    if (!rc && norm2 > 0.0)
+        rc = edgpu_lanczos_tridiag(sj, vv, ch.nlanc, 1e-13, ch.alfa.data(), ch.beta.data(), &ch.nused);
+    const double tr2 = now_s();
+    if (rc) err = edgpu_last_error(ctx);
+    if (vv) edgpu_vec_free(vv);
+    edgpu_sector_free(sj);
+    if (rc) return 1;
+    const double tr3 = now_s();
+    if (norm2 > 0.0) add_to_lanczos_gf(s, Gm, Gr, norm2, st.e, ch.alfa, ch.beta, isign, iorb, iorb, ispin);  // :194
+    if (trace_on())
+        fprintf(stderr, "[build_gf w%d] state %d orb %d spin %d sign %d -> (%d,%d) dim %lld: build %.2f ms apply+chain %.2f ms (%d steps) free %.2f ms poles %.2f ms\n",
+                st.worker, u.istate, iorb, ispin, isign, jup, jdw, (long long)jdim, (tr1 - tr0) * 1e3, (tr2 - tr1) * 1e3, ch.nused, (tr3 - tr2) * 1e3, (now_s() - tr3) * 1e3);
+    return 0;
 }
 
 static int build_gf(ed_solver *s)
 {
     const ed_input &in = s->in;
-    const int Ns = s->Ns;
     const size_t nblk = (size_t)in.Nspin * in.Nspin * in.Norb * in.Norb;
     // allocate_grids (ED_AUX_FUNX.f90:449-461)
     s->wm.resize(in.Lmats);
@@ -501,41 +633,45 @@ static int build_gf(ed_solver *s)
     s->Gmats.assign(nblk * in.Lmats, cplx(0, 0));
     s->Greal.assign(nblk * in.Lreal, cplx(0, 0));
     s->chains.clear();
+    // the chains in the reference's loop order (build_gf_normal :24-31, :132, :150/:203); each runs on the worker context
+    // that owns its state, the workers side by side, every worker summing into its own G
+    std::vector<GfUnit> units;
     for (int ispin = 0; ispin < in.Nspin; ispin++)
-        for (int iorb = 0; iorb < in.Norb; iorb++) {                                   // build_gf_normal :24-31
-            const int isite = (ispin == 0) ? iorb + 1 : iorb + 1 + Ns;                // impIndex, ED_SETUP.f90:443-446
-            for (size_t istate = 0; istate < s->states.size(); istate++) {             // :132
-                EdState &st = s->states[istate];
-                for (int pass = 0; pass < 2; pass++) {
-                    const int dagger = pass == 0 ? 1 : 0, isign = pass == 0 ? 1 : -1;  // :150 cdg first, :203 c
-                    const int jup = st.nup + (ispin == 0 ? (dagger ? 1 : -1) : 0);
-                    const int jdw = st.ndw + (ispin == 1 ? (dagger ? 1 : -1) : 0);
-                    if (jup < 0 || jup > Ns || jdw < 0 || jdw > Ns) continue;          // getCDGsector/getCsector == 0
-                    edgpu_sector *sj = nullptr;
-                    edgpu_vec *vv = nullptr;
-                    GPU_TRY(s, edgpu_sector_build(s->ctx, jup, jdw, &sj));
-                    int64_t jdim = 0;
-                    edgpu_sector_dim(sj, &jdim, nullptr, nullptr);
-                    int rc = edgpu_vec_alloc(sj, &vv);
-                    double norm2 = 0;
-                    if (!rc) rc = edgpu_apply_c(st.sec, sj, isite, dagger, st.vec, vv, 1, &norm2);     // :159-174
-                    EdChain ch;
-                    ch.iorb = iorb; ch.ispin = ispin; ch.isign = isign; ch.istate = (int)istate; ch.norm2 = norm2;
-                    ch.nlanc = (int)std::min<int64_t>(jdim, in.lanc_ngfiter);                           // :177
-                    ch.alfa.assign(ch.nlanc, 0.0);
-                    ch.beta.assign(ch.nlanc, 0.0);
-                    ch.nused = 0;
-                    if (!rc && in.ed_sparse_H && jdim > 1) rc = edgpu_sector_build_csr(sj);              // build_Hv_sector :180
-                    if (!rc && norm2 > 0.0)
-                        rc = edgpu_lanczos_tridiag(sj, vv, ch.nlanc, 1e-13, ch.alfa.data(), ch.beta.data(), &ch.nused);
-                    if (vv) edgpu_vec_free(vv);
-                    edgpu_sector_free(sj);
-                    if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
-                    if (norm2 > 0.0) add_to_lanczos_gf(s, norm2, st.e, ch.alfa, ch.beta, isign, iorb, iorb, ispin);  // :194
-                    s->chains.push_back(std::move(ch));
-                }
+        for (int iorb = 0; iorb < in.Norb; iorb++)
+            for (size_t istate = 0; istate < s->states.size(); istate++)
+                for (int pass = 0; pass < 2; pass++) units.push_back({ispin, iorb, (int)istate, pass});
+    const int nw = (int)s->wctx.size();
+    std::vector<EdChain> chains(units.size());
+    std::vector<std::vector<cplx>> Gm(nw), Gr(nw);
+    std::vector<std::string> errs(nw);
+    std::vector<int> rcs(nw, 0);
+    auto run = [&](int w) {
+        bool any = false;
+        for (size_t k = 0; k < units.size() && !rcs[w]; k++) {
+            if (s->states[units[k].istate].worker != w) continue;
+            if (!any) {
+                any = true;
+                Gm[w].assign(s->Gmats.size(), cplx(0, 0)); Gr[w].assign(s->Greal.size(), cplx(0, 0));
+                if (edgpu_bind_thread(s->wctx[w])) { errs[w] = edgpu_last_error(s->wctx[w]); rcs[w] = 1; return; }
             }
+            rcs[w] = gf_unit(s, units[k], chains[k], Gm[w], Gr[w], errs[w]);
         }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int w = 1; w < nw; w++) th.emplace_back(run, w);
+        run(0);
+        for (auto &t : th) t.join();
+    }
+    for (int w = 0; w < nw; w++)
+        if (rcs[w]) return fail(s, "%s", errs[w].c_str());
+    for (int w = 0; w < nw; w++) {
+        if (Gm[w].empty()) continue;
+        for (size_t i = 0; i < s->Gmats.size(); i++) s->Gmats[i] += Gm[w][i];
+        for (size_t i = 0; i < s->Greal.size(); i++) s->Greal[i] += Gr[w][i];
+    }
+    for (auto &ch : chains)
+        if (ch.nused >= 0) s->chains.push_back(std::move(ch));
     // distributed solve: every rank summed over ITS states, G is the sum over all of them
     GPU_TRY(s, allsum(s, s->Gmats));
     GPU_TRY(s, allsum(s, s->Greal));
@@ -603,7 +739,7 @@ static int build_chi_spin(ed_solver *s)
             if (!rc && nrm > 0.0) rc = edgpu_lanczos_tridiag(st.sec, vv, nlanc, 1e-13, alfa.data(), beta.data(), &nused);
             if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_drop_csr(st.sec);
             edgpu_vec_free(vv);
-            if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
+            if (rc) return fail(s, "%s", edgpu_last_error(s->wctx[st.worker]));
             // the single-orbital routine hands the NORM to add_to_lanczos_spinChi (:101), the total one its SQUARE (:206);
             // both are squared again there (pesoF = vnorm**2, :263) -- reproduced as is
             if (nrm > 0.0) add_to_lanczos_spinchi(s, tot ? nrm * nrm : nrm, st.e, alfa, beta, ic);
@@ -677,7 +813,7 @@ static int build_chi_dens(ed_solver *s)
             if (!rc && nrm > 0.0) rc = edgpu_lanczos_tridiag(st.sec, vv, nlanc, 1e-13, alfa.data(), beta.data(), &nused);
             if (!rc && in.ed_sparse_H && idim > 1) rc = edgpu_sector_drop_csr(st.sec);
             edgpu_vec_free(vv);
-            if (rc) return fail(s, "%s", edgpu_last_error(s->ctx));
+            if (rc) return fail(s, "%s", edgpu_last_error(s->wctx[st.worker]));
             if (nrm <= 0.0) continue;
             if (tot) add_to_lanczos_denschi(s, nrm * nrm, st.e, alfa, beta, s->densChi_tot_iv.data(), s->densChi_tot_tau.data(), s->densChi_tot_w.data(), 1);
             else {
@@ -763,7 +899,8 @@ extern "C" int ed_solve(ed_solver *s, const double *bath, int32_t bath_len, cons
     if (bath_len != ed_get_bath_dimension(&in)) return fail(s, "ED_SOLVE_SINGLE Error: wrong bath dimensions");   // ED_MAIN.f90:258
     if (hloc_cplx) memcpy(s->hloc.data(), hloc_cplx, sizeof(double) * s->hloc.size());                           // set_Hloc :256
     s->bath.assign(bath, bath + bath_len);
-    GPU_TRY(s, edgpu_set_hamiltonian(s->ctx, bath, bath_len, s->hloc.data(), in.uloc, in.ust, in.jh, in.jx, in.jp, in.xmu));
+    for (edgpu_ctx *c : s->wctx)
+        if (edgpu_set_hamiltonian(c, bath, bath_len, s->hloc.data(), in.uloc, in.ust, in.jh, in.jx, in.jp, in.xmu)) return fail(s, "%s", edgpu_last_error(c));
     double t0 = now_s();
     if (int rc = ed_diag(s)) return rc;                     // diagonalize_impurity
     double t1 = now_s();

@@ -19,6 +19,7 @@
 //   k_star_up : 4 rows x one up-block = contiguous runs of the rows.    y += (diag + H_up) x    R(x) R(y) W(y)
 // Algorithmic bytes per H*v are 2*Dim*8; this two-pass scheme moves 5*Dim*8 through HBM because a
 // tile closed under BOTH spins (70^4 doubles at Ns=16) fits no on-chip memory.
+#include <mutex>
 #include "edgpu_internal.h"
 #include <cuda.h>
 #include <algorithm>
@@ -1438,6 +1439,8 @@ static int round_nh(int nh) { return nh <= 4 ? 4 : nh <= 5 ? 5 : nh <= 6 ? 6 : n
 static int ensure_smem(edgpu_ctx *ctx, const void *kern, size_t smem)
 {
     static std::map<const void *, size_t> set;
+    static std::mutex mtx;                                   // contexts of several host threads share the function attributes
+    std::lock_guard<std::mutex> lock(mtx);
     size_t &cur = set[kern];
     if (smem > cur) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

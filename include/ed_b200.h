@@ -44,7 +44,9 @@ typedef struct {
     int32_t chispin_flag;           /* CHISPIN_FLAG (ED_INPUT_VARS.f90:156): build the spin susceptibility in ed_solve */
     int32_t Ltau;                   /* LTAU (ED_INPUT_VARS.f90:148,211): imaginary-time points, raised to int(beta) */
     int32_t chidens_flag;           /* CHIDENS_FLAG (ED_INPUT_VARS.f90:157): charge susceptibility, diagonal + total channels */
-    int32_t reserved[5];
+    int32_t reserved[5];            /* [0], [1]: lanc_ncv_factor, lanc_ncv_add (0 = reference defaults 10, 0); [2]: host worker threads of
+                                       ed_solve, each with a device context and stream of its own, over which the sectors of the scan
+                                       and the Green's-function chains are dealt (0 = 4, 1 = serial; env ED_B200_WORKERS overrides) */
 } ed_input;
 
 void ed_input_defaults(ed_input *in);

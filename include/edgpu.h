@@ -49,6 +49,11 @@ typedef struct {
  * device < 0: use the current CUDA device.  stream: a cudaStream_t (may be NULL = default stream). */
 int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu_ctx **ctx);
 int edgpu_finalize(edgpu_ctx *ctx);
+/* Hosts that drive several contexts from several threads (ed_solve's work units, ED_MAIN.f90:598-636 deals them over MPI
+ * ranks): edgpu_params.reserved[2] bit 0 makes edgpu_init create a non-blocking stream owned by the context (the `stream`
+ * argument is ignored); a thread calls edgpu_bind_thread once before it uses a context (cudaSetDevice). */
+int edgpu_bind_thread(edgpu_ctx *ctx);
+edgpu_ctx *edgpu_sector_context(const edgpu_sector *s);
 const char *edgpu_last_error(const edgpu_ctx *ctx);
 int edgpu_version(void);
 int edgpu_ns(const edgpu_ctx *ctx);                         /* Ns = (Nbath+1)*Norb, ED_SETUP.f90:99-101 */
