@@ -11,7 +11,7 @@ uint64_t edgpu_binom(int n, int k);
 int sector_map_kernel(edgpu_sector *s, int64_t first, int64_t count, uint64_t *d_out);
 int sector_map_check_kernel(edgpu_sector *s, unsigned long long *d_sum, unsigned long long *d_viol);
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst);
-int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st);
+int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st, double *flag = nullptr);
 int vec_fill_random(edgpu_sector *s, int uniform, uint64_t seed, double *dst);
 int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 int csr_build(edgpu_sector *s);
@@ -130,6 +130,7 @@ extern "C" int edgpu_init(const edgpu_params *p, int device, void *stream, edgpu
     if (cudaMalloc(&ctx->d_partials, sizeof(double) * kRedBlocks * 4) != cudaSuccess ||
         cudaMalloc(&ctx->d_dotpart, sizeof(double) * 16384) != cudaSuccess ||
         cudaMalloc(&ctx->d_scal, sizeof(double) * nscal) != cudaSuccess ||
+        cudaMalloc(&ctx->d_flag, sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scal, sizeof(double) * 64) != cudaSuccess) {
         delete ctx;
         return edgpu_fail(nullptr, "edgpu_init: scratch allocation failed");
@@ -159,7 +160,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
     delete ctx;
     return 0;
 }
@@ -377,6 +378,7 @@ extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cpl
         }
     }
     CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)s->nalloc, ctx->stream));        // pad columns stay zero
+    if (is_cplx) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(double), ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[0], ctx->stream));                                    // order after earlier work
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
     int k = 0;
@@ -388,10 +390,15 @@ extern "C" int edgpu_vec_upload(edgpu_vec *v, const double *host, int32_t is_cpl
                                       cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        if (int rc = vec_convert_rows(s, is_cplx ? 1 : 0, r0, r1, ctx->d_stage[b], v->d, ctx->stream)) return rc;
+        if (int rc = vec_convert_rows(s, is_cplx ? 1 : 0, r0, r1, ctx->d_stage[b], v->d, ctx->stream, is_cplx ? ctx->d_flag : nullptr)) return rc;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[b], ctx->stream));
     }
+    double bad = 0.0;
+    if (is_cplx) CUDA_TRY(ctx, cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the vectors of this path are real (ed_mode=normal, real Hloc: H is real symmetric); a complex(8) start vector whose
+    // imaginary part is not zero would silently lose it
+    if (bad != 0.0) return edgpu_fail(ctx, "edgpu_vec_upload: the complex vector has a non-zero imaginary part (the device vectors of this path are real; use edgpu_hxv for complex operands)");
     return 0;
 }
 

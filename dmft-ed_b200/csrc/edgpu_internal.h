@@ -131,6 +131,7 @@ struct edgpu_ctx {
     double *d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaStream_t copy_stream = nullptr;
+    double *d_flag = nullptr;               // edgpu_vec_upload: set by the conversion kernel when an imaginary part is not zero
     bool own_stream = false;                // edgpu_params.reserved[2] bit 0: the context created its (non-blocking) stream
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     EdComm *comm = nullptr;            // set by edgpu_comm_init: reductions of sharded sectors are summed over the ranks

@@ -99,7 +99,10 @@ __device__ __forceinline__ double fldg64(const double *p)
 // spills (local memory has no L1 to live in next to 226 KB of shared memory: every spill reload is an L2 round trip, which
 // made the 12-warp / 168-register build latency-bound); short fibers: 16 warps, 128 registers.
 #ifndef EDGPU_FIB_YW
-#define EDGPU_FIB_YW 0            // y loads in flight per unit (0 = all of them up front)
+#define EDGPU_FIB_YW 8            // up pass: y loads in flight per unit (0 = all of them up front)
+#endif
+#ifndef EDGPU_FIB_YD
+#define EDGPU_FIB_YD 4            // up pass: pairs between the arithmetic of a pair and its "+ y, store" stage
 #endif
 #ifndef EDGPU_FIB_NC_BIG
 #define EDGPU_FIB_NC_BIG 224
@@ -213,10 +216,14 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         const uint32_t own = img4 + oE, ownO = img4 + oO;
         double *yE = yband4 + (q2 ? Ty + 2u : Ty), *yO = yband4 + (q2 ? Ty + 16u : Ty + 2u);
         constexpr int P_LO = OUT_LO / 2, P_HI = (OUT_HI + 1) / 2, NPR = P_HI - P_LO;
-        // y += ... : the pass-1 result (H_dw x) of the unit's pairs comes through a rolling window of W loads in flight
+        // y += ... : the pass-1 result (H_dw x) comes through a window of W loads in flight, and the "+ y, store" stage of a
+        // pair runs D pairs BEHIND its arithmetic (results wait in `pend`): the first loads of a unit then have the unit's
+        // set-up plus D pairs of arithmetic to arrive -- with the add right behind the arithmetic the L2 latency of each
+        // batch of loads was exposed (50 % of the stall samples of the fiber bodies sat on three DADDs per unit).
         // (the producer has pulled the y band into L2 together with the x image)
-        constexpr int W = (EDGPU_FIB_YW) > 0 && (EDGPU_FIB_YW) < NPR ? (EDGPU_FIB_YW) : NPR;
-        double2 yw[W];
+        constexpr int D = (EDGPU_FIB_YD) < NPR ? (EDGPU_FIB_YD) : NPR;
+        constexpr int W = (EDGPU_FIB_YW) > 0 && (EDGPU_FIB_YW) < NPR ? ((EDGPU_FIB_YW) > D ? (EDGPU_FIB_YW) : D) : NPR;
+        double2 yw[W], pend[D];
         auto yaddr = [&](auto kk) -> double * {
             constexpr int K = decltype(kk)::value;
             return ((K & 3) == 0 ? yE : yO) + (K >> 2) * 16;
@@ -242,9 +249,27 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         const int nimp = __popc(impbits) + PART;
         const double dg = dgbase + eo + xt + A.cst.pair_e * (double)(nimp * (nimp - 1) / 2);
         const double sig = neg ? -1.0 : 1.0;
+        // second stage of pair F: add the pass-1 result, <x, y>, store; its window slot goes to pair F + W
+        auto finish = [&](auto ff) {
+            constexpr int F2 = decltype(ff)::value, K = 2 * (P_LO + F2);
+            constexpr bool do0 = K >= OUT_LO && K < OUT_HI, do1 = K + 1 >= OUT_LO && K + 1 < OUT_HI;
+            const double2 xo = flds128(((K & 3) == 0 ? own : ownO) + (uint32_t)(K >> 2) * (uint32_t)MT);
+            const double2 yo = yw[F2 % W];
+            if constexpr (F2 + W < NPR) yw[F2 % W] = fldg128(yaddr(std::integral_constant<int, 2 * (P_LO + F2 + W)>{}));
+            double r0 = 0.0, r1 = 0.0;
+            if constexpr (do0) { r0 = yo.x + pend[F2 % D].x; dsum = fma(xo.x, r0, dsum); }
+            if constexpr (do1) { r1 = yo.y + pend[F2 % D].y; dsum = fma(xo.y, r1, dsum); }
+            // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
+            double *yp = yaddr(std::integral_constant<int, K>{});
+            if constexpr (do0 && do1) fstg128(yp, r0, r1);
+            else if constexpr (do0 && K + 1 >= D0) fstg128(yp, r0, 0.0);        // last pair of an odd fiber: the pad stays zero
+            else if constexpr (do0) yp[0] = r0;
+            else if constexpr (do1) yp[1] = r1;
+        };
         fib::static_for<NPR>([&](auto jj) {
             constexpr int J = decltype(jj)::value, K = 2 * (P_LO + J);
             constexpr bool do0 = K >= OUT_LO && K < OUT_HI, do1 = K + 1 >= OUT_LO && K + 1 < OUT_HI;
+            if constexpr (J >= D) finish(std::integral_constant<int, J - D>{});
             const uint32_t rel = (uint32_t)(K >> 2) * (uint32_t)MT;
             const double2 xo = flds128(((K & 3) == 0 ? own : ownO) + rel);
             double g0 = 0.0, g1 = 0.0;
@@ -254,26 +279,18 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
                 if (do0) g0 = fma(amp[s], v.x, g0);
                 if (do1) g1 = fma(amp[s], v.y, g1);
             }
-            const double2 yo = yw[J % W];
-            if constexpr (J + W < NPR) yw[J % W] = fldg128(yaddr(std::integral_constant<int, 2 * (P_LO + J + W)>{}));
-            double r0 = 0.0, r1 = 0.0;
+            double c0 = 0.0, c1 = 0.0;
             if constexpr (do0) {
                 const double in0 = fib::out<NB, M0, K, IN_LO>(in, A.cst.v0);
-                r0 = yo.x + fma(dg + A.cst.e0[COFF + K], xo.x, fma(sig, in0, PART == 0 ? g0 : -g0));
-                dsum = fma(xo.x, r0, dsum);
+                c0 = fma(dg + A.cst.e0[COFF + K], xo.x, fma(sig, in0, PART == 0 ? g0 : -g0));
             }
             if constexpr (do1) {
                 const double in1 = fib::out<NB, M0, K + 1, IN_LO>(in, A.cst.v0);
-                r1 = yo.y + fma(dg + A.cst.e0[COFF + K + 1], xo.y, fma(sig, in1, PART == 0 ? g1 : -g1));
-                dsum = fma(xo.y, r1, dsum);
+                c1 = fma(dg + A.cst.e0[COFF + K + 1], xo.y, fma(sig, in1, PART == 0 ? g1 : -g1));
             }
-            // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
-            double *yp = yaddr(std::integral_constant<int, K>{});
-            if constexpr (do0 && do1) fstg128(yp, r0, r1);
-            else if constexpr (do0 && K + 1 >= D0) fstg128(yp, r0, 0.0);        // last pair of an odd fiber: the pad stays zero
-            else if constexpr (do0) yp[0] = r0;
-            else if constexpr (do1) yp[1] = r1;
+            pend[J % D] = make_double2(c0, c1);
         });
+        fib::static_for<D>([&](auto tt) { finish(std::integral_constant<int, NPR - D + decltype(tt)::value>{}); });
     }
 }
 
@@ -378,6 +395,8 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                     const char *px = reinterpret_cast<const char *>(A.x + tn.off);
                     for (int ofs = 0; ofs < tn.bytes; ofs += 32768)
                         fbulk_prefetch_l2(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768));
+                    // (pulling the y band of the next tile in as well was measured SLOWER: 1.69 against 1.61 ms -- four
+                    // 157 KB images per SM, 93 MB in all, no longer fit the L2 next to the write-back traffic)
                 }
                 ne[s]++; nfb[s]++;
                 if (two) ne[1]++;

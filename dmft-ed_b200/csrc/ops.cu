@@ -16,7 +16,7 @@ int vec_scale(edgpu_ctx *ctx, double *v, double alpha, int64_t n);
 __global__ void __launch_bounds__(256)
 k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, VAddr va,
           const uint32_t *__restrict__ r2i_up, const uint32_t *__restrict__ r2i_dw,
-          const double *__restrict__ src, double *__restrict__ dst)
+          const double *__restrict__ src, double *__restrict__ dst, double *__restrict__ flag)
 {
     // reference rows [rd_begin, rd_end); the reference-side array starts at row rd_begin (chunked transfers)
     const int64_t ru = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,7 +28,10 @@ k_convert(int mode, int64_t dim_up, int64_t rd_begin, int64_t rd_end, VAddr va,
         // iint < 0: the element belongs to a pair tile of another rank (sharded vectors): nothing to import, zero on export
         switch (mode) {
         case 0: if (iint >= 0) dst[iint] = src[iref]; break;
-        case 1: if (iint >= 0) dst[iint] = src[2 * iref]; break;
+        case 1:
+            if (iint >= 0) dst[iint] = src[2 * iref];
+            if (flag && src[2 * iref + 1] != 0.0) *flag = 1.0;       // this path is real (ed_mode=normal): reported by the caller
+            break;
         case 2: dst[iref] = iint >= 0 ? src[iint] : 0.0; break;
         case 3: dst[2 * iref] = iint >= 0 ? src[iint] : 0.0; dst[2 * iref + 1] = 0.0; break;
         case 4: if (iint >= 0) dst[iint] = src[2 * iref + 1]; break;
@@ -43,17 +46,17 @@ static dim3 grid2d(const edgpu_sector *s) {
 
 int vec_convert(edgpu_sector *s, int mode, const double *src, double *dst)
 {
-    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, 0, s->dim_dw, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst);
+    k_convert<<<grid2d(s), 256, 0, s->ctx->stream>>>(mode, s->dim_up, 0, s->dim_dw, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst, nullptr);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
 
 // the same for reference rows [rd0, rd1) only; the reference-side array is the chunk holding just those rows
-int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st)
+int vec_convert_rows(edgpu_sector *s, int mode, int64_t rd0, int64_t rd1, const double *src, double *dst, cudaStream_t st, double *flag)
 {
     if (rd1 <= rd0) return 0;
     dim3 grid((unsigned)((s->dim_up + 255) / 256), (unsigned)std::min<int64_t>(rd1 - rd0, 32768));
-    k_convert<<<grid, 256, 0, st>>>(mode, s->dim_up, rd0, rd1, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst);
+    k_convert<<<grid, 256, 0, st>>>(mode, s->dim_up, rd0, rd1, sector_vaddr(s), s->up->ref2int, s->dw->ref2int, src, dst, flag);
     CUDA_TRY(s->ctx, cudaGetLastError());
     return 0;
 }
@@ -252,6 +255,9 @@ extern "C" int edgpu_observables(edgpu_sector *s, const edgpu_vec *gs, double pe
     double *d_rows = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&d_rows, sizeof(double) * (size_t)s->dim_dw * nimp));
     const unsigned nb = (unsigned)(s->dim_dw < 4096 ? s->dim_dw : 4096);
+    // [nimp][256] doubles of dynamic shared memory: 64 KB for Norb = 5, above the 48 KB a kernel gets without opting in
+    if (sizeof(double) * 256 * nimp > 48 * 1024)
+        CUDA_TRY(ctx, cudaFuncSetAttribute((const void *)k_obs_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 256 * nimp)));
     k_obs_rows<<<nb, 256, sizeof(double) * 256 * nimp, ctx->stream>>>(norb, s->dim_up, s->dim_dw, sector_vaddr(s), s->up->cfg, gs->d, d_rows);
     CUDA_TRY(ctx, cudaGetLastError());
     std::vector<double> rows((size_t)s->dim_dw * nimp);

@@ -159,6 +159,14 @@ def test_hxv_rejects_bad_input(edb, oracle):
         s.hxv_host(np.zeros(s.dim + 1, dtype=complex))
     with pytest.raises(edb.EdgpuError):
         ctx.sector(6, 0)
+    # the device vectors are real: a complex(8) vector keeps its real part only if the imaginary part is exactly zero
+    z = rng.standard_normal(s.dim) + 0j
+    v = s.vec().upload(z)
+    assert np.array_equal(v.download(), z.real)
+    z[s.dim // 2] += 1e-30j
+    with pytest.raises(edb.EdgpuError, match="non-zero imaginary part"):
+        v.upload(z)
+    v.free()
     hl = np.zeros((1, 1, 1, 1), dtype=complex)
     hl[0, 0, 0, 0] = 1j
     with pytest.raises(edb.EdgpuError, match="complex impHloc"):
