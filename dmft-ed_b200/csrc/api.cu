@@ -246,8 +246,10 @@ static int sector_build_impl(edgpu_ctx *ctx, int32_t nup, int32_t ndw, int rank,
     // pair-tile layout + fiber kernels (hxv_fiber.cu): hxv_kernel = 3 forces them, auto takes them for large sectors;
     // a sharded sector (nranks > 1) exists only in that layout
     // reserved[1] bit 0: the caller will store H (ed_sparse_H=T -> CSR), which needs the single-tile layout
+    // (auto on ONE GPU: Norb = 2 only -- the Norb = 3 blocks read their slot tables from global memory and half of their tiles
+    // take both pipeline slots; measured on Ns=18: 45.6 ms against 37.9 ms of the round-1 tile kernels)
     const bool want_pairs = ctx->par.hxv_kernel == 3 || nranks > 1 ||
-                            (ctx->par.hxv_kernel == 0 && s->dim >= (1ll << 21) && !(ctx->par.reserved[1] & 1));
+                            (ctx->par.hxv_kernel == 0 && s->dim >= (1ll << 21) && !(ctx->par.reserved[1] & 1) && h.norb == 2);
     if (want_pairs && pair_layout_supported(s)) {
         if (int rc = pair_layout_build(s, rank, nranks)) { delete s; return rc; }
     } else if (ctx->par.hxv_kernel == 3 || nranks > 1) {

@@ -111,8 +111,10 @@ __device__ __forceinline__ double fldg64(const double *p)
 #ifndef EDGPU_FIB_NC_DW
 #define EDGPU_FIB_NC_DW 352
 #endif
-template <int NL> struct FibCfg { static constexpr int NC = (NL >= 7) ? EDGPU_FIB_NC_BIG : 480; static constexpr int NT = NC + 32; };
-template <int NL> struct FibCfgDw { static constexpr int NC = (NL >= 7) ? EDGPU_FIB_NC_DW : 480; static constexpr int NT = NC + 32; };
+// 6 levels per star (Norb = 3, Nbath = 5: up to 12 gather slots per fiber): 12 warps / 168 registers in both passes -- the
+// 16-warp build spilled 136 bytes (Ns=18: 50.1 -> 45.6 ms)
+template <int NL> struct FibCfg { static constexpr int NC = NL >= 7 ? EDGPU_FIB_NC_BIG : NL == 6 ? EDGPU_FIB_NC_DW : 480; static constexpr int NT = NC + 32; };
+template <int NL> struct FibCfgDw { static constexpr int NC = NL >= 6 ? EDGPU_FIB_NC_DW : 480; static constexpr int NT = NC + 32; };
 
 // HS variants (gather slots unrolled per fiber): exact for the long fibers, where every dummy slot costs 18 LDS + 36 DFMA
 template <int NL> struct FibHS { static constexpr int n = NL >= 7 ? 4 : 3; };
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                 // (once the own image has landed, so that the two do not compete), the exposed fill then runs at L2 speed
                 if (!HALF && i + 1 < myn && tn.bytes > A.slot && !(A.dbg & 2)) {
                     fmbar_wait_backoff(bfull + 8 * s, (uint32_t)nfb[s] & 1u);
-                    const char *px = reinterpret_cast<const char *>(A.x + tn.off);
+                    const char *px = reinterpret_cast<const char *>(((A.dbg & 8) ? A.y : A.x) + tn.off);
                     for (int ofs = 0; ofs < tn.bytes; ofs += 32768)
                         fbulk_prefetch_l2(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768));
                     // (pulling the y band of the next tile in as well was measured SLOWER: 1.69 against 1.61 ms -- four

@@ -560,7 +560,7 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
     FibArgs A;
     memset(&A, 0, sizeof(A));
     A.pairs = P.d_pairs; A.x = x; A.y = y; A.impmask = (1u << ctx->ham.norb) - 1u; A.norb = ctx->ham.norb; A.slot = P.slot;
-    A.dbg = (ctx->par.reserved[0] >> 13) & 3;
+    A.dbg = ((ctx->par.reserved[0] >> 13) & 3) | (((ctx->par.reserved[0] >> 16) & 1) << 3);
     A.e_dw = s->dw->ediag; A.cfg_dw = s->dw->cfg; A.xtab = ctx->d_xtab;
     PairGenArgs G{};
     G.pairs = P.d_pairs; G.blk_u = FU.d_blocks; G.blk_d = FD.d_blocks;
