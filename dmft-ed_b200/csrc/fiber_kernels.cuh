@@ -6,6 +6,15 @@
 // ------------------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------------------
+#ifndef EDGPU_FIB_EVICT
+#define EDGPU_FIB_EVICT 1          // streamed operands (x images, y stores) leave L2 first: prefetched bands survive until they are used
+#endif
+__device__ __forceinline__ uint64_t fpolicy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void fmbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void fmbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void fmbar_expect_tx_only(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -50,6 +59,28 @@ __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void *src, uint32_
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#ifndef EDGPU_FIB_PFLAST
+#define EDGPU_FIB_PFLAST 0         // L2 prefetches of the up pass (y band, next two-slot x image) with the evict_last priority
+#endif
+__device__ __forceinline__ uint64_t fpolicy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fbulk_prefetch_l2_hint(const void *src, uint32_t bytes, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fbulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ftma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void ftma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -81,6 +112,10 @@ __device__ __forceinline__ double flds64(uint32_t addr)
 __device__ __forceinline__ void fstg128(double *p, double a, double b)
 {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void fstg128_hint(double *p, double a, double b, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
 }
 __device__ __forceinline__ double2 fldg128(const double *p)
 {
@@ -204,7 +239,7 @@ struct FiberMeta {
 // MT: bytes per micro-tile of the IMAGE (128: bands of 4 rows; 64: half bands of 2 rows); y is always in 128-byte micro-tiles.
 template <int NL, int M0, int HS, int PART, int MT>
 __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, int nslot, double eo, int impbits, int neg, uint32_t img4 /* image + r4*32 */,
-                                         int o, int d0p, double dgbase, double xt, double *yband4 /* band + r4*4 */, double &dsum)
+                                         int o, int d0p, double dgbase, double xt, double *yband4 /* band + r4*4 */, double &dsum, uint64_t spol)
 {
     constexpr int NB = NL - 1, D0 = fib::cbinom(NL, M0), A0 = fib::cbinom(NB, M0), NP = (D0 + 1) / 2, COFF = fib::ccoff(NL, M0);
     constexpr int IN_LO = PART == 0 ? (A0 & ~1) : 0, IN_HI = PART == 0 ? 2 * NP : ((A0 + 1) & ~1), NIN = IN_HI - IN_LO;
@@ -263,7 +298,7 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
             if constexpr (do1) { r1 = yo.y + pend[F2 % D].y; dsum = fma(xo.y, r1, dsum); }
             // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
             double *yp = yaddr(std::integral_constant<int, K>{});
-            if constexpr (do0 && do1) fstg128(yp, r0, r1);
+            if constexpr (do0 && do1) { if (EDGPU_FIB_EVICT) fstg128_hint(yp, r0, r1, spol); else fstg128(yp, r0, r1); }
             else if constexpr (do0 && K + 1 >= D0) fstg128(yp, r0, 0.0);        // last pair of an odd fiber: the pad stays zero
             else if constexpr (do0) yp[0] = r0;
             else if constexpr (do1) yp[1] = r1;
@@ -357,6 +392,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             int ne[2] = {0, 0}, nfb[2] = {0, 0}, pos = 0;        // nfb[s]: completed uses of full barrier s
             FibTile t = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
             FibBlockDev bt = A.blk_f[t.blk];
+            const uint64_t pol = fpolicy_evict_first(), plast = fpolicy_evict_last();
             for (int i = 0; i < myn; i++) {
                 FibTile tn = t;
                 if (i + 1 < myn) tn = A.tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
@@ -376,11 +412,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                     const char *src = reinterpret_cast<const char *>(A.x + t.off);
                     for (int ofs = 0; ofs < t.bytes; ofs += 32768) {
                         const int n = t.bytes - ofs < 32768 ? t.bytes - ofs : 32768;
-                        fbulk_g2s(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s);
+                        if (EDGPU_FIB_EVICT) fbulk_g2s_hint(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s, pol);
+                        else fbulk_g2s(dst + (uint32_t)ofs, src + ofs, (uint32_t)n, bfull + 8 * s);
                     }
                     const char *py = reinterpret_cast<const char *>(A.y + t.off);
                     for (int ofs = 0; ofs < t.bytes; ofs += 32768)
-                        fbulk_prefetch_l2(py + ofs, (uint32_t)(t.bytes - ofs < 32768 ? t.bytes - ofs : 32768));
+                        { if (EDGPU_FIB_PFLAST) fbulk_prefetch_l2_hint(py + ofs, (uint32_t)(t.bytes - ofs < 32768 ? t.bytes - ofs : 32768), plast); else fbulk_prefetch_l2(py + ofs, (uint32_t)(t.bytes - ofs < 32768 ? t.bytes - ofs : 32768)); }
                 }
                 // every consumer has finished tile i-2 (or later) here: ring entry (i+1) & 3 = (i-3) & 3 is free.  The entry is
                 // written while the copies fly and published by the (release) arrive that lets full(i) complete.
@@ -394,9 +431,12 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                 // (once the own image has landed, so that the two do not compete), the exposed fill then runs at L2 speed
                 if (!HALF && i + 1 < myn && tn.bytes > A.slot && !(A.dbg & 2)) {
                     fmbar_wait_backoff(bfull + 8 * s, (uint32_t)nfb[s] & 1u);
-                    const char *px = reinterpret_cast<const char *>(((A.dbg & 8) ? A.y : A.x) + tn.off);
+                    const char *px = reinterpret_cast<const char *>(A.x + tn.off), *py = reinterpret_cast<const char *>(A.y + tn.off);
                     for (int ofs = 0; ofs < tn.bytes; ofs += 32768)
-                        fbulk_prefetch_l2(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768));
+                        { if (EDGPU_FIB_PFLAST) fbulk_prefetch_l2_hint(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768), plast); else fbulk_prefetch_l2(px + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768)); }
+                    if (A.dbg & 8)
+                        for (int ofs = 0; ofs < tn.bytes; ofs += 32768)
+                            { if (EDGPU_FIB_PFLAST) fbulk_prefetch_l2_hint(py + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768), plast); else fbulk_prefetch_l2(py + ofs, (uint32_t)(tn.bytes - ofs < 32768 ? tn.bytes - ofs : 32768)); }
                     // (pulling the y band of the next tile in as well was measured SLOWER: 1.69 against 1.61 ms -- four
                     // 157 KB images per SM, 93 MB in all, no longer fit the L2 next to the write-back traffic)
                 }
@@ -409,6 +449,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
         return;
     }
     const int warp = tid >> 5, lane = tid & 31, rl = HALF ? (lane & 1) : (lane & 3);       // row of the image
+    const uint64_t spol = fpolicy_evict_first();
     double dsum = 0.0;
     int nfill0 = 0, nfill1 = 0, pos = 0, cur_blk = -1;
     bool stab = false;
@@ -483,8 +524,8 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
                         fib::static_for<FibHS<NL>::n>([&](auto hh) {
                             constexpr int H = fib_hs<NL>(decltype(hh)::value), HP = decltype(hh)::value == 0 ? 0 : fib_hs<NL>(decltype(hh)::value - 1);
                             if (wmax <= H && (decltype(hh)::value == 0 || wmax > HP)) {
-                                if (part == 0) fiber_up<NL, M0, H, 0, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
-                                else fiber_up<NL, M0, H, 1, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum);
+                                if (part == 0) fiber_up<NL, M0, H, 0, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum, spol);
+                                else fiber_up<NL, M0, H, 1, MT>(A, F, nslot, eo, impbits, neg, img4, o, F.stride, dgb, xt, yband4, dsum, spol);
                             }
                         });
                     }
@@ -570,6 +611,7 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
     if (tid >= NC) {
         if (tid == NC) {
             int ne[2] = {0, 0}, nfb[2] = {0, 0}, pos = 0;        // nfb[s]: completed uses of full barrier s
+            const uint64_t pol = fpolicy_evict_first();
             auto boxes = [&](const FibTile &t, const FibBlockDev &BD, auto &&fn) {
                 for (int g = 0; g < t.b; g++)
                     for (int b = 0; b < BD.nbox; b++) fn(g, b);
@@ -589,6 +631,7 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
                 boxes(t, BD, [&](int g, int b) {
                     const uint32_t d = dst + (uint32_t)g * sbytes + (uint32_t)b * (uint32_t)BD.BR * (uint32_t)(RS * 4);
                     if (HALF) ftma_load_4d(d, A.tmaps + t.pair, 2 * (t.half - 1), 0, t.a + g, b * BD.BR, bfull + 8 * s);
+                    else if (EDGPU_FIB_EVICT) ftma_load_3d_hint(d, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s, pol);
                     else ftma_load_3d(d, A.tmaps + t.pair, 0, t.a + g, b * BD.BR, bfull + 8 * s);
                 });
                 // see the up pass: the next two-slot strip goes to L2 while this one is computed on
