@@ -9,7 +9,7 @@
 #include <vector>
 #include "../../include/edgpu.h"
 
-#define EDGPU_VERSION 210
+#define EDGPU_VERSION 211
 
 // ---- error plumbing: every C-ABI call returns int; message kept in the context (the reference `stop`s) ----
 struct edgpu_ctx;

@@ -59,6 +59,9 @@ __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void *src, uint32_
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#ifndef EDGPU_FIB_YPF
+#define EDGPU_FIB_YPF 0            // up pass: every lane prefetches the y sectors of its next unit into L2 (measured slower: 1.64 vs 1.58 ms)
+#endif
 #ifndef EDGPU_FIB_PFLAST
 #define EDGPU_FIB_PFLAST 0         // L2 prefetches of the up pass (y band, next two-slot x image) with the evict_last priority
 #endif
@@ -340,7 +343,7 @@ struct UpRing {                 // 64 bytes
     int off_lo, off_hi, bytes, blk;
     int a, b, q0, q1;
     int q2, q3, m0, d0p;        // m0 | half << 8
-    int nouter, C4, tab, nwf;
+    int nouter, C4, tab, nwf;   // nwf | A0 << 8 | D0 << 16
 };
 #define UPR(field) ((uint32_t)offsetof(UpRing, field))
 __device__ __forceinline__ int ring_ld(uint32_t addr)
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"((int)(uint32_t)(t.off & 0xffffffffll)), "r"((int)(t.off >> 32)), "r"(t.bytes), "r"(t.blk) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 16u), "r"(t.a), "r"(t.b), "r"(t.q0), "r"(t.q1) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 32u), "r"(t.q2), "r"(t.q3), "r"(BU.m0 | (t.half << 8)), "r"(BU.d0p) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 48u), "r"(BU.nouter), "r"(BU.C4), "r"(BU.tab), "r"(nwf) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 48u), "r"(BU.nouter), "r"(BU.C4), "r"(BU.tab), "r"(nwf | (BU.A0 << 8) | (BU.D0 << 16)) : "memory");
     };
     if (tid == 0) {
         fmbar_init(bfull, 1); fmbar_init(bfull + 8, 1);
@@ -481,12 +484,32 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             return true;
         };
         const int nb = (A.dbg & 1) ? 0 : ring_ld(re + UPR(b));
-        const int nwf2 = 2 * ring_ld(re + UPR(nwf));
+        const int nwfp = ring_ld(re + UPR(nwf));
+        const int nwf2 = 2 * (nwfp & 255);
         int g = 0, rem = warp;
         while (rem >= nwf2) { rem -= nwf2; g++; }
         double dgb = 0.0;
         uint32_t impd = 0;
         bool rowok = g < nb ? rowterms(g, dgb, impd) : false;
+        // L2 prefetch of the y sectors of ONE unit of this lane (row r4, fiber o, phase): issued a unit ahead -- for the first
+        // unit of a tile before the wait for the image -- so that the read-modify-write loads of the unit find their operand
+        // in L2 (the band prefetch of the producer is only a hint and does not keep up on the two-slot tiles)
+        auto ypf = [&](int gq, int remq, bool okq) {
+            if (!EDGPU_FIB_YPF || !okq || gq >= nb) return;
+            const int nwfq = nwf2 >> 1;
+            const int partq = remq >= nwfq ? 1 : 0;
+            const int fbq = (remq - partq * nwfq) * 32 + lane;
+            const int oq = HALF ? (fbq >> 1) : 2 * (fbq >> 3) + ((fbq >> 2) & 1);
+            if (oq >= ring_ld(re + UPR(nouter))) return;
+            const int A0q = (nwfp >> 8) & 255, D0q = (nwfp >> 16) & 255;
+            const int c0q = oq * ring_ld(re + UPR(d0p));
+            const int lo = c0q + (partq ? A0q : 0), hi = c0q + (partq ? D0q : A0q) - 1;
+            const int C4q = ring_ld(re + UPR(C4));
+            const int64_t toffq = (int64_t)(((uint64_t)(uint32_t)ring_ld(re + UPR(off_hi)) << 32) | (uint64_t)(uint32_t)ring_ld(re + UPR(off_lo)));
+            const double *yq = A.y + toffq + (int64_t)gq * C4q * 16 + r4 * 4;
+            for (int sq = lo >> 2; sq <= (hi >> 2); sq++) asm volatile("prefetch.global.L2 [%0];" ::"l"(yq + sq * 16));
+        };
+        ypf(g, rem, rowok);
         fmbar_wait_warp(bfull + 8 * s, (uint32_t)(s ? nfill1 : nfill0) & 1u);
         const uint32_t img0 = slot0 + (uint32_t)s * (uint32_t)A.slot + (uint32_t)rl * 32u;
         while (g < nb) {
@@ -497,6 +520,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
             uint32_t impn = impd;
             bool okn = rowok;
             if (gn != g && gn < nb) okn = rowterms(gn, dgn, impn);
+            ypf(gn, remn, okn);
             const int nwf = nwf2 >> 1;
             const int part = rem >= nwf ? 1 : 0;
             const int fb = (rem - part * nwf) * 32 + lane;
