@@ -59,6 +59,9 @@ __device__ __forceinline__ void fbulk_g2s(uint32_t dst, const void *src, uint32_
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#ifndef EDGPU_FIB_EVICT_DW
+#define EDGPU_FIB_EVICT_DW 0       // the same for the y stores of the down pass
+#endif
 #ifndef EDGPU_FIB_YPF
 #define EDGPU_FIB_YPF 0            // up pass: every lane prefetches the y sectors of its next unit into L2 (measured slower: 1.64 vs 1.58 ms)
 #endif
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(FibCfg<NL>::NT) k_fib_up(const __grid_constant
 // RS: bytes per row of the image (32: strips of 4 columns; 16: half strips of 2 columns)
 template <int NL, int M0, int HS, int PART, int RS>
 __device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, int nslot, int neg, uint32_t img8 /* image + c4*8 */, int o,
-                                         int d0r, double *ystrip4 /* strip + c4 */, int64_t bstride)
+                                         int d0r, double *ystrip4 /* strip + c4 */, int64_t bstride, uint64_t spol)
 {
     constexpr int NB = NL - 1, D0 = fib::cbinom(NL, M0), A0 = fib::cbinom(NB, M0), B0 = D0 - A0;
     constexpr int NIN = PART == 0 ? B0 : A0, NOUT = PART == 0 ? A0 : B0, IN0 = PART == 0 ? A0 : 0, OUT0 = PART == 0 ? 0 : A0;
@@ -608,7 +611,9 @@ __device__ __forceinline__ void fiber_dw(const FibArgs &A, const FiberMeta &F, i
 #pragma unroll
             for (int s = 0; s < HS; s++) g = fma(amp[s], flds64(sb[s] + (uint32_t)K * (uint32_t)RS), g);
             const double inr = fib::out<NB, M0, K, IN0>(in, A.cst.v0);
-            Q[K & 3][(int64_t)(K >> 2) * bstride] = fma(sig, inr, PART == 0 ? g : -g);
+            const double val = fma(sig, inr, PART == 0 ? g : -g);
+            if (EDGPU_FIB_EVICT_DW) asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(Q[K & 3] + (int64_t)(K >> 2) * bstride), "d"(val), "l"(spol) : "memory");
+            else Q[K & 3][(int64_t)(K >> 2) * bstride] = val;
         });
     }
 }
@@ -676,6 +681,7 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
     int nfill0 = 0, nfill1 = 0, pos = 0, cur_blk = -1;
     bool stab = false;
     const int warp = tid >> 5, lane = tid & 31, cl = HALF ? (lane & 1) : (lane & 3);         // column of the image
+    const uint64_t spol = fpolicy_evict_first();
     int b_m0 = 0, b_d0r = 0, b_nouter = 0, b_tab = 0, now = 1;
     uint32_t sbytes = 0;
     FibTile tnext = myn > 0 ? A.tiles[blockIdx.x] : FibTile{};
@@ -720,8 +726,8 @@ __global__ void __launch_bounds__(FibCfgDw<NL>::NT) k_fib_dw(const __grid_consta
                         fib::static_for<FibHS<NL>::n>([&](auto hh) {
                             constexpr int H = fib_hs<NL>(decltype(hh)::value), HP = decltype(hh)::value == 0 ? 0 : fib_hs<NL>(decltype(hh)::value - 1);
                             if (wmax <= H && (decltype(hh)::value == 0 || wmax > HP)) {
-                                if (part == 0) fiber_dw<NL, M0, H, 0, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
-                                else fiber_dw<NL, M0, H, 1, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride);
+                                if (part == 0) fiber_dw<NL, M0, H, 0, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride, spol);
+                                else fiber_dw<NL, M0, H, 1, RS>(A, F, nslot, neg, img8, o, b_d0r, ystrip4, bstride, spol);
                             }
                         });
                     }
