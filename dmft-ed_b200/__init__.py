@@ -426,6 +426,8 @@ def default_input(**kw) -> ed_input:
                 inp.uloc[i] = u
         elif k == "lanc_method":
             inp.lanc_method = {"arpack": 0, "lanczos": 1}.get(v, v)
+        elif k == "workers":                 # host worker threads of ed_solve (ed_input.reserved[2]; 0 = default 4)
+            inp.reserved[2] = int(v)
         else:
             setattr(inp, k, v)
     return inp

@@ -68,7 +68,9 @@ void pool_release(edgpu_ctx *ctx, void *p)
     if (it == ctx->pool_size.end()) { cudaFree(p); return; }
     ctx->pool_free.emplace(it->second, p);
     ctx->pool_held += it->second;
-    const size_t cap = ctx->mem_bytes > 0 ? (size_t)ctx->mem_bytes / 3 : ((size_t)32 << 30);
+    // cached (free) buffers of ONE context: an eighth of the device memory -- several contexts share a device (the worker
+    // threads of ed_solve), and a context can only trim its own cache when an allocation fails
+    const size_t cap = ctx->mem_bytes > 0 ? (size_t)ctx->mem_bytes / 8 : ((size_t)16 << 30);
     if (ctx->pool_held > cap) pool_trim(ctx, cap / 2);
 }
 

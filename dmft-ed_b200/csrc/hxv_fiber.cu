@@ -97,6 +97,9 @@ static int build_fib_spin(edgpu_ctx *ctx, SpinBasis *b)
         fb.d0r = fb.D0 | 1;
         fb.d0p = fb.D0 + ((6 - (fb.D0 & 3)) & 3);                 // smallest value >= D0 that is 2 (mod 4)
         if ((fb.d0p & 3) != 2 || fb.d0p < fb.D0) return edgpu_fail(ctx, "fiber layout: bad column padding");
+        // test hook (bit 17): the smallest multiple of 4 instead -- fewer pad columns (Norb = 3: 16 instead of 18 for 15
+        // configurations, 20 instead of 22), paid with 2-way bank conflicts of the neighbour-fiber loads
+        if (ctx->par.reserved[0] & 131072) fb.d0p = (fb.D0 + 3) & ~3;
         fb.R = fb.nouter * fb.d0r; fb.R4 = (fb.R + 3) / 4;
         fb.C = fb.nouter * fb.d0p; fb.C4 = (fb.C + 3) / 4;
         fb.nbox = (fb.R4 + 255) / 256;

@@ -64,6 +64,30 @@ def test_ed_solve_cfg1_full_scan(oracle, edb):
         sol.close()
 
 
+def test_ed_solve_worker_threads_do_not_change_the_result(edb):
+    """The sectors of the scan and the GF chains are dealt over host worker threads (contexts / streams of their own): the
+    state list (order included), the chains and every function must equal the serial solve; only the order of the additions
+    into G differs."""
+    kw = dict(Norb=2, Nbath=3, uloc=[2.0, 2.0], ust=1.2, jh=0.2, lanc_method="lanczos", lanc_nstates_sector=1, Lmats=64, Lreal=64,
+              lanc_dim_threshold=64, chispin_flag=1, chidens_flag=1)
+    res = []
+    for w in (1, 3, 4):
+        sol = edb.Solver(edb.default_input(workers=w, **kw))
+        sol.solve()
+        st, zeta, egs = sol.states()
+        res.append((st, zeta, egs, sol.chains(), sol.gimp_matsubara(), sol.sigma_matsubara(), sol.dens(), sol.docc(), sol.spinchi()[0], sol.denschi()[0]))
+        sol.close()
+    ref = res[0]
+    for r in res[1:]:
+        assert [(s[1], s[2]) for s in r[0]] == [(s[1], s[2]) for s in ref[0]] and r[1] == ref[1]
+        assert np.allclose([s[0] for s in r[0]], [s[0] for s in ref[0]], rtol=0, atol=1e-13) and abs(r[2] - ref[2]) < 1e-13
+        assert [(c["istate"], c["iorb"], c["ispin"], c["isign"], c["nlanc"]) for c in r[3]] == [(c["istate"], c["iorb"], c["ispin"], c["isign"], c["nlanc"]) for c in ref[3]]
+        for a, b in zip(r[3], ref[3]):
+            assert np.array_equal(a["alfa"], b["alfa"]) and np.array_equal(a["beta"], b["beta"])      # same kernels, same order: bit-equal
+        for k in range(4, 10):
+            assert np.abs(np.asarray(r[k]) - np.asarray(ref[k])).max() < 1e-12
+
+
 def test_ed_solve_two_orbitals_hund(oracle, edb):
     p, ref, sol = run_pair(oracle, edb, Norb=2, Nbath=2, uloc=(2.0, 2.0), ust=1.5, jh=0.25, lanc_dim_threshold=64)
     compare(p, ref, sol)
