@@ -161,6 +161,8 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     ctx->bases.clear();
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto &c : ctx->arena) cudaFree(c.first);
+    ctx->arena.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_dotpart); cudaFree(ctx->d_scal); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_scal); cudaFree(ctx->d_flush); cudaFree(ctx->d_xtab);
     delete ctx;

@@ -131,6 +131,10 @@ struct edgpu_ctx {
     double *d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaStream_t copy_stream = nullptr;
+    // arena of the stored Lanczos basis (edgpu_lanczos_gs): chunks that live as long as the context, carved anew by every
+    // call -- one allocation per ~16 vectors of the largest sector instead of one per Lanczos vector and sector
+    std::vector<std::pair<void *, size_t>> arena;
+    size_t arena_bytes = 0;
     double *d_flag = nullptr;               // edgpu_vec_upload: set by the conversion kernel when an imaginary part is not zero
     bool own_stream = false;                // edgpu_params.reserved[2] bit 0: the context created its (non-blocking) stream
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};

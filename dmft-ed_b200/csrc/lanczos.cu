@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kRedThreads) k_dot_alpha(const double *__restr
     finalize_by_last_block(partials, gridDim.x, 2, nrm, out, ticket);
 }
 
-// w_new = u/nc - (bp/no) w_old - (a/nc) w_cur, written over w_old ; b = sqrt(sum w_new^2), one launch
-__global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict__ old, const double *__restrict__ u,
+// w_new = u/nc - (bp/no) w_old - (a/nc) w_cur, written to `out` (== old: in place) ; b = sqrt(sum w_new^2), one launch
+__global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(const double *old, double *out, const double *__restrict__ u,
                                                              const double *__restrict__ cur, const double *__restrict__ p_bprev,
                                                              const double *__restrict__ p_ncur, const double *__restrict__ p_nold,
                                                              const double *__restrict__ p_a, int64_t n, double *__restrict__ partials,
@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict_
     double acc = 0.0;
     // 16-byte accesses, two independent ones in flight per thread (the buffers are 256-byte aligned; the scalar loop takes an odd tail)
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
-    double2 *__restrict__ old2 = reinterpret_cast<double2 *>(old);
+    const double2 *old2 = reinterpret_cast<const double2 *>(old);
+    double2 *out2 = reinterpret_cast<double2 *>(out);
     const double2 *__restrict__ u2 = reinterpret_cast<const double2 *>(u), *__restrict__ cur2 = reinterpret_cast<const double2 *>(cur);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + stride < n2; i += 2 * stride) {
@@ -207,19 +208,19 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict_
         double2 ta, tb;
         ta.x = ua.x / nc - c_old * oa.x - c_cur * ca.x; ta.y = ua.y / nc - c_old * oa.y - c_cur * ca.y;
         tb.x = ub.x / nc - c_old * ob.x - c_cur * cb.x; tb.y = ub.y / nc - c_old * ob.y - c_cur * cb.y;
-        old2[i] = ta; old2[i + stride] = tb;
+        out2[i] = ta; out2[i + stride] = tb;
         acc += ta.x * ta.x; acc += ta.y * ta.y; acc += tb.x * tb.x; acc += tb.y * tb.y;
     }
     for (; i < n2; i += stride) {
         const double2 ua = u2[i], oa = old2[i], ca = cur2[i];
         double2 ta;
         ta.x = ua.x / nc - c_old * oa.x - c_cur * ca.x; ta.y = ua.y / nc - c_old * oa.y - c_cur * ca.y;
-        old2[i] = ta;
+        out2[i] = ta;
         acc += ta.x * ta.x; acc += ta.y * ta.y;
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const double t = u[n - 1] / nc - c_old * old[n - 1] - c_cur * cur[n - 1];
-        old[n - 1] = t;
+        out[n - 1] = t;
         acc += t * t;
     }
     block_store_partial(acc, partials + blockIdx.x);
@@ -227,6 +228,27 @@ __global__ void __launch_bounds__(kRedThreads) k_lanc_c_norm(double *__restrict_
 }
 
 __global__ void k_set_one(double *p) { *p = 1.0; }
+
+// out = sum_k c[k] * V_k (k ascending, the order of the axpy sequence it replaces): the Ritz vector from a stored Lanczos basis
+__global__ void __launch_bounds__(kRedThreads) k_ritz(const double *const *__restrict__ V, const double *__restrict__ c, int nvec,
+                                                      double *__restrict__ out, int64_t n)
+{
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k = 0; k < nvec; k++) {
+            const double2 v = reinterpret_cast<const double2 *>(V[k])[i];
+            const double ck = c[k];
+            acc.x += ck * v.x; acc.y += ck * v.y;
+        }
+        reinterpret_cast<double2 *>(out)[i] = acc;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int k = 0; k < nvec; k++) acc += c[k] * V[k][n - 1];
+        out[n - 1] = acc;
+    }
+}
 
 // last step of a reduction that was summed over the ranks (sharded sectors): mode 1: sqrt ; 2: / (*nrm)^2
 __global__ void k_fin(double *p, int mode, const double *__restrict__ nrm)
@@ -255,8 +277,10 @@ static int reset_scalars(edgpu_ctx *ctx)
 // One Lanczos step (iteration `iter`, 1-based) on unnormalised vectors: cur = w_iter (norm b_iter, 1 for iter 1),
 // old = w_{iter-1}, u = scratch.  d_b[k] holds blanc(k+1) (d_b[0] = 0), d_a[k] alanc(k+1).  On return w_{iter+1} lies in
 // `old`: the caller rotates (cur, old) -> (old, cur).
-static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, int iter, double *d_a, double *d_b)
+// one step; w_{k+1} goes to `out` (nullptr: over w_{k-1} in `old`, the rotating three-buffer form)
+static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, int iter, double *d_a, double *d_b, double *out = nullptr)
 {
+    if (!out) out = old;
     edgpu_ctx *ctx = s->ctx;
     const int64_t n = s->nalloc;
     const int nb = red_blocks(n);
@@ -282,7 +306,7 @@ static int lanczos_step(edgpu_sector *s, double *cur, double *old, double *u, in
     } else {
         k_dot_alpha<<<nb, kRedThreads, 0, ctx->stream>>>(cur, u, n, ctx->d_partials, p_ncur, d_a + (iter - 1), ticket);
     }
-    k_lanc_c_norm<<<nb, kRedThreads, 0, ctx->stream>>>(old, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials,
+    k_lanc_c_norm<<<nb, kRedThreads, 0, ctx->stream>>>(old, out, u, cur, p_bprev, p_ncur, p_nold, d_a + (iter - 1), n, ctx->d_partials,
                                                        d_b + iter, ticket, sh ? 0 : 1);
     if (sh) {
         if (int rc = comm_allreduce_sum(ctx, d_b + iter, 1)) return rc;
@@ -369,15 +393,62 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
         esave(nitermax + 2, 0.0), Z;
     int nlanc = 0;
 
+    // Stored basis: while the Lanczos vectors fit a budget (a twentieth of the device memory per context) every w_k goes to a
+    // buffer of its own instead of over w_{k-2}, and the Ritz vector is ONE pass over them -- the reference (and the fallback
+    // below) regenerates all of them in a second Lanczos run, which doubled the time of the sector scan.
+    const size_t vbytes = (sizeof(double) * (size_t)n + 255) & ~(size_t)255;
+    const size_t budget = ctx->mem_bytes > 0 ? (size_t)ctx->mem_bytes / 20 : ((size_t)8 << 30);
+    std::vector<double *> basis;                    // basis[k - 1] = w_k (unnormalised), k = 1, 2, ...
+    bool store = vbytes * 8 <= budget && !(ctx->par.reserved[0] & 262144);
+    auto drop_basis = [&]() { basis.clear(); };      // the arena keeps its chunks for the next sector
+    size_t a_chunk = 0, a_off = 0;
+    // next vector of the arena; false: the budget is spent (the caller falls back to the rotating buffers)
+    auto carve = [&](double **q) -> bool {
+        for (;;) {
+            if (a_chunk < ctx->arena.size()) {
+                auto &c = ctx->arena[a_chunk];
+                if (a_off + vbytes <= c.second) { *q = reinterpret_cast<double *>(static_cast<char *>(c.first) + a_off); a_off += vbytes; return true; }
+                a_chunk++; a_off = 0;
+                continue;
+            }
+            if (ctx->arena_bytes + vbytes > budget) {
+                // chunks of earlier, smaller sectors that cannot hold one vector of this one give their share back
+                bool freed = false;
+                for (size_t k = ctx->arena.size(); k-- > 0;)
+                    if (ctx->arena[k].second < vbytes) {
+                        if (!freed) cudaStreamSynchronize(ctx->stream);
+                        cudaFree(ctx->arena[k].first);
+                        ctx->arena_bytes -= ctx->arena[k].second;
+                        ctx->arena.erase(ctx->arena.begin() + k);
+                        if (k < a_chunk) a_chunk--;
+                        freed = true;
+                    }
+                if (!freed || ctx->arena_bytes + vbytes > budget) return false;
+            }
+            size_t want = std::max<size_t>(vbytes * 16, (size_t)256 << 20);
+            want = std::min(want, budget - ctx->arena_bytes);
+            want -= want % vbytes;
+            void *p = nullptr;
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+            ctx->arena.emplace_back(p, want);
+            ctx->arena_bytes += want;
+        }
+    };
+
     // ---- pass 1: tridiagonalise until the lowest Ritz value stops moving (:328-360) ----
     double *vin = w0, *vout = w1, *tmp = w2;
+    if (store) {
+        double *q = nullptr;
+        if (carve(&q)) { basis.push_back(q); vin = q; }
+        else store = false;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(vin, v0->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(vout, 0, sizeof(double) * (size_t)n, ctx->stream));
     if (int rc = reset_scalars(ctx)) return rc;
     if (int rc = normalise(s, vin)) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal, ctx->d_scal + kScalB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_scal[0] == 0.0) return edgpu_fail(ctx, "lanczos_plain_iteration: norm =0!!");
+    if (ctx->h_scal[0] == 0.0) { drop_basis(); return edgpu_fail(ctx, "lanczos_plain_iteration: norm =0!!"); }
     // The reference diagonalises the growing tridiagonal and tests |dE0| after EVERY step.  Small sectors are bound by
     // that host round trip, so the device runs kBatch steps ahead and the host then replays the reference's rule step
     // by step over the new (a, b) pairs: the stopping iteration is identical, at most kBatch - 1 steps are computed in
@@ -388,6 +459,21 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
     for (int iter0 = 1; iter0 <= nitermax && !stop; iter0 += kBatch) {
         const int nb = std::min(kBatch, nitermax - iter0 + 1);
         for (int k = 0; k < nb; k++) {
+            double *qn = nullptr;
+            if (store && !carve(&qn)) {
+                // out of budget: fall back to the rotating three buffers (and to the regenerating second pass)
+                CUDA_TRY(ctx, cudaMemcpyAsync(w0, vin, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+                if (vout != w1) CUDA_TRY(ctx, cudaMemcpyAsync(w1, vout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+                vin = w0; vout = w1;
+                drop_basis();
+                store = false;
+            }
+            if (store) {
+                basis.push_back(qn);
+                if (int rc = lanczos_step(s, vin, vout, tmp, iter0 + k, d_a, d_b, basis.back())) { drop_basis(); return rc; }
+                vout = vin; vin = basis.back();
+                continue;
+            }
             if (int rc = lanczos_step(s, vin, vout, tmp, iter0 + k, d_a, d_b)) return rc;     // (cur, old, scratch)
             double *t = vin; vin = vout; vout = t;
         }
@@ -412,13 +498,40 @@ extern "C" int edgpu_lanczos_gs(edgpu_sector *s, edgpu_vec *v0, int32_t nitermax
             }
         }
     }
-    if (nlanc == 0) return edgpu_fail(ctx, "edgpu_lanczos_gs: Lanczos broke down at the first step");
+    if (nlanc == 0) { drop_basis(); return edgpu_fail(ctx, "edgpu_lanczos_gs: Lanczos broke down at the first step"); }
     for (int i = 0; i < nlanc; i++) { diag[i] = alanc[i]; sub[i] = i > 0 ? blanc[i] : 0.0; }
     Z.assign((size_t)nlanc * nlanc, 0.0);
     for (int i = 0; i < nlanc; i++) Z[i + (size_t)nlanc * i] = 1.0;
     host_tql2(nlanc, diag.data(), sub.data(), Z.data());
     if (e0) *e0 = diag[0];
 
+    if (store) {
+        // ---- Ritz vector sum_k Z(k,1) v_k = sum_k Z(k,1)/b_k w_k from the stored basis (b_1 = 1) ----
+        std::vector<double> coef(nlanc);
+        for (int k = 1; k <= nlanc; k++) coef[k - 1] = Z[k - 1] / (k == 1 ? 1.0 : blanc[k - 1]);
+        void *d_tab = nullptr;
+        int rc = pool_alloc(ctx, (sizeof(double *) + sizeof(double)) * (size_t)nlanc, &d_tab);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(d_tab, basis.data(), sizeof(double *) * (size_t)nlanc, cudaMemcpyHostToDevice, ctx->stream);
+            double *d_coef = reinterpret_cast<double *>(reinterpret_cast<double **>(d_tab) + nlanc);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_coef, coef.data(), sizeof(double) * (size_t)nlanc, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                k_ritz<<<red_blocks(n), kRedThreads, 0, ctx->stream>>>(reinterpret_cast<const double *const *>(d_tab), d_coef, nlanc, v0->d, n);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);       // `coef`, `basis` are host sources of async copies
+            if (e != cudaSuccess) rc = edgpu_fail(ctx, "edgpu_lanczos_gs: %s", cudaGetErrorString(e));
+            pool_release(ctx, d_tab);
+        }
+        drop_basis();
+        if (rc) return rc;
+        if (int rc2 = normalise(s, v0->d)) return rc2;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (nlanc_out) *nlanc_out = nlanc;
+        if (alanc_out) for (int i = 0; i < nlanc; i++) alanc_out[i] = alanc[i];
+        if (blanc_out) for (int i = 0; i < nlanc; i++) blanc_out[i] = i > 0 ? blanc[i] : 0.0;
+        return 0;
+    }
     // ---- pass 2: regenerate the Lanczos vectors and accumulate the Ritz vector sum_k Z(k,1) v_k (:375-384,
     //      with Z(k,1) paired with the k-th basis vector) ----
     vin = w0; vout = w1; tmp = w2;
