@@ -123,9 +123,16 @@ __device__ __forceinline__ void fstg128_hint(double *p, double a, double b, uint
 {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
 }
+#ifndef EDGPU_FIB_NOYLD
+#define EDGPU_FIB_NOYLD 0          // measurement only (wrong results): the up pass does not load y / does not store y
+#endif
+#ifndef EDGPU_FIB_NOYST
+#define EDGPU_FIB_NOYST 0
+#endif
 __device__ __forceinline__ double2 fldg128(const double *p)
 {
     double2 v;
+    if (EDGPU_FIB_NOYLD) return make_double2(0.0, 0.0);
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
@@ -304,7 +311,8 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
             if constexpr (do1) { r1 = yo.y + pend[F2 % D].y; dsum = fma(xo.y, r1, dsum); }
             // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
             double *yp = yaddr(std::integral_constant<int, K>{});
-            if constexpr (do0 && do1) { if (EDGPU_FIB_EVICT) fstg128_hint(yp, r0, r1, spol); else fstg128(yp, r0, r1); }
+            if constexpr (EDGPU_FIB_NOYST) { if (r0 == 1.2345e300) yp[0] = r1; }
+            else if constexpr (do0 && do1) { if (EDGPU_FIB_EVICT) fstg128_hint(yp, r0, r1, spol); else fstg128(yp, r0, r1); }
             else if constexpr (do0 && K + 1 >= D0) fstg128(yp, r0, 0.0);        // last pair of an odd fiber: the pad stays zero
             else if constexpr (do0) yp[0] = r0;
             else if constexpr (do1) yp[1] = r1;
