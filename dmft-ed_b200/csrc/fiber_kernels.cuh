@@ -271,9 +271,9 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         // set-up plus D pairs of arithmetic to arrive -- with the add right behind the arithmetic the L2 latency of each
         // batch of loads was exposed (50 % of the stall samples of the fiber bodies sat on three DADDs per unit).
         // (the producer has pulled the y band into L2 together with the x image)
-        constexpr int D = (EDGPU_FIB_YD) < NPR ? (EDGPU_FIB_YD) : NPR;
-        constexpr int W = (EDGPU_FIB_YW) > 0 && (EDGPU_FIB_YW) < NPR ? ((EDGPU_FIB_YW) > D ? (EDGPU_FIB_YW) : D) : NPR;
-        double2 yw[W], pend[D];
+        constexpr int D = (EDGPU_FIB_YD) < NPR ? (EDGPU_FIB_YD) : NPR;          // 0: the add follows the arithmetic directly
+        constexpr int W = (EDGPU_FIB_YW) > 0 && (EDGPU_FIB_YW) < NPR ? ((EDGPU_FIB_YW) > D ? (EDGPU_FIB_YW) : (D > 0 ? D : 1)) : NPR;
+        double2 yw[W], pend[D > 0 ? D : 1];
         auto yaddr = [&](auto kk) -> double * {
             constexpr int K = decltype(kk)::value;
             return ((K & 3) == 0 ? yE : yO) + (K >> 2) * 16;
@@ -300,15 +300,15 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         const double dg = dgbase + eo + xt + A.cst.pair_e * (double)(nimp * (nimp - 1) / 2);
         const double sig = neg ? -1.0 : 1.0;
         // second stage of pair F: add the pass-1 result, <x, y>, store; its window slot goes to pair F + W
-        auto finish = [&](auto ff) {
+        auto finish = [&](auto ff, const double2 *xop) {
             constexpr int F2 = decltype(ff)::value, K = 2 * (P_LO + F2);
             constexpr bool do0 = K >= OUT_LO && K < OUT_HI, do1 = K + 1 >= OUT_LO && K + 1 < OUT_HI;
-            const double2 xo = flds128(((K & 3) == 0 ? own : ownO) + (uint32_t)(K >> 2) * (uint32_t)MT);
+            const double2 xo = xop ? *xop : flds128(((K & 3) == 0 ? own : ownO) + (uint32_t)(K >> 2) * (uint32_t)MT);
             const double2 yo = yw[F2 % W];
             if constexpr (F2 + W < NPR) yw[F2 % W] = fldg128(yaddr(std::integral_constant<int, 2 * (P_LO + F2 + W)>{}));
             double r0 = 0.0, r1 = 0.0;
-            if constexpr (do0) { r0 = yo.x + pend[F2 % D].x; dsum = fma(xo.x, r0, dsum); }
-            if constexpr (do1) { r1 = yo.y + pend[F2 % D].y; dsum = fma(xo.y, r1, dsum); }
+            if constexpr (do0) { r0 = yo.x + pend[D > 0 ? F2 % (D > 0 ? D : 1) : 0].x; dsum = fma(xo.x, r0, dsum); }
+            if constexpr (do1) { r1 = yo.y + pend[D > 0 ? F2 % (D > 0 ? D : 1) : 0].y; dsum = fma(xo.y, r1, dsum); }
             // a pair that straddles the imp=0 / imp=1 boundary (A0 odd): each phase stores its own element
             double *yp = yaddr(std::integral_constant<int, K>{});
             if constexpr (EDGPU_FIB_NOYST) { if (r0 == 1.2345e300) yp[0] = r1; }
@@ -320,7 +320,7 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
         fib::static_for<NPR>([&](auto jj) {
             constexpr int J = decltype(jj)::value, K = 2 * (P_LO + J);
             constexpr bool do0 = K >= OUT_LO && K < OUT_HI, do1 = K + 1 >= OUT_LO && K + 1 < OUT_HI;
-            if constexpr (J >= D) finish(std::integral_constant<int, J - D>{});
+            if constexpr (D > 0 && J >= D) finish(std::integral_constant<int, J - D>{}, nullptr);
             const uint32_t rel = (uint32_t)(K >> 2) * (uint32_t)MT;
             const double2 xo = flds128(((K & 3) == 0 ? own : ownO) + rel);
             double g0 = 0.0, g1 = 0.0;
@@ -339,9 +339,10 @@ __device__ __forceinline__ void fiber_up(const FibArgs &A, const FiberMeta &F, i
                 const double in1 = fib::out<NB, M0, K + 1, IN_LO>(in, A.cst.v0);
                 c1 = fma(dg + A.cst.e0[COFF + K + 1], xo.y, fma(sig, in1, PART == 0 ? g1 : -g1));
             }
-            pend[J % D] = make_double2(c0, c1);
+            pend[D > 0 ? J % (D > 0 ? D : 1) : 0] = make_double2(c0, c1);
+            if constexpr (D == 0) finish(jj, &xo);
         });
-        fib::static_for<D>([&](auto tt) { finish(std::integral_constant<int, NPR - D + decltype(tt)::value>{}); });
+        fib::static_for<D>([&](auto tt) { finish(std::integral_constant<int, NPR - D + decltype(tt)::value>{}, nullptr); });
     }
 }
 
