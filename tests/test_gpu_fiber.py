@@ -2,8 +2,9 @@
 
 debug flags: 16 = fiber kernels for every block they can take (also the tiny ones), 4 = thread-per-element pair kernels
 only, 0 = the production split (fiber kernels for blocks >= 256 configurations), +4096 = small pipeline slots so that the
-largest images take BOTH slots (the path of the 4900-configuration blocks of Ns=16), 1024 / 2048 = one pass by the
-thread-per-element kernels."""
+largest HALF images take BOTH slots (the path of the 8000-configuration blocks of Ns=18; the images below run as two-slot
+full tiles like the 4900-configuration blocks of Ns=16), +32768 = every image above one slot as half tiles (2 rows of a band /
+2 columns of a strip through tensor maps), 1024 / 2048 = one pass by the thread-per-element kernels."""
 import numpy as np
 import pytest
 
@@ -19,7 +20,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("flags", [16, 4, 0, 16 + 4096, 16 + 1024, 16 + 2048])
+@pytest.mark.parametrize("flags", [16, 4, 0, 16 + 4096, 16 + 1024, 16 + 2048, 16 + 4096 + 32768])
 @pytest.mark.parametrize("name", ["2orb_nb2", "2orb_nb3", "3orb_nb2"])
 def test_fiber_hxv_matches_oracle_all_sectors(oracle, edb, name, flags):
     p, model, ctx, rng = make(oracle, edb, CASES[name], hxv_kernel=3, debug_flags=flags)
