@@ -168,7 +168,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    mv, P, sample, tavg = cpu_reference_sample(args.workload, seconds_target=args.cpu_seconds, steps=max(1, args.steps),
+    # every step is a bounded sample; the whole --steps K --warmup W run is sized to ~2.5 minutes of CPU work
+    nrun = max(1, args.steps) + min(args.warmup, 1)
+    mv, P, sample, tavg = cpu_reference_sample(args.workload, seconds_target=min(args.cpu_seconds, 150.0 / nrun), steps=max(1, args.steps),
                                                warmup=min(args.warmup, 1))
     Norb, Nbath, nup, ndw, desc = WORKLOADS[args.workload]
     line = {
