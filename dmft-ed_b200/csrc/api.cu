@@ -161,6 +161,7 @@ extern "C" int edgpu_finalize(edgpu_ctx *ctx)
     ctx->bases.clear();
     for (int b = 0; b < 2; b++) { cudaFree(ctx->d_stage[b]); if (ctx->copy_stream) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); } }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_gdw); cudaEventDestroy(ctx->ev_fdw); }
     for (auto &c : ctx->arena) cudaFree(c.first);
     ctx->arena.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

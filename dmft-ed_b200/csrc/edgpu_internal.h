@@ -135,6 +135,9 @@ struct edgpu_ctx {
     // call -- one allocation per ~16 vectors of the largest sector instead of one per Lanczos vector and sector
     std::vector<std::pair<void *, size_t>> arena;
     size_t arena_bytes = 0;
+    // side stream of hxv_fiber: the thread-per-element pair kernels (disjoint pairs) fill the tails of the fiber kernels
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_gdw = nullptr, ev_fdw = nullptr;
     double *d_flag = nullptr;               // edgpu_vec_upload: set by the conversion kernel when an imaginary part is not zero
     bool own_stream = false;                // edgpu_params.reserved[2] bit 0: the context created its (non-blocking) stream
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};

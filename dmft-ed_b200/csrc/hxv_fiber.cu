@@ -570,13 +570,54 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
     G.idx_of_cp = P.d_idx_of_cp; G.idx_of_rp = P.d_idx_of_rp; G.cp_start = P.d_cp_start; G.rp_start = P.d_rp_start;
     G.cfg_up = s->up->cfg; G.cfg_dw = s->dw->cfg; G.e_up = s->up->ediag; G.e_dw = s->dw->ediag; G.xtab = ctx->d_xtab;
     G.impmask = A.impmask; G.x = x; G.y = y;
-    // ---- first pass: y = H_dw x (strips of 4 columns; write-only) ----
     const size_t np = std::max<size_t>(1, P.pairs.size());
     const CUtensorMap *tm = nullptr, *tmy = nullptr;
     if (P.n2 + P.n2h + P.n1h > 0)
         if (int rc = fib_tensor_maps(s, x, &tm)) return rc;
     if (P.n1h > 0)
         if (int rc = fib_tensor_maps(s, y, &tmy)) return rc;
+    // dot partials: [fiber up][fiber up, half tiles][pair kernels]
+    const int g1 = P.n1 > 0 ? std::min(ctx->sm_count, P.n1) : 0, g1h = P.n1h > 0 ? std::min(ctx->sm_count, P.n1h) : 0;
+    // ---- thread-per-element pair kernels (blocks without a fiber kernel) on a side stream, so that they fill the tails of the
+    //      persistent fiber kernels.  A pair may take one pass from each family (fiber up block, small down block): the down
+    //      kernels of BOTH families precede the up kernels of both ----
+    cudaStream_t gs = ctx->stream;
+    const bool side = (P.ng1 + P.ng2 > 0) && (P.n1 + P.n2 + P.n1h + P.n2h > 0) && !(ctx->par.reserved[0] & 524288);
+    if (side) {
+        if (!ctx->aux_stream) {
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_gdw, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fdw, cudaEventDisableTiming));
+        }
+        gs = ctx->aux_stream;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(gs, ctx->ev_fork, 0));
+    }
+    auto generic_dw = [&]() {
+        if (P.ng2 <= 0) return;
+        G.list = P.d_g2; G.nlist = P.ng2; G.poshop = P.d_poshop_r; G.nhop = s->dw->nhop; G.amp = s->dw->amp; G.hop_ld = s->dw->dim; G.dot_out = nullptr;
+        const int64_t per = P.g2_elems / P.ng2 + 1;
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), (unsigned)std::min(P.ng2, 2048));
+        k_pair_dw<<<grid, 256, 0, gs>>>(G);
+    };
+    int ndg = 0;
+    auto generic_up = [&]() {
+        if (P.ng1 <= 0) return;
+        G.list = P.d_g1; G.nlist = P.ng1; G.poshop = P.d_poshop_c; G.nhop = s->up->nhop; G.amp = s->up->amp; G.hop_ld = s->up->dim;
+        const int64_t per = P.g1_elems / P.ng1 + 1;
+        const unsigned gy = (unsigned)std::min(P.ng1, 32);
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), gy);
+        G.dot_out = dot ? dot + g1 + g1h : nullptr;
+        k_pair_up<<<grid, 256, 0, gs>>>(G);
+        ndg = (int)(grid.x * grid.y);
+    };
+    if (side) {
+        generic_dw();
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_gdw, gs));
+    }
+    // ---- first pass: y = H_dw x (strips of 4 columns; write-only) ----
     A.cst = FD.cst; A.blk_f = FD.d_blocks; A.blk_o = FU.d_blocks; A.outer = FD.d_outer; A.amps = FD.d_amps;
     A.tmaps_y = nullptr; A.dot_out = nullptr;
     if (P.n2 > 0) {
@@ -587,37 +628,29 @@ int hxv_fiber(edgpu_sector *s, const double *x, double *y, double *dot, int *ndo
         A.tiles = P.d_t2h; A.ntiles = P.n2h; A.tmaps = tm + np;
         if (int rc = fib_launch_any(ctx, P.nl, 2, true, A, std::min(ctx->sm_count, P.n2h))) return rc;
     }
-    if (P.ng2 > 0) {
-        G.list = P.d_g2; G.nlist = P.ng2; G.poshop = P.d_poshop_r; G.nhop = s->dw->nhop; G.amp = s->dw->amp; G.hop_ld = s->dw->dim; G.dot_out = nullptr;
-        const int64_t per = P.g2_elems / P.ng2 + 1;
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), (unsigned)std::min(P.ng2, 2048));
-        k_pair_dw<<<grid, 256, 0, ctx->stream>>>(G);
+    if (!side) generic_dw();
+    else {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fdw, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(gs, ctx->ev_fdw, 0));
+        generic_up();
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, gs));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gdw, 0));
     }
     // ---- second pass: y += (diag + H_up) x (bands of 4 rows; read-modify-write, partial <x, y>) ----
     A.cst = FU.cst; A.blk_f = FU.d_blocks; A.blk_o = FD.d_blocks; A.outer = FU.d_outer; A.amps = FU.d_amps;
     if (P.n1 > 0) {
         A.tiles = P.d_t1; A.ntiles = P.n1; A.tmaps = nullptr; A.tmaps_y = nullptr;
-        const int grid = std::min(ctx->sm_count, P.n1);
-        A.dot_out = dot ? dot + nd : nullptr;
-        if (int rc = fib_launch_any(ctx, P.nl, 1, false, A, grid)) return rc;
-        if (dot) nd += grid;
+        A.dot_out = dot ? dot : nullptr;
+        if (int rc = fib_launch_any(ctx, P.nl, 1, false, A, g1)) return rc;
     }
     if (P.n1h > 0) {
         A.tiles = P.d_t1h; A.ntiles = P.n1h; A.tmaps = tm + 2 * np; A.tmaps_y = tmy + 2 * np;
-        const int grid = std::min(ctx->sm_count, P.n1h);
-        A.dot_out = dot ? dot + nd : nullptr;
-        if (int rc = fib_launch_any(ctx, P.nl, 1, true, A, grid)) return rc;
-        if (dot) nd += grid;
+        A.dot_out = dot ? dot + g1 : nullptr;
+        if (int rc = fib_launch_any(ctx, P.nl, 1, true, A, g1h)) return rc;
     }
-    if (P.ng1 > 0) {
-        G.list = P.d_g1; G.nlist = P.ng1; G.poshop = P.d_poshop_c; G.nhop = s->up->nhop; G.amp = s->up->amp; G.hop_ld = s->up->dim;
-        const int64_t per = P.g1_elems / P.ng1 + 1;
-        const unsigned gy = (unsigned)std::min(P.ng1, 32);
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 2, (per + 255) / 256)), gy);
-        G.dot_out = dot ? dot + nd : nullptr;
-        k_pair_up<<<grid, 256, 0, ctx->stream>>>(G);
-        if (dot) nd += (int)(grid.x * grid.y);
-    }
+    if (!side) generic_up();
+    else CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (dot) nd = g1 + g1h + ndg;
     CUDA_TRY(ctx, cudaGetLastError());
     if (nd > kDotSlots) return edgpu_fail(ctx, "fiber H*v: too many dot partials (%d)", nd);
     if (ndot) *ndot = nd;
