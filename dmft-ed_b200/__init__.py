@@ -65,7 +65,7 @@ ED_SYMBOLS = [
     "ed_get_g0imp_matsubara", "ed_get_g0imp_real", "ed_get_dens", "ed_get_dens_up", "ed_get_dens_dw", "ed_get_docc",
     "ed_get_mag", "ed_get_sz2_n2", "ed_get_grids", "ed_get_spinchi", "ed_get_denschi", "ed_get_state_count", "ed_get_state", "ed_get_state_vector",
     "ed_get_sector_energy", "ed_get_sector_nlanc", "ed_get_chain_count", "ed_get_chain", "ed_set_sectors_mask", "ed_get_timings",
-    "ed_host_eigh", "ed_host_eigh_tridiag",
+    "ed_host_eigh", "ed_host_eigvals", "ed_host_eigh_tridiag",
 ]
 
 
@@ -177,6 +177,7 @@ def lib():
     L.ed_set_sectors_mask.argtypes = [vp, i32p, C.c_int32]
     L.ed_get_timings.argtypes = [vp, dp]
     L.ed_host_eigh.argtypes = [C.c_int32, dp, dp]
+    L.ed_host_eigvals.argtypes = [C.c_int32, dp, dp]
     L.ed_host_eigh_tridiag.argtypes = [C.c_int32, dp, dp, dp, dp]
     _lib = L
     return L

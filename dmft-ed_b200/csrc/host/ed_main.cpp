@@ -248,9 +248,10 @@ extern "C" int ed_set_sectors_mask(ed_solver *s, const int32_t *pairs, int32_t n
 // ---------------------------------------------------------------------------------------------------------
 // dense symmetric eigensolver: Householder tridiagonalisation + tql2 (LAPACK eigh in the reference)
 // ---------------------------------------------------------------------------------------------------------
-static void tred2(int n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e)
+static void tred2(int n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e, bool vectors = true)
 {
     // a: row-major n x n symmetric; on return a holds the orthogonal transformation Q (a[k*n+i] = Q_ki)
+    // vectors = false: the reduction only (d, e of the tridiagonal matrix; a is left in its reduced form)
     auto A = [&](int i, int j) -> double & { return a[(size_t)i * n + j]; };
     for (int i = n - 1; i >= 1; i--) {
         const int l = i - 1;
@@ -286,6 +287,11 @@ static void tred2(int n, std::vector<double> &a, std::vector<double> &d, std::ve
     }
     d[0] = 0.0;
     e[0] = 0.0;
+    if (!vectors) {
+        // the diagonal is final after the reduction (the accumulation below touches A(k, j) with k, j < i only before it reads A(i, i))
+        for (int i = 0; i < n; i++) d[i] = A(i, i);
+        return;
+    }
     for (int i = 0; i < n; i++) {
         const int l = i - 1;
         if (d[i] != 0.0) {
@@ -315,6 +321,22 @@ extern "C" int ed_host_eigh(int32_t n, double *a_colmajor, double *w)
     if (ierr) return ierr;
     memcpy(w, d.data(), sizeof(double) * n);
     memcpy(a_colmajor, z.data(), sizeof(double) * (size_t)n * n);
+    return 0;
+}
+
+// eigenvalues only (same reduction and QL iteration as ed_host_eigh, without accumulating the transformations: ~4x cheaper);
+// the values are bit-identical to those of ed_host_eigh
+extern "C" int ed_host_eigvals(int32_t n, const double *a_colmajor, double *w)
+{
+    if (n < 1) return 1;
+    if (n == 1) { w[0] = a_colmajor[0]; return 0; }
+    std::vector<double> a((size_t)n * n), d(n), e(n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) a[(size_t)i * n + j] = 0.5 * (a_colmajor[i + (size_t)n * j] + a_colmajor[j + (size_t)n * i]);
+    tred2(n, a, d, e, false);
+    int ierr = host_tql2(n, d.data(), e.data(), nullptr);
+    if (ierr) return ierr;
+    memcpy(w, d.data(), sizeof(double) * n);
     return 0;
 }
 
@@ -419,7 +441,16 @@ static int diag_sectors(ed_solver *s, int worker, const std::vector<std::pair<in
                 std::vector<double> w(dim);
                 rc = edgpu_sector_dense(sec, H.data());                                                   // :188-193
                 if (rc) { bad("ed_diag"); edgpu_sector_free(sec); return 1; }
-                if (ed_host_eigh((int)dim, H.data(), w.data())) { L.err = "ed_diag: dense eigh failed"; edgpu_sector_free(sec); return 1; }
+                // Most LAPACK sectors cannot hold a ground state: their eigenVALUES decide that (a state is kept only if it lies
+                // within gs_threshold of the running minimum or below it, :224-235), the vectors are computed only then.
+                bool vectors = true;
+                if (dim >= 16) {
+                    if (ed_host_eigvals((int)dim, H.data(), w.data())) { L.err = "ed_diag: dense eigh failed"; edgpu_sector_free(sec); return 1; }
+                    vectors = w[0] <= oldzero + in.gs_threshold;
+                }
+                if (vectors) {
+                    if (ed_host_eigh((int)dim, H.data(), w.data())) { L.err = "ed_diag: dense eigh failed"; edgpu_sector_free(sec); return 1; }
+                } else H.clear();
                 for (int64_t i = 0; i < neigen; i++) { evals.push_back(w[i]); evecs.push_back(nullptr); }   // uploaded on demand
             }
             L.sector_e[{nup, ndw}] = evals.empty() ? 0.0 : evals[0];

@@ -127,6 +127,8 @@ int ed_get_timings(const ed_solver *s, double *t4);
 /* host linear algebra used by the mirror (LAPACK eigh in the reference: ED_DIAG.f90:194, ED_GF_NORMAL.f90:618);
  * exported for CPU-side tests.  a: n x n column-major symmetric, overwritten by eigenvectors; w: eigenvalues. */
 int ed_host_eigh(int32_t n, double *a, double *w);
+/* eigenvalues only (a is not modified): the pre-pass of the LAPACK sectors, whose vectors are computed only when a state can be kept */
+int ed_host_eigvals(int32_t n, const double *a, double *w);
 int ed_host_eigh_tridiag(int32_t n, const double *diag, const double *sub /* sub[1..n-1] */, double *w, double *z);
 
 #ifdef __cplusplus

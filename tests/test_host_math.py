@@ -14,6 +14,11 @@ def test_dense_eigh(edb, n):
     assert np.allclose(w, np.linalg.eigvalsh(A), atol=1e-11, rtol=0)
     assert np.abs(A @ a - a * w).max() < 1e-11
     assert np.abs(a.T @ a - np.eye(n)).max() < 1e-12
+    # the eigenvalue-only pre-pass of the LAPACK sectors: the same reduction and QL sweeps, no accumulation -> the same bits
+    a2 = np.asfortranarray(A.copy())
+    w2 = np.zeros(n)
+    assert edb.lib().ed_host_eigvals(n, a2.ctypes.data_as(edb.dp), w2.ctypes.data_as(edb.dp)) == 0
+    assert np.array_equal(a2, A) and np.array_equal(w2, w)
 
 
 @pytest.mark.parametrize("n", [1, 2, 50, 200])
