@@ -96,6 +96,16 @@ MODULE ED_GPU_BINDING
        integer(c_int32_t),intent(out)  :: nlanc
        type(c_ptr),value               :: alanc,blanc          ! c_null_ptr: not wanted
      end function edgpu_lanczos_gs
+     integer(c_int) function edgpu_lanczos_eigs(s,neigen,ncv,maxrestart,tol,seed,evals,vecs,nconv,nmatvec) bind(C,name="edgpu_lanczos_eigs")
+       import :: c_int,c_int32_t,c_int64_t,c_double,c_ptr
+       type(c_ptr),value         :: s
+       integer(c_int32_t),value  :: neigen,ncv,maxrestart
+       real(c_double),value      :: tol
+       integer(c_int64_t),value  :: seed
+       real(c_double)            :: evals(*)
+       type(c_ptr)               :: vecs(*)
+       integer(c_int32_t)        :: nconv,nmatvec
+     end function edgpu_lanczos_eigs
      integer(c_int) function edgpu_lanczos_tridiag(s,v,nlanc,threshold,alfa,beta,nused) bind(C,name="edgpu_lanczos_tridiag")
        import :: c_int,c_ptr,c_int32_t,c_double
        type(c_ptr),value              :: s,v
@@ -159,6 +169,7 @@ MODULE ED_GPU_BINDING
 
   public :: gpu_ctx
   public :: gpu_init, gpu_finalize, gpu_set_hamiltonian, gpu_check
+  public :: gpu_lanc_eigs
   public :: gpu_lanc_eigh, gpu_lanc_gf_chain, gpu_lanc_spinchi_chain, gpu_lanc_denschi_chain, gpu_observables
   public :: gpu_comm_init, gpu_shard_lanc_tridiag
   public :: edgpu_sector_build, edgpu_sector_free, edgpu_vec_free, edgpu_hxv
@@ -222,6 +233,23 @@ contains
     ! delete_Hv_sector (ED_DIAG.f90:186): the stored matrix goes, the sector handle stays in the state list
     if(sparse_H)call gpu_check(edgpu_sector_drop_csr(sec),"delete_Hv_sector")
   end subroutine gpu_lanc_eigh
+
+  !> replaces the sp_eigh (ARPACK) branch of ed_diag_c (ED_DIAG.f90:149-166): Neigen lowest pairs of sector (nup,ndw) from a
+  !> basis of Nblock vectors.  eig_values(1:Neigen) ascending; vecs(1:Neigen) are device handles (the state list keeps them;
+  !> edgpu_vec_download(vecs(i),cvec,1) gives the complex(8) copy in the reference order).
+  subroutine gpu_lanc_eigs(nup,ndw,sparse_H,Neigen,Nblock,Nitermax,tol,eig_values,sec,vecs)
+    integer,intent(in)      :: nup,ndw,Neigen,Nblock,Nitermax
+    logical,intent(in)      :: sparse_H
+    real(8),intent(in)      :: tol
+    real(8),intent(out)     :: eig_values(Neigen)
+    type(c_ptr),intent(out) :: sec,vecs(Neigen)
+    integer(c_int32_t)      :: nconv,nmatvec
+    call gpu_check(edgpu_sector_build(gpu_ctx,int(nup,c_int32_t),int(ndw,c_int32_t),sec),"build_Hv_sector")
+    if(sparse_H)call gpu_check(edgpu_sector_build_csr(sec),"ed_buildH_c")
+    call gpu_check(edgpu_lanczos_eigs(sec,int(Neigen,c_int32_t),int(Nblock,c_int32_t),int(max(1,Nitermax),c_int32_t),tol,&
+         1234567_c_int64_t,eig_values,vecs,nconv,nmatvec),"sp_eigh")
+    if(sparse_H)call gpu_check(edgpu_sector_drop_csr(sec),"delete_Hv_sector")
+  end subroutine gpu_lanc_eigs
 
   !> replaces one half of lanc_build_gf_normal_c (ED_GF_NORMAL.f90:150-200 for cdg, :203-253 for c):
   !> seed = c^+_isite|gs> or c_isite|gs>, normalise, tridiagonalise in the target sector (jup,jdw).
